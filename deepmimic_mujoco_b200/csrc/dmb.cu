@@ -1,0 +1,727 @@
+// dmb.cu -- kernels + C-ABI of libdmb200.so (see include/dmb.h).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+//
+// Kernel design (DESIGN.md has the full account):
+//   * one warp per env, W envs per CTA, persistent grid (<= #SMs CTAs, each warp strides
+//     over envs);
+//   * the fp32 model tables are staged once per CTA in shared memory; each warp owns an
+//     EnvS tile (qpos/qvel, kinematic tree, sparse inertia factor, contact list, the
+//     half-solved constraint Jacobian Y and the packed Delassus matrix AR) -- per-env state
+//     crosses HBM exactly once per step in each direction (coalesced env-major rows);
+//   * the whole RK4 step (4 forward evaluations incl. collision and PGS), mocap lookup,
+//     reward, termination and auto-reset are fused in this one kernel.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "dmb_device.cuh"
+
+namespace dmb {
+
+struct DevPtrs {
+  const ModelS* model;
+  const float* mocap_cfg;  // [F][nq]
+  const float* mocap_vel;  // [F][nv]
+  const float* ref_aux;    // [F][DMB_REF_AUX]
+};
+
+// ---------------------------------------------------------------------------------------
+// state I/O helpers (lane-coalesced env-major rows)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_state(const ModelS& M, EnvS& S, const dmb_state_t& st, int env, int lane) {
+  for (int i = lane; i < M.nq; i += 32) S.qpos[i] = st.qpos[(size_t)env * DMB_QSTRIDE + i];
+  for (int i = lane; i < M.nv; i += 32) {
+    S.qvel[i] = st.qvel[(size_t)env * DMB_VSTRIDE + i];
+    S.warm[i] = st.warm[(size_t)env * DMB_VSTRIDE + i];
+  }
+  if (lane == 0) S.flags = 0;
+  __syncwarp();
+}
+__device__ __forceinline__ void store_state(const ModelS& M, EnvS& S, const dmb_state_t& st, int env, int lane) {
+  for (int i = lane; i < DMB_QSTRIDE; i += 32) st.qpos[(size_t)env * DMB_QSTRIDE + i] = i < M.nq ? S.qpos[i] : 0.f;
+  for (int i = lane; i < DMB_VSTRIDE; i += 32) {
+    st.qvel[(size_t)env * DMB_VSTRIDE + i] = i < M.nv ? S.qvel[i] : 0.f;
+    st.warm[(size_t)env * DMB_VSTRIDE + i] = i < M.nv ? S.warm[i] : 0.f;
+  }
+}
+// obs = qpos[7:] || qvel[6:]   (dp_env_v3.py:62-65)
+__device__ __forceinline__ void write_obs(const ModelS& M, const EnvS& S, float* obs, float* rec, int env, int lane) {
+  const int np = M.nq - 7, nvv = M.nv - 6, od = np + nvv;
+  for (int o = lane; o < od; o += 32) {
+    const float v = o < np ? S.qpos[7 + o] : S.qvel[6 + o - np];
+    if (obs) obs[(size_t)env * od + o] = v;
+    if (rec) rec[(size_t)env * (od + 2) + o] = v;
+  }
+}
+
+// action -> per-dof actuator force (mj_fwdActuation with the ctrl clamp; optional PD)
+__device__ __forceinline__ void set_ctrl(const ModelS& M, EnvS& S, const float* action, int env, int lane) {
+  for (int d = lane; d < M.nv; d += 32) S.ctrlf[d] = 0.f;
+  __syncwarp();
+  if (lane < M.nu) {
+    const int d = M.act_dofadr[lane];
+    float a = action[(size_t)env * M.nu + lane];
+    if (M.ctrl_mode != 0) {
+      // PD on the joint angle: action = target angle.  mode 1 restates the intent of
+      // MujocoInterface.action2torque (mujoco_interface.py:97-107): v_target = p_err/dt;
+      // mode 2 is the plain PD  kp (a - q) - kd qvel.  Torque is mapped back to ctrl by the gear.
+      const int j = lane;  // actuator u drives hinge joint with qpos index 7+u in this model family
+      (void)j;
+      const float q = S.qpos[d + 1];  // hinge dof d <-> qpos d+1 (free joint: 7 qpos, 6 dofs)
+      const float perr = a - q;
+      float tau;
+      if (M.ctrl_mode == 1) tau = M.dof_kp[d] * perr + M.dof_kd[d] * (perr / M.pd_dt - S.qvel[d]);
+      else tau = M.dof_kp[d] * perr - M.dof_kd[d] * S.qvel[d];
+      a = tau / M.dof_gear[d];
+    }
+    if (!(a == a)) a = 0.f;
+    a = fminf(fmaxf(a, M.dof_ctrl_lo[d]), M.dof_ctrl_hi[d]);
+    S.ctrlf[d] = M.dof_gear[d] * a;
+  }
+  __syncwarp();
+}
+
+// mj_integratePos from X0 with velocity S.x_dv and step h into S.qpos (lane = joint)
+__device__ __forceinline__ void integrate_pos(const ModelS& M, EnvS& S, int lane, float h) {
+  if (lane < M.njnt) {
+    const int qa = M.jnt_qposadr[lane], da = M.jnt_dofadr[lane];
+    if (M.jnt_type[lane] == DMB_JNT_FREE) {
+      S.qpos[qa] = S.x_q0[qa] + h * S.x_dv[da];
+      S.qpos[qa + 1] = S.x_q0[qa + 1] + h * S.x_dv[da + 1];
+      S.qpos[qa + 2] = S.x_q0[qa + 2] + h * S.x_dv[da + 2];
+      V3 ax = v3(S.x_dv[da + 3], S.x_dv[da + 4], S.x_dv[da + 5]);
+      const float ang = h * normalize(ax);
+      float sn, cs;
+      sincosf(0.5f * ang, &sn, &cs);
+      Q4 qr; qr.w = cs; qr.x = sn * ax.x; qr.y = sn * ax.y; qr.z = sn * ax.z;
+      Q4 q0; q0.w = S.x_q0[qa + 3]; q0.x = S.x_q0[qa + 4]; q0.y = S.x_q0[qa + 5]; q0.z = S.x_q0[qa + 6];
+      Q4 qn = qnormalize(qmul(qnormalize(q0), qr));
+      S.qpos[qa + 3] = qn.w; S.qpos[qa + 4] = qn.x; S.qpos[qa + 5] = qn.y; S.qpos[qa + 6] = qn.z;
+    } else {
+      S.qpos[qa] = S.x_q0[qa] + h * S.x_dv[da];
+    }
+  }
+}
+
+// mj_step with RK4 (mj_RungeKutta N=4).  Returns the CoM height of the last stage evaluation.
+__device__ float rk4_step(const ModelS& M, EnvS& S, int lane) {
+  const float h = M.timestep;
+  for (int i = lane; i < M.nq; i += 32) S.x_q0[i] = S.qpos[i];
+  for (int i = lane; i < M.nv; i += 32) S.x_v0[i] = S.qvel[i];
+  __syncwarp();
+  float zc = forward_eval(M, S, lane, nullptr);
+  const float Bw[4] = {1.f / 6.f, 1.f / 3.f, 1.f / 3.f, 1.f / 6.f};
+  const float Ac[3] = {0.5f, 0.5f, 1.f};
+  for (int i = lane; i < M.nv; i += 32) { S.x_sv[i] = Bw[0] * S.qvel[i]; S.x_sa[i] = Bw[0] * S.qacc[i]; }
+  __syncwarp();
+  for (int st = 1; st < 4; st++) {
+    const float a = Ac[st - 1];
+    // X[st] = X0 (+) h * a * (V[st-1], F[st-1])
+    for (int i = lane; i < M.nv; i += 32) {
+      S.x_dv[i] = a * S.qvel[i];
+      S.qvel[i] = S.x_v0[i] + h * (a * S.qacc[i]);
+    }
+    __syncwarp();
+    integrate_pos(M, S, lane, h);
+    __syncwarp();
+    zc = forward_eval(M, S, lane, nullptr);
+    for (int i = lane; i < M.nv; i += 32) { S.x_sv[i] += Bw[st] * S.qvel[i]; S.x_sa[i] += Bw[st] * S.qacc[i]; }
+    __syncwarp();
+  }
+  for (int i = lane; i < M.nv; i += 32) { S.x_dv[i] = S.x_sv[i]; S.qvel[i] = S.x_v0[i] + h * S.x_sa[i]; }
+  __syncwarp();
+  integrate_pos(M, S, lane, h);
+  __syncwarp();
+  return zc;
+}
+
+// reference-state initialisation (dp_env_v3.py:67-71,148-164); Philox keyed by (seed, env id)
+__device__ void reset_env(const ModelS& M, EnvS& S, const DevPtrs& P, const dmb_state_t& st, int env, int lane,
+                          unsigned long long seed, unsigned first_env_id, int mode) {
+  const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+  const unsigned eid = first_env_id + (unsigned)env;
+  const unsigned rc = st.reset_count[env];
+  const int clip = st.clip[env];
+  const int len = M.clip_len[clip], start = M.clip_start[clip];
+  unsigned r[4];
+  philox4x32(k0, k1, eid, rc, 0u, 0u, r);
+  int idx = (int)(u01(r[0]) * (float)len);
+  if (idx >= len) idx = len - 1;
+  if (mode == 0) {
+    for (int i = lane; i < M.nq; i += 32) S.qpos[i] = P.mocap_cfg[(size_t)(start + idx) * M.nq + i];
+    for (int i = lane; i < M.nv; i += 32) S.qvel[i] = P.mocap_vel[(size_t)(start + idx) * M.nv + i];
+  } else {
+    for (int i = lane; i < M.nq + M.nv; i += 32) {
+      philox4x32(k0, k1, eid, rc, 1u + (unsigned)(i >> 2), 0u, r);
+      const float nz = M.reset_noise * (2.f * u01(r[i & 3]) - 1.f);
+      if (i < M.nq) S.qpos[i] = M.qpos0[i] + nz; else S.qvel[i - M.nq] = nz;
+    }
+  }
+  for (int i = lane; i < M.nv; i += 32) S.warm[i] = 0.f;
+  if (lane == 0) {
+    st.idx_init[env] = idx; st.idx_curr[env] = idx; st.reset_count[env] = rc + 1u;
+    st.ep_len[env] = 0; st.ep_ret[env] = 0.f;
+  }
+  __syncwarp();
+}
+
+// quaternion of a hinge triple, R = Rx(a) Ry(b) Rz(c)
+__device__ __forceinline__ Q4 quat_from_xyz(float a, float b, float c) {
+  float sa, ca, sb, cb, sc, cc;
+  sincosf(0.5f * a, &sa, &ca); sincosf(0.5f * b, &sb, &cb); sincosf(0.5f * c, &sc, &cc);
+  Q4 qx; qx.w = ca; qx.x = sa; qx.y = 0.f; qx.z = 0.f;
+  Q4 qy; qy.w = cb; qy.x = 0.f; qy.y = sb; qy.z = 0.f;
+  Q4 qz; qz.w = cc; qz.x = 0.f; qz.y = 0.f; qz.z = sc;
+  return qmul(qmul(qx, qy), qz);
+}
+__device__ __forceinline__ float quat_diff_theta(Q4 a, Q4 b) {
+  Q4 ac; ac.w = a.w; ac.x = -a.x; ac.y = -a.y; ac.z = -a.z;
+  const Q4 qd = qmul(ac, b);
+  return 2.f * atan2f(sqrtf(qd.x * qd.x + qd.y * qd.y + qd.z * qd.z), fabsf(qd.w));
+}
+
+// 5-term DeepMimic imitation reward (code.md:979-1146 adapted to the hinge model; weights and
+// scales from dp_env_v3.py:42-53).  Needs fresh kinematics at the post-step state; the
+// reference pose's end-effector / CoM-velocity features are tabulated per frame (ref_aux).
+__device__ float reward_imitate(const ModelS& M, EnvS& S, const DevPtrs& P, int lane, int frame) {
+  const float* rq = P.mocap_cfg + (size_t)frame * M.nq;
+  const float* rv = P.mocap_vel + (size_t)frame * M.nv;
+  const float* aux = P.ref_aux + (size_t)frame * DMB_REF_AUX;
+  kinematics(M, S, lane);
+  com_pos(M, S, lane);
+  for (int d = lane; d < M.nv; d += 32) {
+    const float qv = S.qvel[d];
+#pragma unroll
+    for (int k = 0; k < 6; k++) S.buf6[6 * d + k] = S.cdof[6 * d + k] * qv;
+  }
+  __syncwarp();
+  // CoM velocity: sum_b m_b (v_lin + w x (xipos_b - com)) / M
+  float px = 0.f, py = 0.f, pz = 0.f;
+  if (lane >= 1 && lane < M.nbody) {
+    const int b = lane;
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    unsigned long long mk = M.body_dofmask[b];
+    while (mk) {
+      const int d = __ffsll((long long)mk) - 1;
+      mk &= mk - 1;
+#pragma unroll
+      for (int k = 0; k < 6; k++) v[k] += S.buf6[6 * d + k];
+    }
+    const V3 r = ld3(&S.xipos[3 * b]) - ld3(S.com);
+    const V3 vb = v3(v[3], v[4], v[5]) + cross(v3(v[0], v[1], v[2]), r);
+    const float ms = M.body_mass[b];
+    px = ms * vb.x; py = ms * vb.y; pz = ms * vb.z;
+  }
+  const float vcx = warp_sum(px) * M.inv_total_mass, vcy = warp_sum(py) * M.inv_total_mass,
+              vcz = warp_sum(pz) * M.inv_total_mass;
+  // end effectors in the root heading frame (lane = end effector)
+  float ee = 0.f;
+  if (lane < M.nee) {
+    const float* R = &S.xmat[9];
+    const float heading = atan2f(R[3], R[0]);
+    float sh, ch;
+    sincosf(heading, &sh, &ch);
+    const int b = M.ee_body[lane];
+    const V3 w = ld3(&S.xpos[3 * b]) + mat_vec(&S.xmat[9 * b], ld3(M.ee_pos[lane]));
+    const float rx = w.x - S.xpos[3], ry = w.y - S.xpos[4];
+    const float e0 = ch * rx + sh * ry - aux[3 * lane], e1 = -sh * rx + ch * ry - aux[3 * lane + 1],
+                e2 = w.z - aux[3 * lane + 2];
+    ee = e0 * e0 + e1 * e1 + e2 * e2;
+  }
+  ee = warp_sum(ee);
+  if (M.nee > 0) ee /= (float)M.nee;
+  // pose error: lane = body (root quaternion on lane 1, hinge triples / single hinges on lanes >= 2)
+  float pe = 0.f, th_root = 0.f;
+  if (lane == 1) {
+    Q4 q0; q0.w = S.qpos[3]; q0.x = S.qpos[4]; q0.y = S.qpos[5]; q0.z = S.qpos[6];
+    Q4 q1; q1.w = rq[3]; q1.x = rq[4]; q1.y = rq[5]; q1.z = rq[6];
+    th_root = quat_diff_theta(qnormalize(q0), qnormalize(q1));
+    pe = M.dof_weight[3] * th_root * th_root;
+  } else if (lane >= 2 && lane < M.nbody) {
+    const int da = M.body_dofadr[lane], nd = M.body_dofnum[lane];
+    if (nd == 3) {
+      const float th = quat_diff_theta(quat_from_xyz(S.qpos[da + 1], S.qpos[da + 2], S.qpos[da + 3]),
+                                       quat_from_xyz(rq[da + 1], rq[da + 2], rq[da + 3]));
+      pe = M.dof_weight[da] * th * th;
+    } else if (nd == 1) {
+      const float dq = S.qpos[da + 1] - rq[da + 1];
+      pe = M.dof_weight[da] * dq * dq;
+    }
+  }
+  th_root = __shfl_sync(DMB_FULL, th_root, 1);
+  const float pose_err = warp_sum(pe);
+  float ve = 0.f;
+  for (int d = lane; d < M.nv; d += 32) if (d >= 3) { const float dv = S.qvel[d] - rv[d]; ve += M.dof_weight[d] * dv * dv; }
+  const float vel_err = warp_sum(ve);
+  float rp = 0.f, rvv = 0.f, rw = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float a = S.qpos[i] - rq[i], b = S.qvel[i] - rv[i], c = S.qvel[3 + i] - rv[3 + i];
+    rp += a * a; rvv += b * b; rw += c * c;
+  }
+  const float root_err = rp + 0.1f * th_root * th_root + 0.01f * rvv + 0.001f * rw;
+  const float cx = aux[12] - vcx, cy = aux[13] - vcy, cz = aux[14] - vcz;
+  const float com_err = 0.1f * (cx * cx + cy * cy + cz * cz);
+  return M.w_pose * expf(-M.s_err * M.s_pose * pose_err) + M.w_vel * expf(-M.s_err * M.s_vel * vel_err) +
+         M.w_ee * expf(-M.s_err * M.s_ee * ee) + M.w_root * expf(-M.s_err * M.s_root * root_err) +
+         M.w_com * expf(-M.s_err * M.s_com * com_err);
+}
+
+__device__ __forceinline__ bool state_bad(const ModelS& M, const EnvS& S, int lane) {
+  bool bad = false;
+  for (int i = lane; i < M.nq; i += 32) bad |= !(fabsf(S.qpos[i]) < 1e10f);
+  for (int i = lane; i < M.nv; i += 32) bad |= !(fabsf(S.qvel[i]) < 1e10f);
+  return __any_sync(DMB_FULL, bad);
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void stage_model(ModelS* dst, const ModelS* src) {
+  const int n = (int)(sizeof(ModelS) / 4);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) ((int*)dst)[i] = ((const int*)src)[i];
+  __syncthreads();
+}
+
+constexpr size_t MODEL_BYTES = (sizeof(ModelS) + 15) & ~(size_t)15;
+
+__global__ void k_step(DevPtrs P, dmb_state_t st, const float* __restrict__ action, dmb_step_out_t out, int N,
+                       unsigned long long seed, unsigned first_env_id) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ModelS& M = *reinterpret_cast<ModelS*>(smem);
+  EnvS* tiles = reinterpret_cast<EnvS*>(smem + MODEL_BYTES);
+  stage_model(&M, P.model);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  EnvS& S = tiles[warp];
+  const int od = (M.nq - 7) + (M.nv - 6);
+  for (int env = blockIdx.x * W + warp; env < N; env += gridDim.x * W) {
+    load_state(M, S, st, env, lane);
+    bool bad = state_bad(M, S, lane);
+    float zc = 0.f;
+    if (!bad) {
+      set_ctrl(M, S, action, env, lane);
+      zc = rk4_step(M, S, lane);
+      bad = state_bad(M, S, lane);
+    }
+    // reward (dp_env_v3.py:117 / 89-104)
+    float rew = 1.0f;
+    int idx_curr = st.idx_curr[env];
+    const int clip = st.clip[env];
+    if (M.reward_mode == 1) {
+      const int len = M.clip_len[clip], start = M.clip_start[clip];
+      float e = 0.f;
+      for (int j = lane; j < M.nq - 7; j += 32)
+        e += fabsf(S.qpos[7 + j] - P.mocap_cfg[(size_t)(start + idx_curr) * M.nq + 7 + j]);
+      e = warp_sum(e);
+      rew = expf(-e);
+      idx_curr = (idx_curr + 1) % len;
+    } else if (M.reward_mode == 4) {
+      if (!bad) rew = reward_imitate(M, S, P, lane, M.clip_start[clip] + idx_curr);
+      idx_curr = (idx_curr + 1) % M.clip_len[clip];
+    }
+    if (bad) rew = 0.f;
+    // termination (dp_env_v3.py:134-139) on the CoM height of the last stage evaluation
+    const bool done = bad || zc < M.z_min || zc > M.z_max;
+    const int flags = S.flags | (bad ? 4 : 0);
+    int ep_len = st.ep_len[env] + 1;
+    float ep_ret = st.ep_ret[env] + rew;
+    if (lane == 0) {
+      out.reward[env] = rew;
+      out.done[env] = done ? 1 : 0;
+      if (out.rec) { out.rec[(size_t)env * (od + 2) + od] = rew; out.rec[(size_t)env * (od + 2) + od + 1] = done ? 1.f : 0.f; }
+      if (out.last_ret) out.last_ret[env] = ep_ret;
+      if (out.last_len) out.last_len[env] = ep_len;
+      st.flags[env] = flags;
+      st.idx_curr[env] = idx_curr;
+      st.ep_len[env] = ep_len;
+      st.ep_ret[env] = ep_ret;
+    }
+    __syncwarp();
+    if (done && M.auto_reset) reset_env(M, S, P, st, env, lane, seed, first_env_id, M.reset_mode);
+    else if (bad) {  // keep a finite state in HBM
+      for (int i = lane; i < M.nq; i += 32) S.qpos[i] = M.qpos0[i];
+      for (int i = lane; i < M.nv; i += 32) { S.qvel[i] = 0.f; S.warm[i] = 0.f; }
+      __syncwarp();
+    }
+    write_obs(M, S, out.obs, out.rec, env, lane);
+    store_state(M, S, st, env, lane);
+    __syncwarp();
+  }
+}
+
+__global__ void k_reset(DevPtrs P, dmb_state_t st, const unsigned char* __restrict__ mask, int mode, float* obs, int N,
+                        unsigned long long seed, unsigned first_env_id) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ModelS& M = *reinterpret_cast<ModelS*>(smem);
+  EnvS* tiles = reinterpret_cast<EnvS*>(smem + MODEL_BYTES);
+  stage_model(&M, P.model);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  EnvS& S = tiles[warp];
+  for (int env = blockIdx.x * W + warp; env < N; env += gridDim.x * W) {
+    if (mask && !mask[env]) continue;
+    reset_env(M, S, P, st, env, lane, seed, first_env_id, mode < 0 ? M.reset_mode : mode);
+    if (lane == 0) st.flags[env] = 0;
+    write_obs(M, S, obs, nullptr, env, lane);
+    store_state(M, S, st, env, lane);
+    __syncwarp();
+  }
+}
+
+__global__ void k_obs(DevPtrs P, dmb_state_t st, float* obs, int N) {
+  const int nq = P.model->nq, nv = P.model->nv;
+  const int np = nq - 7, od = np + nv - 6;
+  const size_t total = (size_t)N * od;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t env = i / od;
+    const int o = (int)(i % od);
+    obs[i] = o < np ? st.qpos[env * DMB_QSTRIDE + 7 + o] : st.qvel[env * DMB_VSTRIDE + 6 + o - np];
+  }
+}
+
+__global__ void k_forward_debug(DevPtrs P, dmb_state_t st, const float* __restrict__ ctrl, float* dbgout, int N) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ModelS& M = *reinterpret_cast<ModelS*>(smem);
+  EnvS* tiles = reinterpret_cast<EnvS*>(smem + MODEL_BYTES);
+  stage_model(&M, P.model);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  EnvS& S = tiles[warp];
+  for (int env = blockIdx.x * W + warp; env < N; env += gridDim.x * W) {
+    load_state(M, S, st, env, lane);
+    // ctrl is given directly (no PD) in the debug path
+    for (int d = lane; d < M.nv; d += 32) S.ctrlf[d] = 0.f;
+    __syncwarp();
+    if (lane < M.nu) {
+      const int d = M.act_dofadr[lane];
+      float a = ctrl[(size_t)env * M.nu + lane];
+      a = fminf(fmaxf(a, M.dof_ctrl_lo[d]), M.dof_ctrl_hi[d]);
+      S.ctrlf[d] = M.dof_gear[d] * a;
+    }
+    __syncwarp();
+    float* row = dbgout + (size_t)env * dbg::stride;
+    for (int i = lane; i < dbg::stride; i += 32) row[i] = 0.f;
+    __syncwarp();
+    const float zc = forward_eval(M, S, lane, row);
+    for (int i = lane; i < M.nbody * 3; i += 32) { row[dbg::xpos + i] = S.xpos[i]; row[dbg::xipos + i] = S.xipos[i]; }
+    for (int i = lane; i < M.nbody * 4; i += 32) row[dbg::xquat + i] = S.xquat[i];
+    for (int i = lane; i < M.nbody * 6; i += 32) row[dbg::cvel + i] = S.cvel[i];
+    for (int i = lane; i < M.nv; i += 32) row[dbg::qacc + i] = S.qacc[i];
+    for (int r = lane; r < S.nefc; r += 32) row[dbg::efc_force + r] = S.e_f[r];
+    for (int c = lane; c < S.ncon; c += 32) {
+      float* cr = row + dbg::contact + 16 * c;
+      cr[0] = S.c_dist[c];
+      for (int k = 0; k < 3; k++) cr[1 + k] = S.c_pos[3 * c + k];
+      for (int k = 0; k < 9; k++) cr[4 + k] = S.c_frame[9 * c + k];
+      cr[13] = (float)S.c_g1[c]; cr[14] = (float)S.c_g2[c]; cr[15] = (float)S.c_dim[c];
+    }
+    if (lane == 0) {
+      row[dbg::com] = S.com[0]; row[dbg::com + 1] = S.com[1]; row[dbg::com + 2] = S.com[2];
+      row[dbg::ncon] = (float)S.ncon; row[dbg::nefc] = (float)S.nefc; row[dbg::iter] = (float)S.iter;
+      row[dbg::z_com] = zc;
+      st.flags[env] = S.flags;
+    }
+    // mj_forward leaves qacc_warmstart = qacc
+    for (int i = lane; i < DMB_VSTRIDE; i += 32) st.warm[(size_t)env * DMB_VSTRIDE + i] = i < M.nv ? S.warm[i] : 0.f;
+    __syncwarp();
+  }
+}
+
+}  // namespace dmb
+
+// =========================================================================================
+// host side
+// =========================================================================================
+using namespace dmb;
+
+struct dmb_handle_s {
+  int device = 0;
+  int num_envs = 0;
+  unsigned long long seed = 0;
+  unsigned first_env_id = 0;
+  ModelS hmodel;
+  ModelS* dmodel = nullptr;
+  float *d_cfg = nullptr, *d_vel = nullptr, *d_aux = nullptr;
+  int grid = 0, block = 0, smem = 0, envs_per_cta = 0;
+  int nu = 0, obs_dim = 0;
+  std::string err;
+};
+
+static std::string g_err;
+
+static int fail(dmb_handle_t h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_err = msg;
+  return code;
+}
+#define CUDA_TRY(h, expr)                                                                          \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return fail(h, DMB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mocap_t* mc, ModelS& S, std::string& why) {
+  memset(&S, 0, sizeof(S));
+  if (m->nv > NVC || m->nq > NQC || m->nbody > NB || m->njnt > NJ || m->ngeom > NG || m->npair > NP || m->nu > NU ||
+      m->nM > NMX || m->nv > 64) { why = "model exceeds kernel capacities"; return DMB_ERR_MODEL; }
+  if (m->max_efc > MAXROW - 1 || m->max_con > MAXC || m->max_con > 32 || m->max_efc < m->njnt) {
+    why = "max_efc must be <= 63 and >= njnt, max_con <= 24"; return DMB_ERR_MODEL;
+  }
+  S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.nbody = m->nbody; S.njnt = m->njnt; S.ngeom = m->ngeom;
+  S.npair = m->npair; S.nM = m->nM; S.iterations = m->iterations; S.max_con = m->max_con; S.max_efc = m->max_efc;
+  S.timestep = (float)m->timestep; S.tolerance = (float)m->tolerance; S.margin = (float)m->margin;
+  S.pgs_scale = (float)(1.0 / (m->meaninertia * (m->nv > 1 ? m->nv : 1)));
+  for (int k = 0; k < 3; k++) S.gravity[k] = (float)m->gravity[k];
+  for (int k = 0; k < 5; k++) S.solimp[k] = (float)m->solimp[k];
+  {  // mj_makeImpedance spring constants (refsafe)
+    double tc = m->solref[0], dr = m->solref[1];
+    if (tc < 2 * m->timestep) tc = 2 * m->timestep;
+    double dmax = m->solimp[1]; dmax = dmax < 1e-4 ? 1e-4 : (dmax > 0.9999 ? 0.9999 : dmax);
+    double kk = dmax * dmax * tc * tc * dr * dr, bb = dmax * tc;
+    S.imp_k = (float)(1.0 / (kk > 1e-15 ? kk : 1e-15));
+    S.imp_b = (float)(2.0 / (bb > 1e-15 ? bb : 1e-15));
+  }
+  double mass = 0;
+  int maxdepth = 0;
+  for (int b = 0; b < m->nbody; b++) {
+    S.body_parent[b] = (int8_t)m->body_parent[b]; S.body_depth[b] = (int8_t)m->body_depth[b];
+    S.body_jntadr[b] = (int8_t)m->body_jntadr[b]; S.body_jntnum[b] = (int8_t)m->body_jntnum[b];
+    S.body_dofadr[b] = (int8_t)m->body_dofadr[b]; S.body_dofnum[b] = (int8_t)m->body_dofnum[b];
+    if (m->body_jntnum[b] > JPB) { why = "more than 3 joints on a body"; return DMB_ERR_MODEL; }
+    for (int k = 0; k < 3; k++) { S.body_pos[b][k] = (float)m->body_pos[b][k]; S.body_ipos[b][k] = (float)m->body_ipos[b][k]; }
+    for (int k = 0; k < 4; k++) S.body_quat[b][k] = (float)m->body_quat[b][k];
+    for (int k = 0; k < 6; k++) S.body_inertia[b][k] = (float)m->body_inertia[b][k];
+    S.body_mass[b] = (float)m->body_mass[b];
+    S.body_invw[b] = (float)m->body_invweight0[b][0];
+    mass += m->body_mass[b];
+    if (m->body_depth[b] > maxdepth) maxdepth = m->body_depth[b];
+    if (b > 0) {
+      int p = m->body_parent[b];
+      if (p > 0) {
+        if (S.body_nchild[p] >= 4) { why = "more than 4 children on a body"; return DMB_ERR_MODEL; }
+        S.body_child[p][S.body_nchild[p]++] = (int8_t)b;
+      }
+    }
+  }
+  S.maxdepth = maxdepth;
+  S.inv_total_mass = (float)(1.0 / mass);
+  for (int j = 0; j < m->njnt; j++) {
+    S.jnt_type[j] = (int8_t)m->jnt_type[j]; S.jnt_qposadr[j] = (int8_t)m->jnt_qposadr[j];
+    S.jnt_dofadr[j] = (int8_t)m->jnt_dofadr[j]; S.jnt_limited[j] = (int8_t)m->jnt_limited[j];
+    S.jnt_bodyid[j] = (int8_t)m->jnt_bodyid[j];
+    for (int k = 0; k < 3; k++) S.jnt_axis[j][k] = (float)m->jnt_axis[j][k];
+    S.jnt_range[j][0] = (float)m->jnt_range[j][0]; S.jnt_range[j][1] = (float)m->jnt_range[j][1];
+    S.jnt_qpos0[j] = m->jnt_type[j] == DMB_JNT_HINGE ? (float)m->qpos0[m->jnt_qposadr[j]] : 0.f;
+    if (m->jnt_type[j] == DMB_JNT_HINGE && m->jnt_qposadr[j] != m->jnt_dofadr[j] + 1) {
+      why = "hinge qpos/dof addressing must be qposadr == dofadr + 1 (single leading free joint)"; return DMB_ERR_MODEL;
+    }
+  }
+  for (int d = 0; d < m->nv; d++) {
+    S.dof_bodyid[d] = (int8_t)m->dof_bodyid[d];
+    const int j = m->dof_jntid[d];
+    if (m->jnt_type[j] == DMB_JNT_FREE) {
+      const int k = d - m->jnt_dofadr[j];
+      S.dof_kind[d] = k < 3 ? DOF_FREE_TRANS : DOF_FREE_ROT;
+      S.dof_axisk[d] = (int8_t)(k % 3);
+    } else { S.dof_kind[d] = DOF_HINGE; S.dof_axisk[d] = 0; }
+    int c = 0;
+    for (int a = m->dof_parentid[d]; a >= 0; a = m->dof_parentid[a]) {
+      if (c >= MAXANC) { why = "dof chain longer than 12"; return DMB_ERR_MODEL; }
+      S.dof_anc[d][c++] = (int8_t)a;
+    }
+    S.dof_nanc[d] = (int8_t)c;
+    S.dof_Madr[d] = (int16_t)m->dof_Madr[d];
+    S.dof_armature[d] = (float)m->dof_armature[d]; S.dof_damping[d] = (float)m->dof_damping[d];
+    S.dof_invw[d] = (float)m->dof_invweight0[d];
+    S.dof_act[d] = -1; S.dof_gear[d] = 1.f; S.dof_ctrl_lo[d] = 0.f; S.dof_ctrl_hi[d] = 0.f;
+    S.dof_weight[d] = (float)m->dof_weight[d];
+    // velocity seen by cdof_dot (mj_comVel): hinge -> all chain ancestors; free rot -> the 3
+    // translational dofs only; free trans -> irrelevant (cdof_dot = 0)
+    unsigned long long mk = 0;
+    if (S.dof_kind[d] == DOF_HINGE) for (int a = m->dof_parentid[d]; a >= 0; a = m->dof_parentid[a]) mk |= 1ull << a;
+    else if (S.dof_kind[d] == DOF_FREE_ROT) for (int k = 0; k < 3; k++) mk |= 1ull << (m->jnt_dofadr[j] + k);
+    S.dof_velmask[d] = mk;
+    int e = m->dof_Madr[d];
+    for (int a = d; a >= 0; a = m->dof_parentid[a]) { S.M_i[e] = (uint8_t)d; S.M_j[e] = (uint8_t)a; e++; }
+  }
+  for (int b = 0; b < m->nbody; b++) {
+    unsigned long long mk = 0;
+    for (int bb = b; bb > 0; bb = m->body_parent[bb])
+      for (int d = m->body_dofadr[bb]; d < m->body_dofadr[bb] + m->body_dofnum[bb]; d++) mk |= 1ull << d;
+    S.body_dofmask[b] = mk;
+  }
+  { int t = 0; for (int q = 0; q < MAXANC; q++) for (int p = 0; p <= q; p++) { S.tri_p[t] = (uint8_t)p; S.tri_q[t] = (uint8_t)q; t++; } }
+  for (int g = 0; g < m->ngeom; g++) {
+    S.geom_type[g] = (int8_t)m->geom_type[g]; S.geom_bodyid[g] = (int8_t)m->geom_bodyid[g];
+    S.geom_condim[g] = (int8_t)m->geom_condim[g];
+    if (m->geom_condim[g] != 1 && m->geom_condim[g] != 3) { why = "condim must be 1 or 3"; return DMB_ERR_MODEL; }
+    for (int k = 0; k < 3; k++) { S.geom_size[g][k] = (float)m->geom_size[g][k]; S.geom_pos[g][k] = (float)m->geom_pos[g][k]; }
+    for (int k = 0; k < 4; k++) S.geom_quat[g][k] = (float)m->geom_quat[g][k];
+    S.geom_identq[g] = (m->geom_quat[g][0] == 1.0 && m->geom_quat[g][1] == 0.0 && m->geom_quat[g][2] == 0.0 && m->geom_quat[g][3] == 0.0);
+    S.geom_rbound[g] = (float)m->geom_rbound[g]; S.geom_mu[g] = (float)m->geom_friction[g][0];
+  }
+  for (int p = 0; p < m->npair; p++) { S.pair_g1[p] = (uint8_t)m->pair_geom1[p]; S.pair_g2[p] = (uint8_t)m->pair_geom2[p]; }
+  for (int u = 0; u < m->nu; u++) {
+    const int d = m->act_dofadr[u];
+    S.act_dofadr[u] = (int8_t)d; S.dof_act[d] = (int8_t)u; S.dof_gear[d] = (float)m->act_gear[u];
+    S.dof_ctrl_lo[d] = (float)m->act_ctrlrange[u][0]; S.dof_ctrl_hi[d] = (float)m->act_ctrlrange[u][1];
+    S.dof_kp[d] = (float)m->act_kp[u]; S.dof_kd[d] = (float)m->act_kd[u];
+  }
+  for (int i = 0; i < m->nq; i++) S.qpos0[i] = (float)m->qpos0[i];
+  S.nee = m->nee;
+  for (int e = 0; e < m->nee; e++) { S.ee_body[e] = m->ee_body[e]; for (int k = 0; k < 3; k++) S.ee_pos[e][k] = (float)m->ee_pos[e][k]; }
+  S.ctrl_mode = c->ctrl_mode; S.reward_mode = c->reward_mode; S.reset_mode = c->reset_mode; S.auto_reset = c->auto_reset;
+  S.z_min = (float)c->z_min; S.z_max = (float)c->z_max; S.reset_noise = (float)c->reset_noise; S.pd_dt = (float)m->timestep;
+  S.w_pose = (float)c->w_pose; S.w_vel = (float)c->w_vel; S.w_ee = (float)c->w_end_eff; S.w_root = (float)c->w_root; S.w_com = (float)c->w_com;
+  S.s_pose = (float)c->s_pose; S.s_vel = (float)c->s_vel; S.s_ee = (float)c->s_end_eff; S.s_root = (float)c->s_root; S.s_com = (float)c->s_com;
+  S.s_err = (float)c->s_err;
+  if (c->reward_mode != 0 && c->reward_mode != 1 && c->reward_mode != 4) { why = "reward_mode must be 0, 1 or 4"; return DMB_ERR_ARG; }
+  if (c->ctrl_mode < 0 || c->ctrl_mode > 2) { why = "ctrl_mode must be 0, 1 or 2"; return DMB_ERR_ARG; }
+  S.nclip = mc->nclip; S.nframe_total = mc->nframe_total;
+  if (mc->nclip < 1 || mc->nclip > DMB_MAX_CLIP) { why = "need 1..16 motion clips"; return DMB_ERR_ARG; }
+  for (int k = 0; k < mc->nclip; k++) { S.clip_start[k] = mc->clip_start[k]; S.clip_len[k] = mc->clip_len[k]; }
+  return DMB_OK;
+}
+
+extern "C" {
+
+int dmb_version(void) { return DMB_VERSION; }
+int32_t dmb_sizeof_model(void) { return (int32_t)sizeof(dmb_model_t); }
+int32_t dmb_sizeof_config(void) { return (int32_t)sizeof(dmb_config_t); }
+int32_t dmb_sizeof_mocap(void) { return (int32_t)sizeof(dmb_mocap_t); }
+
+const char* dmb_last_error(dmb_handle_t h) { return h ? h->err.c_str() : g_err.c_str(); }
+
+int32_t dmb_debug_stride(void) { return dbg::stride; }
+
+int32_t dmb_debug_offset(const char* name) {
+  struct { const char* n; int o; } tab[] = {
+      {"xpos", dbg::xpos}, {"xquat", dbg::xquat}, {"xipos", dbg::xipos}, {"com", dbg::com}, {"qM", dbg::qM},
+      {"qLD", dbg::qLD}, {"qfrc_bias", dbg::qfrc_bias}, {"qfrc_smooth", dbg::qfrc_smooth},
+      {"qacc_smooth", dbg::qacc_smooth}, {"ncon", dbg::ncon}, {"nefc", dbg::nefc}, {"iter", dbg::iter},
+      {"z_com", dbg::z_com}, {"contact", dbg::contact}, {"efc_pos", dbg::efc_pos}, {"efc_R", dbg::efc_R},
+      {"efc_aref", dbg::efc_aref}, {"efc_b", dbg::efc_b}, {"efc_force", dbg::efc_force},
+      {"efc_AR_diag", dbg::efc_AR_diag}, {"qacc", dbg::qacc}, {"cvel", dbg::cvel}};
+  if (!name) return -1;
+  for (auto& t : tab) if (!strcmp(t.n, name)) return t.o;
+  return -1;
+}
+
+int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_mocap_t* mocap, int32_t num_envs,
+               int32_t cuda_device, uint64_t seed, uint32_t first_env_id, dmb_handle_t* out) {
+  if (!model || !config || !mocap || !out || num_envs <= 0) return fail(nullptr, DMB_ERR_ARG, "dmb_create: bad argument");
+  if (!mocap->data_config || !mocap->data_vel || mocap->nframe_total <= 0) return fail(nullptr, DMB_ERR_ARG, "dmb_create: empty mocap tables");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, DMB_ERR_NO_DEVICE, "no CUDA device visible: libdmb200 has no CPU fallback");
+  if (cuda_device < 0 || cuda_device >= ndev) return fail(nullptr, DMB_ERR_ARG, "dmb_create: bad device index");
+  dmb_handle_t h = new (std::nothrow) dmb_handle_s();
+  if (!h) return fail(nullptr, DMB_ERR_ARG, "out of host memory");
+  std::string why;
+  int rc = build_model(model, config, mocap, h->hmodel, why);
+  if (rc != DMB_OK) { delete h; return fail(nullptr, rc, "dmb_create: " + why); }
+  h->device = cuda_device; h->num_envs = num_envs; h->seed = seed; h->first_env_id = first_env_id;
+  h->nu = model->nu; h->obs_dim = (model->nq - 7) + (model->nv - 6);
+  cudaError_t e = cudaSetDevice(cuda_device);
+  if (e != cudaSuccess) { delete h; return fail(nullptr, DMB_ERR_CUDA, cudaGetErrorString(e)); }
+  const size_t F = (size_t)mocap->nframe_total;
+  const size_t ncfg = F * model->nq, nvel = F * model->nv, naux = F * DMB_REF_AUX;
+  float* tmp = new float[ncfg > naux ? (ncfg > nvel ? ncfg : nvel) : (naux > nvel ? naux : nvel)];
+  auto upload = [&](const double* src, size_t n, float** dst) -> cudaError_t {
+    cudaError_t ee = cudaMalloc((void**)dst, n * sizeof(float));
+    if (ee != cudaSuccess) return ee;
+    for (size_t i = 0; i < n; i++) tmp[i] = src ? (float)src[i] : 0.f;
+    return cudaMemcpy(*dst, tmp, n * sizeof(float), cudaMemcpyHostToDevice);
+  };
+  e = cudaMalloc((void**)&h->dmodel, sizeof(ModelS));
+  if (e == cudaSuccess) e = cudaMemcpy(h->dmodel, &h->hmodel, sizeof(ModelS), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = upload(mocap->data_config, ncfg, &h->d_cfg);
+  if (e == cudaSuccess) e = upload(mocap->data_vel, nvel, &h->d_vel);
+  if (e == cudaSuccess) e = upload(mocap->ref_aux, naux, &h->d_aux);
+  delete[] tmp;
+  if (e != cudaSuccess) { std::string msg = cudaGetErrorString(e); dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, "dmb_create: " + msg); }
+  // launch geometry: as many env tiles per CTA as opt-in shared memory allows, one CTA per SM
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, cuda_device);
+  if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, cudaGetErrorString(e)); }
+  const size_t maxsmem = prop.sharedMemPerBlockOptin;
+  int W = (int)((maxsmem - MODEL_BYTES) / sizeof(EnvS));
+  if (W > 16) W = 16;
+  if (W < 1) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, "not enough shared memory for one env tile"); }
+  h->envs_per_cta = W; h->block = 32 * W;
+  h->smem = (int)(MODEL_BYTES + (size_t)W * sizeof(EnvS));
+  int need = (num_envs + W - 1) / W;
+  h->grid = need < prop.multiProcessorCount ? need : prop.multiProcessorCount;
+  for (auto fn : {(const void*)k_step, (const void*)k_reset, (const void*)k_forward_debug}) {
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
+    if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
+  }
+  *out = h;
+  return DMB_OK;
+}
+
+int dmb_destroy(dmb_handle_t h) {
+  if (!h) return DMB_ERR_ARG;
+  cudaSetDevice(h->device);
+  cudaFree(h->dmodel); cudaFree(h->d_cfg); cudaFree(h->d_vel); cudaFree(h->d_aux);
+  delete h;
+  return DMB_OK;
+}
+
+static bool state_ok(const dmb_state_t* st) {
+  return st && st->qpos && st->qvel && st->warm && st->clip && st->idx_init && st->idx_curr && st->reset_count &&
+         st->ep_len && st->ep_ret && st->flags;
+}
+static DevPtrs devptrs(dmb_handle_t h) { DevPtrs P; P.model = h->dmodel; P.mocap_cfg = h->d_cfg; P.mocap_vel = h->d_vel; P.ref_aux = h->d_aux; return P; }
+
+int dmb_reset(dmb_handle_t h, const dmb_state_t* st, const uint8_t* mask, int32_t mode, float* obs, void* stream) {
+  if (!h) return DMB_ERR_ARG;
+  if (!state_ok(st) || mode < -1 || mode > 1) return fail(h, DMB_ERR_ARG, "dmb_reset: bad argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  k_reset<<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, mask, mode, obs, h->num_envs, h->seed, h->first_env_id);
+  CUDA_TRY(h, cudaGetLastError());
+  return DMB_OK;
+}
+
+int dmb_step(dmb_handle_t h, const dmb_state_t* st, const float* action, const dmb_step_out_t* out, void* stream) {
+  if (!h) return DMB_ERR_ARG;
+  if (!state_ok(st) || !action || !out || !out->obs || !out->reward || !out->done) return fail(h, DMB_ERR_ARG, "dmb_step: bad argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  k_step<<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
+  CUDA_TRY(h, cudaGetLastError());
+  return DMB_OK;
+}
+
+int dmb_get_obs(dmb_handle_t h, const dmb_state_t* st, float* obs, void* stream) {
+  if (!h) return DMB_ERR_ARG;
+  if (!state_ok(st) || !obs) return fail(h, DMB_ERR_ARG, "dmb_get_obs: bad argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t total = (size_t)h->num_envs * h->obs_dim;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 4096) blocks = 4096;
+  k_obs<<<blocks, 256, 0, (cudaStream_t)stream>>>(devptrs(h), *st, obs, h->num_envs);
+  CUDA_TRY(h, cudaGetLastError());
+  return DMB_OK;
+}
+
+int dmb_forward_debug(dmb_handle_t h, const dmb_state_t* st, const float* ctrl, float* dbgout, void* stream) {
+  if (!h) return DMB_ERR_ARG;
+  if (!state_ok(st) || !ctrl || !dbgout) return fail(h, DMB_ERR_ARG, "dmb_forward_debug: bad argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  k_forward_debug<<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, ctrl, dbgout, h->num_envs);
+  CUDA_TRY(h, cudaGetLastError());
+  return DMB_OK;
+}
+
+int dmb_launch_info(dmb_handle_t h, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* envs_per_cta) {
+  if (!h) return DMB_ERR_ARG;
+  if (grid) *grid = h->grid;
+  if (block) *block = h->block;
+  if (smem_bytes) *smem_bytes = h->smem;
+  if (envs_per_cta) *envs_per_cta = h->envs_per_cta;
+  return DMB_OK;
+}
+
+}  // extern "C"

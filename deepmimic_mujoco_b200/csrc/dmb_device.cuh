@@ -1,0 +1,929 @@
+// dmb_device.cuh -- one-warp-per-env forward dynamics (MuJoCo pipeline restated for sm_100a).
+//
+// Every function below is executed by the 32 lanes of the warp that owns the env tile `S`.
+// Lane mappings: bodies/geoms/contacts/joints -> lane, dofs -> lane and
+// lane+32, constraint rows -> lane and lane+32.  The reference path being replaced is
+// mj_forward inside mj_step (dp_env_v3.py:112 -> mujoco_py MjSim.step); stage names in the
+// comments are MuJoCo's.
+#pragma once
+#include "dmb_math.cuh"
+#include "dmb_types.cuh"
+
+namespace dmb {
+
+// ------------------------------------------------------------------------------------------
+// mj_kinematics: lane = body, one tree level per round.  Also writes the world-frame hinge
+// axes into cdof[.][0:3] (the angular part of cdof) and the geom poses (lane = geom).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void kinematics(const ModelS& M, EnvS& S, int lane) {
+  const int b = lane;
+  const bool act = b >= 1 && b < M.nbody;
+  if (lane == 0) {
+    S.xpos[0] = S.xpos[1] = S.xpos[2] = 0.f;
+    S.xquat[0] = 1.f; S.xquat[1] = S.xquat[2] = S.xquat[3] = 0.f;
+    S.xmat[0] = 1.f; S.xmat[1] = 0.f; S.xmat[2] = 0.f; S.xmat[3] = 0.f; S.xmat[4] = 1.f; S.xmat[5] = 0.f;
+    S.xmat[6] = 0.f; S.xmat[7] = 0.f; S.xmat[8] = 1.f;
+    S.xipos[0] = S.xipos[1] = S.xipos[2] = 0.f;
+  }
+  // half-angle sin/cos of this body's hinge joints (independent of the parent pose)
+  float sn[JPB], cs[JPB];
+  int jadr = 0, jnum = 0, depth = -1;
+  if (act) {
+    jadr = M.body_jntadr[b]; jnum = M.body_jntnum[b]; depth = M.body_depth[b];
+#pragma unroll
+    for (int k = 0; k < JPB; k++) {
+      sn[k] = 0.f; cs[k] = 1.f;
+      if (k < jnum && M.jnt_type[jadr + k] == DMB_JNT_HINGE) {
+        int qa = M.jnt_qposadr[jadr + k];
+        sincosf(0.5f * (S.qpos[qa] - M.jnt_qpos0[jadr + k]), &sn[k], &cs[k]);
+      }
+    }
+  }
+  __syncwarp();
+  for (int lev = 1; lev <= M.maxdepth; lev++) {
+    if (act && depth == lev) {
+      const int p = M.body_parent[b];
+      V3 pos = ld3(&S.xpos[3 * p]) + mat_vec(&S.xmat[9 * p], ld3(M.body_pos[b]));
+      Q4 qp; qp.w = S.xquat[4 * p]; qp.x = S.xquat[4 * p + 1]; qp.y = S.xquat[4 * p + 2]; qp.z = S.xquat[4 * p + 3];
+      Q4 qb; qb.w = M.body_quat[b][0]; qb.x = M.body_quat[b][1]; qb.y = M.body_quat[b][2]; qb.z = M.body_quat[b][3];
+      Q4 quat = qmul(qp, qb);
+#pragma unroll
+      for (int k = 0; k < JPB; k++) {
+        if (k < jnum) {
+          const int j = jadr + k;
+          if (M.jnt_type[j] == DMB_JNT_FREE) {
+            const int qa = M.jnt_qposadr[j];
+            pos = v3(S.qpos[qa], S.qpos[qa + 1], S.qpos[qa + 2]);
+            quat.w = S.qpos[qa + 3]; quat.x = S.qpos[qa + 4]; quat.y = S.qpos[qa + 5]; quat.z = S.qpos[qa + 6];
+            quat = qnormalize(quat);
+          } else {
+            V3 ax = ld3(M.jnt_axis[j]);
+            st3(&S.cdof[6 * M.jnt_dofadr[j]], qrot(quat, ax));
+            Q4 ql; ql.w = cs[k]; ql.x = sn[k] * ax.x; ql.y = sn[k] * ax.y; ql.z = sn[k] * ax.z;
+            quat = qmul(quat, ql);
+          }
+        }
+      }
+      quat = qnormalize(quat);
+      st3(&S.xpos[3 * b], pos);
+      S.xquat[4 * b] = quat.w; S.xquat[4 * b + 1] = quat.x; S.xquat[4 * b + 2] = quat.y; S.xquat[4 * b + 3] = quat.z;
+      float m[9];
+      quat2mat(m, quat);
+#pragma unroll
+      for (int k = 0; k < 9; k++) S.xmat[9 * b + k] = m[k];
+      st3(&S.xipos[3 * b], pos + mat_vec(m, ld3(M.body_ipos[b])));
+    }
+    __syncwarp();
+  }
+  // geoms
+  if (lane < M.ngeom) {
+    const int g = lane, gb = M.geom_bodyid[g];
+    st3(&S.gpos[3 * g], ld3(&S.xpos[3 * gb]) + mat_vec(&S.xmat[9 * gb], ld3(M.geom_pos[g])));
+    if (M.geom_identq[g]) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) S.gmat[9 * g + k] = S.xmat[9 * gb + k];
+    } else {
+      Q4 qb; qb.w = S.xquat[4 * gb]; qb.x = S.xquat[4 * gb + 1]; qb.y = S.xquat[4 * gb + 2]; qb.z = S.xquat[4 * gb + 3];
+      Q4 qg; qg.w = M.geom_quat[g][0]; qg.x = M.geom_quat[g][1]; qg.y = M.geom_quat[g][2]; qg.z = M.geom_quat[g][3];
+      float m[9];
+      quat2mat(m, qmul(qb, qg));
+#pragma unroll
+      for (int k = 0; k < 9; k++) S.gmat[9 * g + k] = m[k];
+    }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_comPos: whole-model CoM (warp-shuffle reduction over bodies), cinert (lane = body),
+// cdof (lane = dof).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void com_pos(const ModelS& M, EnvS& S, int lane) {
+  const int b = lane;
+  const bool act = b >= 1 && b < M.nbody;
+  float ms = act ? M.body_mass[b] : 0.f;
+  V3 xi = act ? ld3(&S.xipos[3 * b]) : v3(0.f, 0.f, 0.f);
+  float cx = warp_sum(ms * xi.x) * M.inv_total_mass;
+  float cy = warp_sum(ms * xi.y) * M.inv_total_mass;
+  float cz = warp_sum(ms * xi.z) * M.inv_total_mass;
+  if (lane == 0) { S.com[0] = cx; S.com[1] = cy; S.com[2] = cz; }
+  const V3 com = v3(cx, cy, cz);
+  if (lane < M.nbody) {
+    float* ci = &S.cinert[10 * b];
+    if (!act) {
+#pragma unroll
+      for (int k = 0; k < 10; k++) ci[k] = 0.f;
+    } else {
+      const float* I = M.body_inertia[b];
+      const float* R = &S.xmat[9 * b];
+      // W = R * Ib * R'
+      float Ib[9] = {I[0], I[3], I[4], I[3], I[1], I[5], I[4], I[5], I[2]};
+      float RI[9], W[9];
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) RI[3 * r + c] = R[3 * r] * Ib[c] + R[3 * r + 1] * Ib[3 + c] + R[3 * r + 2] * Ib[6 + c];
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) W[3 * r + c] = RI[3 * r] * R[3 * c] + RI[3 * r + 1] * R[3 * c + 1] + RI[3 * r + 2] * R[3 * c + 2];
+      V3 d = xi - com;
+      ci[0] = W[0] + ms * (d.y * d.y + d.z * d.z);
+      ci[1] = W[4] + ms * (d.x * d.x + d.z * d.z);
+      ci[2] = W[8] + ms * (d.x * d.x + d.y * d.y);
+      ci[3] = W[1] - ms * d.x * d.y;
+      ci[4] = W[2] - ms * d.x * d.z;
+      ci[5] = W[5] - ms * d.y * d.z;
+      ci[6] = ms * d.x; ci[7] = ms * d.y; ci[8] = ms * d.z; ci[9] = ms;
+    }
+  }
+  for (int d = lane; d < M.nv; d += 32) {
+    const int db = M.dof_bodyid[d];
+    const V3 off = com - ld3(&S.xpos[3 * db]);
+    float* cd = &S.cdof[6 * d];
+    const int kind = M.dof_kind[d], k = M.dof_axisk[d];
+    if (kind == DOF_FREE_TRANS) {
+      cd[0] = cd[1] = cd[2] = 0.f;
+      cd[3] = k == 0 ? 1.f : 0.f; cd[4] = k == 1 ? 1.f : 0.f; cd[5] = k == 2 ? 1.f : 0.f;
+    } else {
+      V3 ax;
+      if (kind == DOF_FREE_ROT) { ax = v3(S.xmat[9 * db + k], S.xmat[9 * db + 3 + k], S.xmat[9 * db + 6 + k]); st3(cd, ax); }
+      else ax = ld3(cd);  // written by kinematics()
+      st3(cd + 3, cross(ax, off));
+    }
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_crb + mj_factorM: composite inertias (parents gather children, level by level), the
+// nM sparse inertia entries (lane = entry) and the in-place sparse L'DL factorisation.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, float* dbg_qM) {
+  const int b = lane;
+  if (lane < M.nbody) {
+#pragma unroll
+    for (int k = 0; k < 10; k++) S.crb[10 * b + k] = S.cinert[10 * b + k];
+  }
+  __syncwarp();
+  for (int lev = M.maxdepth - 1; lev >= 1; lev--) {
+    if (b >= 1 && b < M.nbody && M.body_depth[b] == lev) {
+      const int nc = M.body_nchild[b];
+      for (int c = 0; c < nc; c++) {
+        const int ch = M.body_child[b][c];
+#pragma unroll
+        for (int k = 0; k < 10; k++) S.crb[10 * b + k] += S.crb[10 * ch + k];
+      }
+    }
+    __syncwarp();
+  }
+  for (int d = lane; d < M.nv; d += 32) mul_inert_vec(&S.buf6[6 * d], &S.crb[10 * M.dof_bodyid[d]], &S.cdof[6 * d]);
+  __syncwarp();
+  for (int e = lane; e < M.nM; e += 32) {
+    const int i = M.M_i[e], j = M.M_j[e];
+    const float* a = &S.cdof[6 * j];
+    const float* bf = &S.buf6[6 * i];
+    float s = a[0] * bf[0] + a[1] * bf[1] + a[2] * bf[2] + a[3] * bf[3] + a[4] * bf[4] + a[5] * bf[5];
+    if (i == j) s += M.dof_armature[i];
+    S.qLD[e] = s;
+    if (dbg_qM) dbg_qM[e] = s;
+  }
+  __syncwarp();
+  // sparse L'DL (mj_factorM): for k = nv-1..0 eliminate dof k from all its ancestors
+  for (int k = M.nv - 1; k >= 0; k--) {
+    const int c = M.dof_nanc[k];
+    if (c == 0) continue;
+    const int adrk = M.dof_Madr[k];
+    const float inv = 1.0f / S.qLD[adrk];
+    const int npair = c * (c + 1) / 2;
+    for (int t = lane; t < npair; t += 32) {
+      const int p = M.tri_p[t], q = M.tri_q[t];  // p <= q
+      const int i = M.dof_anc[k][p];
+      S.qLD[M.dof_Madr[i] + (q - p)] -= S.qLD[adrk + 1 + p] * S.qLD[adrk + 1 + q] * inv;
+    }
+    __syncwarp();
+    if (lane < c) S.qLD[adrk + 1 + lane] *= inv;
+    __syncwarp();
+  }
+  for (int d = lane; d < M.nv; d += 32) {
+    float di = 1.0f / S.qLD[M.dof_Madr[d]];
+    S.dinv[d] = di;
+    S.dsq[d] = sqrtf(di);
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_comVel + mj_rne(flg_acc=0) + passive + actuation: leaves the smooth generalised force
+// qfrc_smooth = passive - bias + actuator in S.vec0.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void smooth_forces(const ModelS& M, EnvS& S, int lane, float* dbg_bias) {
+  // w[a] = cdof[a] * qvel[a]
+  for (int d = lane; d < M.nv; d += 32) {
+    const float qv = S.qvel[d];
+#pragma unroll
+    for (int k = 0; k < 6; k++) S.buf6[6 * d + k] = S.cdof[6 * d + k] * qv;
+  }
+  __syncwarp();
+  // cdof_dot[d] = crossMotion(velocity seen by dof d, cdof[d])
+  for (int d = lane; d < M.nv; d += 32) {
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    unsigned long long mk = M.dof_velmask[d];
+    while (mk) {
+      const int a = __ffsll((long long)mk) - 1;
+      mk &= mk - 1;
+#pragma unroll
+      for (int k = 0; k < 6; k++) v[k] += S.buf6[6 * a + k];
+    }
+    if (M.dof_kind[d] == DOF_FREE_TRANS) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) S.cdofd[6 * d + k] = 0.f;
+    } else {
+      cross_motion(&S.cdofd[6 * d], v, &S.cdof[6 * d]);
+    }
+  }
+  __syncwarp();
+  // body velocities and accelerations (sums over the dof chain), body forces
+  if (lane < M.nbody) {
+    const int b = lane;
+    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float a[6] = {0.f, 0.f, 0.f, -M.gravity[0], -M.gravity[1], -M.gravity[2]};
+    unsigned long long mk = M.body_dofmask[b];
+    while (mk) {
+      const int d = __ffsll((long long)mk) - 1;
+      mk &= mk - 1;
+      const float qv = S.qvel[d];
+#pragma unroll
+      for (int k = 0; k < 6; k++) { v[k] += S.buf6[6 * d + k]; a[k] += S.cdofd[6 * d + k] * qv; }
+    }
+    float f[6], t1[6], t2[6];
+    if (b == 0) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) { f[k] = 0.f; v[k] = 0.f; }
+    } else {
+      mul_inert_vec(f, &S.cinert[10 * b], a);
+      mul_inert_vec(t1, &S.cinert[10 * b], v);
+      cross_force(t2, v, t1);
+#pragma unroll
+      for (int k = 0; k < 6; k++) f[k] += t2[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) { S.cvel[6 * b + k] = v[k]; S.cfrc[6 * b + k] = f[k]; }
+  }
+  __syncwarp();
+  for (int lev = M.maxdepth - 1; lev >= 1; lev--) {
+    const int b = lane;
+    if (b >= 1 && b < M.nbody && M.body_depth[b] == lev) {
+      const int nc = M.body_nchild[b];
+      for (int c = 0; c < nc; c++) {
+        const int ch = M.body_child[b][c];
+#pragma unroll
+        for (int k = 0; k < 6; k++) S.cfrc[6 * b + k] += S.cfrc[6 * ch + k];
+      }
+    }
+    __syncwarp();
+  }
+  for (int d = lane; d < M.nv; d += 32) {
+    const float* cd = &S.cdof[6 * d];
+    const float* cf = &S.cfrc[6 * M.dof_bodyid[d]];
+    const float bias = cd[0] * cf[0] + cd[1] * cf[1] + cd[2] * cf[2] + cd[3] * cf[3] + cd[4] * cf[4] + cd[5] * cf[5];
+    if (dbg_bias) dbg_bias[d] = bias;
+    S.vec0[d] = -M.dof_damping[d] * S.qvel[d] - bias + S.ctrlf[d];
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// narrow phase (restates oracle/dm_oracle.c raw_* functions in fp32)
+// ------------------------------------------------------------------------------------------
+struct RawCon { float dist; V3 pos, n, y; };
+
+__device__ __forceinline__ int raw_plane_sphere(RawCon& c, float margin, V3 ppos, V3 pn, V3 spos, float r) {
+  const float cdist = dot(spos - ppos, pn);
+  if (cdist > margin + r) return 0;
+  c.dist = cdist - r;
+  c.pos = spos - (r + 0.5f * c.dist) * pn;
+  c.n = pn;
+  c.y = v3(0.f, 0.f, 0.f);
+  return 1;
+}
+__device__ __forceinline__ int raw_sphere_sphere(RawCon& c, float margin, V3 p1, float r1, V3 p2, float r2) {
+  V3 dif = p2 - p1;
+  const float dist = norm(dif);
+  if (dist > margin + r1 + r2) return 0;
+  c.dist = dist - r1 - r2;
+  c.n = dist < DMB_MINVAL ? v3(1.f, 0.f, 0.f) : (1.0f / dist) * dif;
+  c.pos = p1 + (r1 + 0.5f * c.dist) * c.n;
+  c.y = v3(0.f, 0.f, 0.f);
+  return 1;
+}
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return x > hi ? hi : (x < lo ? lo : x); }
+
+__device__ int raw_sphere_box(RawCon& c, float margin, V3 spos, float r, V3 bpos, const float* bmat, V3 bs) {
+  const V3 center = matT_vec(bmat, spos - bpos);
+  const V3 cl = v3(clampf(center.x, -bs.x, bs.x), clampf(center.y, -bs.y, bs.y), clampf(center.z, -bs.z, bs.z));
+  const V3 deep = center - cl;
+  const float dist = norm(deep);
+  if (dist - r > margin) return 0;
+  V3 nloc, ploc;
+  if (dist <= DMB_MINVAL) {
+    float gx = bs.x - fabsf(center.x), gy = bs.y - fabsf(center.y), gz = bs.z - fabsf(center.z);
+    float closest = gx; int kk = 0;
+    if (gy < closest) { closest = gy; kk = 1; }
+    if (gz < closest) { closest = gz; kk = 2; }
+    V3 nf = v3(0.f, 0.f, 0.f);
+    if (kk == 0) nf.x = center.x > 0.f ? 1.f : -1.f;
+    else if (kk == 1) nf.y = center.y > 0.f ? 1.f : -1.f;
+    else nf.z = center.z > 0.f ? 1.f : -1.f;
+    c.dist = -closest - r;
+    nloc = -1.f * nf;
+    ploc = center + (0.5f * (closest - r)) * nf;
+  } else {
+    c.dist = dist - r;
+    const V3 nout = (1.0f / dist) * deep;
+    nloc = -1.f * nout;
+    ploc = cl + (0.5f * c.dist) * nout;
+  }
+  c.n = mat_vec(bmat, nloc);
+  c.pos = mat_vec(bmat, ploc) + bpos;
+  c.y = v3(0.f, 0.f, 0.f);
+  return 1;
+}
+
+__device__ __forceinline__ float capbox_dfdt(V3 c, V3 u, V3 s, float t) {
+  float g = 0.f, p;
+  p = c.x + t * u.x; if (p > s.x) g += (p - s.x) * u.x; else if (p < -s.x) g += (p + s.x) * u.x;
+  p = c.y + t * u.y; if (p > s.y) g += (p - s.y) * u.y; else if (p < -s.y) g += (p + s.y) * u.y;
+  p = c.z + t * u.z; if (p > s.z) g += (p - s.z) * u.z; else if (p < -s.z) g += (p + s.z) * u.z;
+  return g;
+}
+
+__device__ int raw_capsule_box(RawCon* c, float margin, V3 cpos, const float* cmat, float r, float h, V3 bpos,
+                               const float* bmat, V3 bs) {
+  const V3 axis = v3(cmat[2], cmat[5], cmat[8]);
+  const V3 cl = matT_vec(bmat, cpos - bpos);
+  const V3 u = matT_vec(bmat, axis);
+  float knot[8];
+  int nk = 0;
+  knot[nk++] = -h;
+  const float cc[3] = {cl.x, cl.y, cl.z}, uu[3] = {u.x, u.y, u.z}, ss[3] = {bs.x, bs.y, bs.z};
+  for (int k = 0; k < 3; k++) {
+    if (fabsf(uu[k]) > 1e-12f) {
+      const float t1 = (ss[k] - cc[k]) / uu[k], t2 = (-ss[k] - cc[k]) / uu[k];
+      if (t1 > -h && t1 < h) knot[nk++] = t1;
+      if (t2 > -h && t2 < h) knot[nk++] = t2;
+    }
+  }
+  knot[nk++] = h;
+  for (int i = 1; i < nk; i++) {
+    float v = knot[i];
+    int j = i - 1;
+    while (j >= 0 && knot[j] > v) { knot[j + 1] = knot[j]; j--; }
+    knot[j + 1] = v;
+  }
+  float tlo, thi;
+  {
+    float gprev = capbox_dfdt(cl, u, bs, knot[0]);
+    if (gprev >= 0.f) tlo = knot[0];
+    else {
+      tlo = knot[nk - 1];
+      for (int i = 1; i < nk; i++) {
+        const float g = capbox_dfdt(cl, u, bs, knot[i]);
+        if (g >= 0.f) { tlo = knot[i - 1] - gprev * (knot[i] - knot[i - 1]) / (g - gprev); break; }
+        gprev = g;
+      }
+    }
+  }
+  {
+    float gnext = capbox_dfdt(cl, u, bs, knot[nk - 1]);
+    if (gnext <= 0.f) thi = knot[nk - 1];
+    else {
+      thi = knot[0];
+      for (int i = nk - 2; i >= 0; i--) {
+        const float g = capbox_dfdt(cl, u, bs, knot[i]);
+        if (g <= 0.f) { thi = knot[i + 1] - gnext * (knot[i] - knot[i + 1]) / (g - gnext); break; }
+        gnext = g;
+      }
+    }
+  }
+  const float ts = (thi - tlo > 1e-6f * h) ? (fabsf(tlo) <= fabsf(thi) ? tlo : thi) : 0.5f * (tlo + thi);
+  int n = 0;
+  n += raw_sphere_box(c[n], margin, cpos + ts * axis, r, bpos, bmat, bs);
+  const float te = (h - ts >= ts + h) ? h : -h;
+  if (fabsf(te - ts) > 0.01f * h) n += raw_sphere_box(c[n], margin, cpos + te * axis, r, bpos, bmat, bs);
+  return n;
+}
+
+__device__ int raw_capsule_capsule(RawCon* c, float margin, V3 pos1, const float* mat1, float r1, float h1, V3 pos2,
+                                   const float* mat2, float r2, float h2) {
+  const V3 a1 = v3(mat1[2], mat1[5], mat1[8]), a2 = v3(mat2[2], mat2[5], mat2[8]);
+  const V3 dif = pos1 - pos2;
+  const float ma = dot(a1, a1), mb = -dot(a1, a2), mc = dot(a2, a2);
+  const float u = -dot(a1, dif), v = dot(a2, dif);
+  const float det = ma * mc - mb * mb;
+  if (fabsf(det) >= 1e-10f) {
+    float x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+    if (x1 > h1) { x1 = h1; x2 = (v - mb * h1) / mc; }
+    else if (x1 < -h1) { x1 = -h1; x2 = (v + mb * h1) / mc; }
+    if (x2 > h2) { x2 = h2; x1 = (u - mb * h2) / ma; }
+    else if (x2 < -h2) { x2 = -h2; x1 = (u + mb * h2) / ma; }
+    x1 = clampf(x1, -h1, h1);
+    return raw_sphere_sphere(c[0], margin, pos1 + x1 * a1, r1, pos2 + x2 * a2, r2);
+  }
+  int n = 0;
+  float x1, x2;
+  x2 = clampf((v - mb * h1) / mc, -h2, h2);
+  n += raw_sphere_sphere(c[n], margin, pos1 + h1 * a1, r1, pos2 + x2 * a2, r2);
+  x2 = clampf((v + mb * h1) / mc, -h2, h2);
+  n += raw_sphere_sphere(c[n], margin, pos1 - h1 * a1, r1, pos2 + x2 * a2, r2);
+  if (n == 2) return n;
+  x1 = clampf((u - mb * h2) / ma, -h1, h1);
+  n += raw_sphere_sphere(c[n], margin, pos1 + x1 * a1, r1, pos2 + h2 * a2, r2);
+  if (n == 2) return n;
+  x1 = clampf((u + mb * h2) / ma, -h1, h1);
+  n += raw_sphere_sphere(c[n], margin, pos1 + x1 * a1, r1, pos2 - h2 * a2, r2);
+  return n;
+}
+
+__device__ int raw_box_box(RawCon* c, float margin, V3 pos1, const float* mat1, V3 s1, V3 pos2, const float* mat2,
+                           V3 s2) {
+  int n = 0;
+  for (int pass = 0; pass < 2 && n < 4; pass++) {
+    const V3 vp = pass == 0 ? pos2 : pos1;
+    const float* vm = pass == 0 ? mat2 : mat1;
+    const V3 vs = pass == 0 ? s2 : s1;
+    const V3 bp = pass == 0 ? pos1 : pos2;
+    const float* bm = pass == 0 ? mat1 : mat2;
+    const V3 bs = pass == 0 ? s1 : s2;
+    for (int i = 0; i < 8 && n < 4; i++) {
+      const V3 loc = v3((i & 1) ? vs.x : -vs.x, (i & 2) ? vs.y : -vs.y, (i & 4) ? vs.z : -vs.z);
+      const V3 w = mat_vec(vm, loc) + vp;
+      if (raw_sphere_box(c[n], margin, w, 0.f, bp, bm, bs)) {
+        if (pass == 0) c[n].n = -1.f * c[n].n;
+        n++;
+      }
+    }
+  }
+  return n;
+}
+
+// mju_makeFrame
+__device__ __forceinline__ void make_frame(float* f, V3 n, V3 y) {
+  normalize(n);
+  if (norm(y) < 0.5f) {
+    y = v3(0.f, 0.f, 0.f);
+    if (n.y < 0.5f && n.y > -0.5f) y.y = 1.f; else y.z = 1.f;
+  }
+  y = y - dot(n, y) * n;
+  normalize(y);
+  st3(f, n); st3(f + 3, y); st3(f + 6, cross(n, y));
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_collision: broad phase (lane = candidate pair, 4 rounds) -> compacted survivor list ->
+// narrow phase (lane = survivor) -> contacts compacted in pair order by warp prefix sums.
+// ------------------------------------------------------------------------------------------
+__device__ void collision(const ModelS& M, EnvS& S, int lane) {
+  const float margin = M.margin;
+  int nsurv = 0;
+  for (int base = 0; base < M.npair; base += 32) {
+    const int p = base + lane;
+    bool keep = false;
+    if (p < M.npair) {
+      const int g1 = M.pair_g1[p], g2 = M.pair_g2[p];
+      const V3 dif = ld3(&S.gpos[3 * g2]) - ld3(&S.gpos[3 * g1]);
+      if (M.geom_type[g1] == DMB_GEOM_PLANE) {
+        const V3 nrm = v3(S.gmat[9 * g1 + 2], S.gmat[9 * g1 + 5], S.gmat[9 * g1 + 8]);
+        keep = !(dot(dif, nrm) > M.geom_rbound[g2] + margin);
+      } else {
+        const float bound = M.geom_rbound[g1] + M.geom_rbound[g2] + margin;
+        keep = !(dot(dif, dif) > bound * bound);
+      }
+    }
+    const unsigned bal = __ballot_sync(DMB_FULL, keep);
+    if (keep) S.surv[nsurv + __popc(bal & ((1u << lane) - 1u))] = p;
+    nsurv += __popc(bal);
+  }
+  __syncwarp();
+  int ncon = 0;
+  for (int base = 0; base < nsurv; base += 32) {
+    RawCon rc[4];
+    int n = 0, g1 = 0, g2 = 0;
+    if (base + lane < nsurv) {
+      const int p = S.surv[base + lane];
+      g1 = M.pair_g1[p]; g2 = M.pair_g2[p];
+      const int t1 = M.geom_type[g1], t2 = M.geom_type[g2];
+      const V3 pos1 = ld3(&S.gpos[3 * g1]), pos2 = ld3(&S.gpos[3 * g2]);
+      const float* mat1 = &S.gmat[9 * g1];
+      const float* mat2 = &S.gmat[9 * g2];
+      const V3 s1 = ld3(M.geom_size[g1]), s2 = ld3(M.geom_size[g2]);
+      if (t1 == DMB_GEOM_PLANE) {
+        const V3 nrm = v3(mat1[2], mat1[5], mat1[8]);
+        if (t2 == DMB_GEOM_SPHERE) {
+          n = raw_plane_sphere(rc[0], margin, pos1, nrm, pos2, s2.x);
+        } else if (t2 == DMB_GEOM_CAPSULE) {
+          const V3 axis = v3(mat2[2], mat2[5], mat2[8]);
+          n += raw_plane_sphere(rc[n], margin, pos1, nrm, pos2 + s2.y * axis, s2.x);
+          n += raw_plane_sphere(rc[n], margin, pos1, nrm, pos2 - s2.y * axis, s2.x);
+          for (int i = 0; i < n; i++) rc[i].y = axis;
+        } else if (t2 == DMB_GEOM_BOX) {
+          const float dist = dot(pos2 - pos1, nrm);
+          for (int i = 0; i < 8 && n < 4; i++) {
+            const V3 vec = v3((i & 1) ? s2.x : -s2.x, (i & 2) ? s2.y : -s2.y, (i & 4) ? s2.z : -s2.z);
+            const V3 corner = mat_vec(mat2, vec);
+            const float ldist = dot(nrm, corner);
+            if (dist + ldist > margin || ldist > 0.f) continue;
+            rc[n].dist = dist + ldist;
+            rc[n].pos = corner + pos2 - (0.5f * rc[n].dist) * nrm;
+            rc[n].n = nrm;
+            rc[n].y = v3(0.f, 0.f, 0.f);
+            n++;
+          }
+        }
+      } else if (t1 == DMB_GEOM_SPHERE && t2 == DMB_GEOM_SPHERE) {
+        n = raw_sphere_sphere(rc[0], margin, pos1, s1.x, pos2, s2.x);
+      } else if (t1 == DMB_GEOM_SPHERE && t2 == DMB_GEOM_CAPSULE) {
+        const V3 axis = v3(mat2[2], mat2[5], mat2[8]);
+        const float x = clampf(dot(axis, pos1 - pos2), -s2.y, s2.y);
+        n = raw_sphere_sphere(rc[0], margin, pos1, s1.x, pos2 + x * axis, s2.x);
+      } else if (t1 == DMB_GEOM_SPHERE && t2 == DMB_GEOM_BOX) {
+        n = raw_sphere_box(rc[0], margin, pos1, s1.x, pos2, mat2, s2);
+      } else if (t1 == DMB_GEOM_CAPSULE && t2 == DMB_GEOM_CAPSULE) {
+        n = raw_capsule_capsule(rc, margin, pos1, mat1, s1.x, s1.y, pos2, mat2, s2.x, s2.y);
+      } else if (t1 == DMB_GEOM_CAPSULE && t2 == DMB_GEOM_BOX) {
+        n = raw_capsule_box(rc, margin, pos1, mat1, s1.x, s1.y, pos2, mat2, s2);
+      } else if (t1 == DMB_GEOM_BOX && t2 == DMB_GEOM_BOX) {
+        n = raw_box_box(rc, margin, pos1, mat1, s1, pos2, mat2, s2);
+      }
+    }
+    const int incl = warp_incl_scan(n, lane);
+    const int total = __shfl_sync(DMB_FULL, incl, 31);
+    const int off = ncon + incl - n;
+    for (int i = 0; i < n; i++) {
+      const int ci = off + i;
+      if (ci < M.max_con) {
+        S.c_dist[ci] = rc[i].dist;
+        st3(&S.c_pos[3 * ci], rc[i].pos);
+        make_frame(&S.c_frame[9 * ci], rc[i].n, rc[i].y);
+        S.c_g1[ci] = g1; S.c_g2[ci] = g2;
+        const int cd1 = M.geom_condim[g1], cd2 = M.geom_condim[g2];
+        S.c_dim[ci] = cd1 > cd2 ? cd1 : cd2;
+        S.c_mu[ci] = fmaxf(M.geom_mu[g1], M.geom_mu[g2]);
+      }
+    }
+    ncon += total;
+  }
+  if (ncon > M.max_con) { ncon = M.max_con; if (lane == 0) S.flags |= 1; }
+  if (lane == 0) S.ncon = ncon;
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_makeConstraint + mj_makeImpedance + mj_referenceConstraint, producing
+//   Y rows 0..nefc-1 = J rows (lane = dof), row nefc = qfrc_smooth,
+//   per-row pos / margin / R / aref (lane = row).
+// Limit rows come first (joint order, lower then upper), then contacts in contact order:
+// 1 frictionless row (condim 1) or 4 pyramid edges (condim 3).
+// ------------------------------------------------------------------------------------------
+__device__ void make_constraint(const ModelS& M, EnvS& S, int lane) {
+  int* e_src = S.e_src;
+  // ---- joint limits: lane = joint
+  int cnt = 0;
+  float dlo = 0.f, dhi = 0.f;
+  int dofj = 0;
+  if (lane < M.njnt && M.jnt_limited[lane] && M.jnt_type[lane] == DMB_JNT_HINGE) {
+    const float q = S.qpos[M.jnt_qposadr[lane]];
+    dofj = M.jnt_dofadr[lane];
+    dlo = q - M.jnt_range[lane][0];
+    dhi = M.jnt_range[lane][1] - q;
+    cnt = (dlo < 0.f) + (dhi < 0.f);
+  }
+  const int incl = warp_incl_scan(cnt, lane);
+  const int nlimit = __shfl_sync(DMB_FULL, incl, 31);
+  {
+    int r = incl - cnt;
+    if (dlo < 0.f && cnt) { S.e_pos[r] = dlo; S.e_margin[r] = 0.f; e_src[r] = -(1 + dofj) * 2; r++; }      // J = +1
+    if (dhi < 0.f && cnt) { S.e_pos[r] = dhi; S.e_margin[r] = 0.f; e_src[r] = -(1 + dofj) * 2 - 1; }       // J = -1
+  }
+  // ---- contact row addresses: lane = contact
+  int ncon = S.ncon;
+  int nrow = 0;
+  if (lane < ncon) nrow = S.c_dim[lane] == 1 ? 1 : 4;
+  const int cincl = warp_incl_scan(nrow, lane);
+  int adr = nlimit + cincl - nrow;
+  const bool fits = lane < ncon && adr + nrow <= M.max_efc;
+  const unsigned fitbal = __ballot_sync(DMB_FULL, fits);
+  // contacts are dropped from the first one that does not fit (oracle: make_constraint)
+  const unsigned wantbal = ncon >= 32 ? 0xffffffffu : ((1u << ncon) - 1u);
+  if (fitbal != wantbal) {
+    const int firstbad = __ffs(~fitbal & wantbal) - 1;
+    ncon = firstbad;
+    if (lane == 0) { S.flags |= 2; S.ncon = ncon; }
+  }
+  int nefc = nlimit;
+  if (ncon > 0) {
+    const int lastadr = __shfl_sync(DMB_FULL, adr + nrow, ncon - 1);
+    nefc = lastadr;
+  }
+  if (lane < ncon) {
+    S.c_adr[lane] = adr;
+    for (int k = 0; k < nrow; k++) { e_src[adr + k] = lane * 4 + k; S.e_pos[adr + k] = S.c_dist[lane]; S.e_margin[adr + k] = M.margin; }
+  }
+  if (lane == 0) { S.nefc = nefc; S.nlimit = nlimit; }
+  __syncwarp();
+  // ---- J rows into Y: lane = dof
+  const V3 com = ld3(S.com);
+  for (int d = lane; d < M.nv; d += 32) {
+    for (int r = 0; r < nlimit; r++) {
+      const int src = -e_src[r];          // 2*(1+dof) or 2*(1+dof)+1
+      const int dof = (src >> 1) - 1;
+      S.Y[r * YS + d] = (dof == d) ? ((src & 1) ? -1.f : 1.f) : 0.f;
+    }
+    const V3 ca = ld3(&S.cdof[6 * d]), cl = ld3(&S.cdof[6 * d + 3]);
+    for (int c = 0; c < ncon; c++) {
+      const int b1 = M.geom_bodyid[S.c_g1[c]], b2 = M.geom_bodyid[S.c_g2[c]];
+      const int in2 = (int)((M.body_dofmask[b2] >> d) & 1ull), in1 = (int)((M.body_dofmask[b1] >> d) & 1ull);
+      const float sg = (float)(in2 - in1);
+      const int a = S.c_adr[c];
+      const float* fr = &S.c_frame[9 * c];
+      if (S.c_dim[c] == 1) {
+        float jn = 0.f;
+        if (sg != 0.f) { const V3 p = cl + cross(ca, ld3(&S.c_pos[3 * c]) - com); jn = sg * dot(ld3(fr), p); }
+        S.Y[a * YS + d] = jn;
+      } else {
+        float jn = 0.f, j1 = 0.f, j2 = 0.f;
+        if (sg != 0.f) {
+          const V3 p = cl + cross(ca, ld3(&S.c_pos[3 * c]) - com);
+          jn = sg * dot(ld3(fr), p); j1 = sg * dot(ld3(fr + 3), p); j2 = sg * dot(ld3(fr + 6), p);
+        }
+        const float mu = S.c_mu[c];
+        S.Y[a * YS + d] = jn + mu * j1;
+        S.Y[(a + 1) * YS + d] = jn - mu * j1;
+        S.Y[(a + 2) * YS + d] = jn + mu * j2;
+        S.Y[(a + 3) * YS + d] = jn - mu * j2;
+      }
+    }
+    S.Y[nefc * YS + d] = S.vec0[d];  // smooth force rides along as the last row
+  }
+  // ---- per-row impedance, R, aref: lane = row
+  for (int r = lane; r < nefc; r += 32) {
+    const int src = e_src[r];
+    float dA, vel, mu = 0.f;
+    bool pyramid = false;
+    if (src < 0) {
+      const int s2 = -src, dof = (s2 >> 1) - 1;
+      dA = M.dof_invw[dof];
+      vel = (s2 & 1) ? -S.qvel[dof] : S.qvel[dof];
+    } else {
+      const int c = src >> 2, k = src & 3;
+      const int b1 = M.geom_bodyid[S.c_g1[c]], b2 = M.geom_bodyid[S.c_g2[c]];
+      const float tran = M.body_invw[b1] + M.body_invw[b2];
+      const V3 off = ld3(&S.c_pos[3 * c]) - com;
+      const V3 v2 = ld3(&S.cvel[6 * b2 + 3]) + cross(ld3(&S.cvel[6 * b2]), off);
+      const V3 v1 = ld3(&S.cvel[6 * b1 + 3]) + cross(ld3(&S.cvel[6 * b1]), off);
+      const V3 vr = v2 - v1;
+      const float* fr = &S.c_frame[9 * c];
+      const float vn = dot(ld3(fr), vr);
+      if (S.c_dim[c] == 1) { dA = tran; vel = vn; }
+      else {
+        pyramid = true;
+        mu = S.c_mu[c];
+        const float vt = dot(ld3(fr + 3 * (1 + (k >> 1))), vr);
+        vel = vn + ((k & 1) ? -mu : mu) * vt;
+        dA = tran + mu * mu * tran;
+      }
+    }
+    // getimpedance (solimp sigmoid)
+    const float pos = S.e_pos[r], mg = S.e_margin[r];
+    float dmin = clampf(M.solimp[0], 0.0001f, 0.9999f), dmax = clampf(M.solimp[1], 0.0001f, 0.9999f);
+    const float width = M.solimp[2], mid = clampf(M.solimp[3], 0.0001f, 0.9999f), power = fmaxf(M.solimp[4], 1.f);
+    float imp;
+    if (dmin == dmax || width <= DMB_MINVAL) imp = 0.5f * (dmin + dmax);
+    else {
+      const float x = fabsf((pos - mg) / width);
+      if (x >= 1.f) imp = dmax;
+      else if (x == 0.f) imp = dmin;
+      else {
+        float y;
+        if (power == 1.f) y = x;
+        else if (power == 2.f) y = x <= mid ? x * x / mid : 1.f - (1.f - x) * (1.f - x) / (1.f - mid);
+        else y = x <= mid ? powf(x, power) / powf(mid, power - 1.f) : 1.f - powf(1.f - x, power) / powf(1.f - mid, power - 1.f);
+        imp = dmin + y * (dmax - dmin);
+      }
+    }
+    float R = fmaxf((1.f - imp) * dA / imp, DMB_MINVAL);
+    if (pyramid) R = 2.f * mu * mu * R;
+    S.e_R[r] = R;
+    S.e_aref[r] = -M.imp_b * vel - M.imp_k * imp * (pos - mg);
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// Half solve  Y_r <- D^-1/2 L^-T Y_r  for all rows at once: lane = row, serial over dofs with
+// warp-uniform loop bounds (L entries are broadcast reads).  Dofs on which no row of the pass
+// has support are skipped with one vote.  Also builds the per-row support masks.
+// ------------------------------------------------------------------------------------------
+__device__ void half_solve_rows(const ModelS& M, EnvS& S, int lane, int nrows) {
+  for (int base = 0; base < nrows; base += 32) {
+    const int r = base + lane;
+    const bool act = r < nrows;
+    float* y = &S.Y[(act ? r : 0) * YS];
+    for (int i = M.nv - 1; i >= 0; i--) {
+      const float yi = act ? y[i] : 0.f;
+      if (!__any_sync(DMB_FULL, yi != 0.f)) continue;
+      const int c = M.dof_nanc[i], adr = M.dof_Madr[i] + 1;
+      if (act) {
+        for (int k = 0; k < c; k++) y[M.dof_anc[i][k]] -= S.qLD[adr + k] * yi;
+      }
+    }
+    unsigned long long mask = 0ull;
+    if (act) {
+      for (int i = 0; i < M.nv; i++) {
+        const float v = y[i] * S.dsq[i];
+        y[i] = v;
+        if (v != 0.f) mask |= 1ull << i;
+      }
+      S.rowmask[r] = mask;
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
+
+// Gram matrix AR = Y Y' + diag(R) (packed lower triangle), b = Y y_s - aref.  lane = row.
+__device__ void gram(const ModelS& M, EnvS& S, int lane, int nefc) {
+  for (int base = 0; base < nefc; base += 32) {
+    const int r = base + lane;
+    const bool act = r < nefc;
+    const float* yr = &S.Y[(act ? r : 0) * YS];
+    const int smax = min(nefc - 1, base + 31);
+    for (int s = 0; s <= smax; s++) {
+      unsigned long long mk = S.rowmask[s];
+      const float* ys = &S.Y[s * YS];
+      float acc = 0.f;
+      while (mk) {
+        const int k = __ffsll((long long)mk) - 1;
+        mk &= mk - 1;
+        acc += yr[k] * ys[k];
+      }
+      if (act && s <= r) S.AR[tri(r) + s] = (s == r) ? acc + S.e_R[r] : acc;
+    }
+    {  // b
+      unsigned long long mk = S.rowmask[nefc];
+      const float* ys = &S.Y[nefc * YS];
+      float acc = 0.f;
+      while (mk) {
+        const int k = __ffsll((long long)mk) - 1;
+        mk &= mk - 1;
+        acc += yr[k] * ys[k];
+      }
+      if (act) S.e_b[r] = acc - S.e_aref[r];
+    }
+  }
+  __syncwarp();
+}
+
+// single-vector ops on the sparse factor, lane = ancestor slot
+// x <- D^1/2 L x   (z-space image of an acceleration)
+__device__ void mul_L_sqrtD(const ModelS& M, EnvS& S, int lane, const float* x, float* z) {
+  for (int i = lane; i < M.nv; i += 32) {
+    const int c = M.dof_nanc[i], adr = M.dof_Madr[i] + 1;
+    float s = x[i];
+    for (int k = 0; k < c; k++) s += S.qLD[adr + k] * x[M.dof_anc[i][k]];
+    z[i] = s / S.dsq[i];
+  }
+  __syncwarp();
+}
+// x <- L^-1 D^-1/2 t   (back substitution root -> leaves; reduction over <= MAXANC ancestors)
+__device__ void back_solve(const ModelS& M, EnvS& S, int lane, float* t) {
+  for (int i = lane; i < M.nv; i += 32) t[i] *= S.dsq[i];
+  __syncwarp();
+  for (int i = 0; i < M.nv; i++) {
+    const int c = M.dof_nanc[i];
+    if (c == 0) continue;
+    float part = 0.f;
+    if (lane < c) part = S.qLD[M.dof_Madr[i] + 1 + lane] * t[M.dof_anc[i][lane]];
+    // c <= 12 < 16: reduce over the low half-warp
+    part += __shfl_xor_sync(DMB_FULL, part, 8);
+    part += __shfl_xor_sync(DMB_FULL, part, 4);
+    part += __shfl_xor_sync(DMB_FULL, part, 2);
+    part += __shfl_xor_sync(DMB_FULL, part, 1);
+    if (lane == 0) t[i] -= part;
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mj_fwdConstraint: warmstart + PGS on the dual (all rows are scalar, force >= 0), then
+// qacc = L^-1 D^-1/2 (y_s + Y' f).  Residuals res = AR f + b live in registers (lane = row and
+// row+32); a row update broadcasts its force increment and every lane applies one column of AR.
+// ------------------------------------------------------------------------------------------
+__device__ void solve_constraints(const ModelS& M, EnvS& S, int lane, int nefc) {
+  const int r0 = lane, r1 = lane + 32;
+  const bool a0 = r0 < nefc, a1 = r1 < nefc;
+  float f0 = 0.f, f1 = 0.f, res0 = 0.f, res1 = 0.f;
+  int iter = 0;
+  if (nefc > 0) {
+    // warmstart forces from qacc_warmstart: jar = J qacc_w - aref = Y (D^1/2 L qacc_w) - aref
+    mul_L_sqrtD(M, S, lane, S.warm, S.vec1);
+    float jar0 = 0.f, jar1 = 0.f;
+    if (a0) { const float* y = &S.Y[r0 * YS]; for (int k = 0; k < M.nv; k++) jar0 += y[k] * S.vec1[k]; jar0 -= S.e_aref[r0]; }
+    if (a1) { const float* y = &S.Y[r1 * YS]; for (int k = 0; k < M.nv; k++) jar1 += y[k] * S.vec1[k]; jar1 -= S.e_aref[r1]; }
+    f0 = (a0 && jar0 < 0.f) ? -jar0 / S.e_R[r0] : 0.f;
+    f1 = (a1 && jar1 < 0.f) ? -jar1 / S.e_R[r1] : 0.f;
+    if (a0) S.e_f[r0] = f0;
+    if (a1) S.e_f[r1] = f1;
+    __syncwarp();
+    // res = AR f + b ; cost = sum f (0.5 (res - b) + b)
+    const float b0 = a0 ? S.e_b[r0] : 0.f, b1 = a1 ? S.e_b[r1] : 0.f;
+    res0 = b0; res1 = b1;
+    for (int s = 0; s < nefc; s++) {
+      const float fs = S.e_f[s];
+      if (fs != 0.f) {
+        if (a0) res0 += S.AR[r0 >= s ? tri(r0) + s : tri(s) + r0] * fs;
+        if (a1) res1 += S.AR[r1 >= s ? tri(r1) + s : tri(s) + r1] * fs;
+      }
+    }
+    float cost = f0 * 0.5f * (res0 + b0) + f1 * 0.5f * (res1 + b1);
+    cost = warp_sum(cost);
+    if (cost > 0.f) { f0 = 0.f; f1 = 0.f; res0 = b0; res1 = b1; }
+    const float d0 = a0 ? S.AR[tri(r0) + r0] : 1.f, d1 = a1 ? S.AR[tri(r1) + r1] : 1.f;
+    const float inv0 = 1.0f / d0, inv1 = 1.0f / d1;
+    // PGS sweeps
+    while (iter < M.iterations) {
+      float imp = 0.f;
+      for (int i = 0; i < nefc; i++) {
+        const int ol = i & 31;
+        const bool hi = i >= 32;
+        const float myres = hi ? res1 : res0, myf = hi ? f1 : f0, myinv = hi ? inv1 : inv0;
+        const float fnew = fmaxf(0.f, myf - myres * myinv);
+        const float delta = __shfl_sync(DMB_FULL, fnew - myf, ol);
+        if (delta != 0.f) {
+          if (lane == ol) {
+            imp -= 0.5f * delta * delta * (hi ? d1 : d0) + delta * myres;
+            if (hi) f1 = fnew; else f0 = fnew;
+          }
+          res0 += S.AR[r0 >= i ? tri(r0) + i : tri(i) + r0] * delta;
+          if (nefc > 32) res1 += S.AR[r1 >= i ? tri(r1) + i : tri(i) + r1] * delta;
+        }
+      }
+      iter++;
+      imp = warp_sum(imp) * M.pgs_scale;
+      if (imp < M.tolerance) break;
+    }
+    if (a0) S.e_f[r0] = f0;
+    if (a1) S.e_f[r1] = f1;
+    __syncwarp();
+  }
+  if (lane == 0) S.iter = iter;
+  // t = y_s + sum_r Y_r f_r  (lane = dof)
+  for (int d = lane; d < M.nv; d += 32) {
+    float t = S.Y[nefc * YS + d];
+    for (int r = 0; r < nefc; r++) {
+      const float fr = S.e_f[r];
+      if (fr != 0.f) t += S.Y[r * YS + d] * fr;
+    }
+    S.qacc[d] = t;
+  }
+  __syncwarp();
+  back_solve(M, S, lane, S.qacc);
+  for (int d = lane; d < M.nv; d += 32) S.warm[d] = S.qacc[d];
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// One full forward evaluation (mj_forward) at (S.qpos, S.qvel, S.ctrlf, S.warm) -> S.qacc.
+// Returns the whole-body CoM height of this evaluation (what DPEnv.is_done reads from the
+// stale mjData.xipos after mj_step, dp_env_v3.py:134-139).
+// ------------------------------------------------------------------------------------------
+__device__ float forward_eval(const ModelS& M, EnvS& S, int lane, float* dbgrow) {
+  kinematics(M, S, lane);
+  com_pos(M, S, lane);
+  crb_factor(M, S, lane, dbgrow ? dbgrow + dbg::qM : nullptr);
+  smooth_forces(M, S, lane, dbgrow ? dbgrow + dbg::qfrc_bias : nullptr);
+  collision(M, S, lane);
+  make_constraint(M, S, lane);
+  const int nefc = S.nefc;
+  half_solve_rows(M, S, lane, nefc + 1);
+  gram(M, S, lane, nefc);
+  if (dbgrow) {
+    // qacc_smooth = L^-1 D^-1/2 y_s for the dump (not needed by the solver)
+    for (int d = lane; d < M.nv; d += 32) S.vec1[d] = S.Y[nefc * YS + d];
+    __syncwarp();
+    back_solve(M, S, lane, S.vec1);
+    for (int d = lane; d < M.nv; d += 32) { dbgrow[dbg::qacc_smooth + d] = S.vec1[d]; dbgrow[dbg::qfrc_smooth + d] = S.vec0[d]; }
+    for (int e = lane; e < M.nM; e += 32) dbgrow[dbg::qLD + e] = S.qLD[e];
+    for (int r = lane; r < nefc; r += 32) {
+      dbgrow[dbg::efc_pos + r] = S.e_pos[r]; dbgrow[dbg::efc_R + r] = S.e_R[r];
+      dbgrow[dbg::efc_aref + r] = S.e_aref[r]; dbgrow[dbg::efc_b + r] = S.e_b[r];
+      dbgrow[dbg::efc_AR_diag + r] = S.AR[tri(r) + r];
+    }
+    __syncwarp();
+  }
+  solve_constraints(M, S, lane, nefc);
+  return S.com[2];
+}
+
+}  // namespace dmb

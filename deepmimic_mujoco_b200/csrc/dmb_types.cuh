@@ -1,0 +1,129 @@
+// dmb_types.cuh -- device-side (fp32) model tables and per-env shared-memory tile.
+//
+// One warp owns one env.  Everything an env needs during one RK4 step lives in its EnvS
+// tile in shared memory; the fp32 model (ModelS) is copied once per CTA into shared memory
+// because most of its tables are indexed per lane (body / dof / geom ids), which the
+// constant cache would serialise.
+#pragma once
+#include <cstdint>
+
+#include "../../include/dmb.h"
+
+namespace dmb {
+
+constexpr int NB = DMB_MAX_BODY;  // 16
+constexpr int NJ = DMB_MAX_JNT;   // 32
+constexpr int NVC = 36;           // dof capacity of the kernel (nv <= 36; humanoid: 34)
+constexpr int NQC = 40;
+constexpr int NG = DMB_MAX_GEOM;  // 16
+constexpr int NP = DMB_MAX_PAIR;  // 128
+constexpr int NU = DMB_MAX_U;     // 32
+constexpr int NMX = DMB_MAX_M;    // 320
+constexpr int MAXANC = 12;        // longest dof ancestor chain (humanoid: 12)
+constexpr int MAXROW = 64;        // constraint rows (<= 63) + 1 row for the smooth force
+constexpr int MAXC = 24;          // contact capacity per env
+constexpr int YS = 37;            // row stride of Y (odd -> conflict-free lane=row access)
+constexpr int NTRI = (MAXROW - 1) * MAXROW / 2;  // packed lower triangle of AR (63 rows)
+constexpr int JPB = 3;            // joints per body capacity
+
+enum DofKind : int8_t { DOF_FREE_TRANS = 0, DOF_FREE_ROT = 1, DOF_HINGE = 2 };
+
+struct ModelS {
+  // sizes / options
+  int nq, nv, nu, nbody, njnt, ngeom, npair, nM;
+  int iterations, max_con, max_efc, maxdepth;
+  int nclip, nframe_total, nee, pad_i;
+  float timestep, tolerance, pgs_scale, margin;
+  float gravity[3], inv_total_mass;
+  float imp_k, imp_b;        // reference spring constants after refsafe (mj_makeImpedance)
+  float solimp[5], pad_f;
+  // bodies
+  int8_t body_parent[NB], body_depth[NB], body_jntadr[NB], body_jntnum[NB], body_dofadr[NB], body_dofnum[NB];
+  int8_t body_nchild[NB], body_child[NB][4];
+  float body_pos[NB][3], body_quat[NB][4], body_ipos[NB][3], body_inertia[NB][6], body_mass[NB], body_invw[NB];
+  unsigned long long body_dofmask[NB];  // dofs on the chain world..b (inclusive)
+  // joints
+  int8_t jnt_type[NJ], jnt_qposadr[NJ], jnt_dofadr[NJ], jnt_limited[NJ], jnt_bodyid[NJ];
+  float jnt_axis[NJ][3], jnt_range[NJ][2], jnt_qpos0[NJ];
+  // dofs
+  int8_t dof_bodyid[NVC], dof_kind[NVC], dof_axisk[NVC], dof_nanc[NVC], dof_anc[NVC][MAXANC], dof_act[NVC];
+  int16_t dof_Madr[NVC];
+  unsigned long long dof_velmask[NVC];  // dofs summed into the velocity seen by cdof_dot (mj_comVel)
+  float dof_armature[NVC], dof_damping[NVC], dof_invw[NVC], dof_gear[NVC], dof_ctrl_lo[NVC], dof_ctrl_hi[NVC];
+  float dof_kp[NVC], dof_kd[NVC], dof_weight[NVC];
+  // inertia entries
+  uint8_t M_i[NMX], M_j[NMX];
+  uint8_t tri_p[80], tri_q[80];  // pair decode for the sparse L'DL update (q-major)
+  // geoms
+  int8_t geom_type[NG], geom_bodyid[NG], geom_condim[NG], geom_identq[NG];
+  float geom_size[NG][3], geom_pos[NG][3], geom_quat[NG][4], geom_rbound[NG], geom_mu[NG];
+  uint8_t pair_g1[NP], pair_g2[NP];
+  // actuators
+  int8_t act_dofadr[NU];
+  // env config
+  int ctrl_mode, reward_mode, reset_mode, auto_reset;
+  float z_min, z_max, reset_noise, pd_dt;
+  float w_pose, w_vel, w_ee, w_root, w_com, s_pose, s_vel, s_ee, s_root, s_com, s_err, pad_g;
+  // reference pose
+  float qpos0[NQC];
+  // end effectors + clips
+  int ee_body[DMB_MAX_EE];
+  float ee_pos[DMB_MAX_EE][3];
+  int clip_start[DMB_MAX_CLIP], clip_len[DMB_MAX_CLIP];
+};
+
+// Per-env tile.  fp32.  Layout notes: Y rows have an odd stride so that lane=row accesses hit
+// 32 different banks; AR is the packed lower triangle (row r starts at r(r+1)/2).
+struct EnvS {
+  float qpos[NQC], qvel[NQC], ctrlf[NQC];
+  float xpos[NB * 3], xquat[NB * 4], xmat[NB * 9], xipos[NB * 3];
+  float com[4];
+  float cinert[NB * 10], crb[NB * 10];
+  float cdof[NVC * 6], cdofd[NVC * 6], buf6[NVC * 6];
+  float qLD[NMX], dinv[NVC], dsq[NVC];
+  float cvel[NB * 6], cacc[NB * 6], cfrc[NB * 6];
+  float gpos[NG * 3], gmat[NG * 9];
+  float vec0[NQC], vec1[NQC], qacc[NQC], warm[NQC];
+  // contacts
+  float c_dist[MAXC], c_pos[MAXC * 3], c_frame[MAXC * 9], c_mu[MAXC];
+  int c_g1[MAXC], c_g2[MAXC], c_dim[MAXC], c_adr[MAXC];
+  // constraint rows
+  float Y[MAXROW * YS];
+  float AR[NTRI + MAXROW];
+  float e_pos[MAXROW], e_margin[MAXROW], e_R[MAXROW], e_aref[MAXROW], e_b[MAXROW], e_f[MAXROW];
+  unsigned long long rowmask[MAXROW];
+  int surv[NP];  // surviving broad-phase pairs
+  int e_src[MAXROW];  // row source: >=0 contact*4+edge, <0 joint limit (see make_constraint)
+  // RK4 bookkeeping: X0, weighted sums of stage velocities / accelerations, stage increment
+  float x_q0[NQC], x_v0[NQC], x_sv[NQC], x_sa[NQC], x_dv[NQC];
+  int ncon, nefc, nlimit, flags, iter, nsurv, pad0, pad1;
+};
+
+// Debug row layout (floats) for dmb_forward_debug
+namespace dbg {
+constexpr int xpos = 0;                     // NB*3
+constexpr int xquat = xpos + NB * 3;        // NB*4
+constexpr int xipos = xquat + NB * 4;       // NB*3
+constexpr int com = xipos + NB * 3;         // 4
+constexpr int qM = com + 4;                 // NMX
+constexpr int qLD = qM + NMX;               // NMX
+constexpr int qfrc_bias = qLD + NMX;        // NQC
+constexpr int qfrc_smooth = qfrc_bias + NQC;
+constexpr int qacc_smooth = qfrc_smooth + NQC;
+constexpr int ncon = qacc_smooth + NQC;     // 1
+constexpr int nefc = ncon + 1;
+constexpr int iter = nefc + 1;
+constexpr int z_com = iter + 1;
+constexpr int contact = z_com + 1;          // MAXC * 16: dist, pos3, frame9, g1, g2, dim
+constexpr int efc_pos = contact + MAXC * 16;
+constexpr int efc_R = efc_pos + MAXROW;
+constexpr int efc_aref = efc_R + MAXROW;
+constexpr int efc_b = efc_aref + MAXROW;
+constexpr int efc_force = efc_b + MAXROW;
+constexpr int efc_AR_diag = efc_force + MAXROW;
+constexpr int qacc = efc_AR_diag + MAXROW;  // NQC
+constexpr int cvel = qacc + NQC;            // NB*6
+constexpr int stride = cvel + NB * 6;
+}  // namespace dbg
+
+}  // namespace dmb

@@ -1,0 +1,203 @@
+"""BatchedSim: env-major batched state in PyTorch CUDA tensors + the libdmb200 C-ABI.
+
+This is the host side of the hot path: it owns the state tensors (qpos/qvel/warmstart/phase/...),
+passes raw device pointers through ctypes and enqueues every call on torch's current CUDA stream.
+There is no CPU fallback: constructing a BatchedSim without a CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+from .mjcf import ModelTables, load_tables
+from .mocap import Clip, MocapTables, concat_clips, load_clip
+from .model_blob import REF_AUX, DmbConfig, DmbMocap, DmbModel, default_config, pack_model
+
+ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
+
+
+def default_model_tables() -> ModelTables:
+    """Compiled dp_env_v3.xml tables shipped with the repo (tools/build_assets.py)."""
+    return load_tables(os.path.join(ASSETS, "dp_env_v3.model.npz"))
+
+
+def motion_path(name: str) -> str:
+    return os.path.join(ASSETS, "motions", name + ".npz")
+
+
+def load_motions(names: Sequence[str]) -> MocapTables:
+    clips = []
+    for n in names:
+        clips.append(load_clip(n) if os.path.exists(n) else load_clip(motion_path(n), name=n))
+    return concat_clips(clips)
+
+
+def make_mocap_struct(mc: MocapTables, ref_aux: Optional[np.ndarray] = None):
+    """DmbMocap + the numpy arrays that back its pointers (keep them alive)."""
+    cfg = np.ascontiguousarray(mc.data_config, dtype=np.float64)
+    vel = np.ascontiguousarray(np.nan_to_num(mc.data_vel, nan=0.0, posinf=0.0, neginf=0.0), dtype=np.float64)
+    aux = np.zeros((cfg.shape[0], REF_AUX)) if ref_aux is None else np.ascontiguousarray(ref_aux, dtype=np.float64)
+    s = DmbMocap()
+    s.nclip, s.nframe_total = len(mc.names), cfg.shape[0]
+    for k in range(len(mc.names)):
+        s.clip_start[k], s.clip_len[k], s.clip_dt[k] = int(mc.clip_start[k]), int(mc.clip_len[k]), float(mc.clip_dt[k])
+    dp = C.POINTER(C.c_double)
+    s.data_config, s.data_vel, s.ref_aux = cfg.ctypes.data_as(dp), vel.ctypes.data_as(dp), aux.ctypes.data_as(dp)
+    return s, (cfg, vel, aux)
+
+
+class BatchedSim:
+    """N envs on one GPU.  All tensors are CUDA, env-major, contiguous."""
+
+    def __init__(self, num_envs: int, motions: Sequence[str] = ("walk",), device: Optional[torch.device] = None,
+                 seed: int = 0, first_env_id: int = 0, config: Optional[DmbConfig] = None,
+                 model_tables: Optional[ModelTables] = None, clip_ids: Optional[torch.Tensor] = None,
+                 max_con: int = 24, max_efc: int = 63, ref_aux: Optional[np.ndarray] = None):
+        if not torch.cuda.is_available():
+            raise _lib.DmbError("BatchedSim needs a CUDA device: the hot path has no CPU fallback")
+        self.L = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.N = int(num_envs)
+        self.tables = model_tables if model_tables is not None else default_model_tables()
+        self.model: DmbModel = pack_model(self.tables, max_con=max_con, max_efc=max_efc)
+        self.config: DmbConfig = config if config is not None else default_config()
+        self.mocap: MocapTables = load_motions(list(motions))
+        self._mc_struct, self._mc_keep = make_mocap_struct(self.mocap, ref_aux)
+        self.nq, self.nv, self.nu = self.tables.nq, self.tables.nv, self.tables.nu
+        self.obs_dim = (self.nq - 7) + (self.nv - 6)
+        self.handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.dmb_create(C.byref(self.model), C.byref(self.config), C.byref(self._mc_struct), self.N,
+                                         self.device.index, C.c_uint64(seed), C.c_uint32(first_env_id),
+                                         C.byref(self.handle)), None, "dmb_create")
+        d, N = self.device, self.N
+        f32, i32 = torch.float32, torch.int32
+        self.qpos = torch.zeros(N, _lib.QSTRIDE, dtype=f32, device=d)
+        self.qvel = torch.zeros(N, _lib.VSTRIDE, dtype=f32, device=d)
+        self.warm = torch.zeros(N, _lib.VSTRIDE, dtype=f32, device=d)
+        self.clip = torch.zeros(N, dtype=i32, device=d) if clip_ids is None else clip_ids.to(d, i32).contiguous()
+        self.idx_init = torch.zeros(N, dtype=i32, device=d)
+        self.idx_curr = torch.zeros(N, dtype=i32, device=d)
+        self.reset_count = torch.zeros(N, dtype=i32, device=d)  # bit pattern of uint32
+        self.ep_len = torch.zeros(N, dtype=i32, device=d)
+        self.ep_ret = torch.zeros(N, dtype=f32, device=d)
+        self.flags = torch.zeros(N, dtype=i32, device=d)
+        self.obs = torch.zeros(N, self.obs_dim, dtype=f32, device=d)
+        self.reward = torch.zeros(N, dtype=f32, device=d)
+        self.done = torch.zeros(N, dtype=torch.uint8, device=d)
+        self.rec = torch.zeros(N, self.obs_dim + 2, dtype=f32, device=d)
+        self.last_ret = torch.zeros(N, dtype=f32, device=d)
+        self.last_len = torch.zeros(N, dtype=i32, device=d)
+        self._st = _lib.DmbState(*[t.data_ptr() for t in (self.qpos, self.qvel, self.warm, self.clip, self.idx_init,
+                                                           self.idx_curr, self.reset_count, self.ep_len, self.ep_ret,
+                                                           self.flags)])
+        self._out = _lib.DmbStepOut(self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                                    self.rec.data_ptr(), self.last_ret.data_ptr(), self.last_len.data_ptr())
+        qpos0 = torch.tensor(self.tables.qpos0, dtype=f32, device=d)
+        self.qpos[:, : self.nq] = qpos0
+
+    # ------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.L.dmb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_info(self) -> Dict[str, int]:
+        g, b, s, w = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        self.L.dmb_launch_info(self.handle, C.byref(g), C.byref(b), C.byref(s), C.byref(w))
+        return dict(grid=g.value, block=b.value, smem_bytes=s.value, envs_per_cta=w.value)
+
+    # ------------------------------------------------------------------------------------
+    def reset(self, mask: Optional[torch.Tensor] = None, mode: int = -1) -> torch.Tensor:
+        """(Re)initialise envs (all, or where mask != 0); returns the observation tensor [N,56]."""
+        mp = None
+        if mask is not None:
+            mask = mask.to(self.device, torch.uint8).contiguous()
+            mp = C.c_void_p(mask.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.dmb_reset(self.handle, C.byref(self._st), mp, mode, C.c_void_p(self.obs.data_ptr()),
+                                        self._stream()), self.handle, "dmb_reset")
+        return self.obs
+
+    def step(self, action: torch.Tensor):
+        """One env step for all envs.  action: CUDA float32 [N, nu].  Returns (obs, reward, done) tensors
+        (views of internal buffers, overwritten by the next call)."""
+        if action.device != self.device or action.dtype != torch.float32 or not action.is_contiguous() \
+                or tuple(action.shape) != (self.N, self.nu):
+            raise ValueError("action must be a contiguous CUDA float32 tensor of shape [N, nu] on the sim's device")
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.dmb_step(self.handle, C.byref(self._st), C.c_void_p(action.data_ptr()),
+                                       C.byref(self._out), self._stream()), self.handle, "dmb_step")
+        return self.obs, self.reward, self.done
+
+    def get_obs(self) -> torch.Tensor:
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.dmb_get_obs(self.handle, C.byref(self._st), C.c_void_p(self.obs.data_ptr()),
+                                          self._stream()), self.handle, "dmb_get_obs")
+        return self.obs
+
+    def set_state(self, qpos, qvel, warm=None, idx_curr=None):
+        """Overwrite state from arrays [N,nq] / [N,nv] (numpy or torch, any float dtype)."""
+        q = torch.as_tensor(np.asarray(qpos) if not torch.is_tensor(qpos) else qpos).to(self.device, torch.float32)
+        v = torch.as_tensor(np.asarray(qvel) if not torch.is_tensor(qvel) else qvel).to(self.device, torch.float32)
+        self.qpos.zero_(); self.qvel.zero_()
+        self.qpos[:, : self.nq] = q
+        self.qvel[:, : self.nv] = v
+        self.warm.zero_()
+        if warm is not None:
+            w = torch.as_tensor(np.asarray(warm) if not torch.is_tensor(warm) else warm).to(self.device, torch.float32)
+            self.warm[:, : self.nv] = w
+        if idx_curr is not None:
+            self.idx_curr.copy_(torch.as_tensor(idx_curr).to(self.device, torch.int32))
+
+    def get_state(self):
+        return (self.qpos[:, : self.nq].double().cpu().numpy(), self.qvel[:, : self.nv].double().cpu().numpy(),
+                self.warm[:, : self.nv].double().cpu().numpy())
+
+    # ------------------------------------------------------------------------------------
+    def forward_debug(self, ctrl: torch.Tensor) -> Dict[str, np.ndarray]:
+        """Run one mj_forward at the current state and return the stage outputs as numpy arrays."""
+        stride = self.L.dmb_debug_stride()
+        dbg = torch.zeros(self.N, stride, dtype=torch.float32, device=self.device)
+        ctrl = ctrl.to(self.device, torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.dmb_forward_debug(self.handle, C.byref(self._st), C.c_void_p(ctrl.data_ptr()),
+                                                C.c_void_p(dbg.data_ptr()), self._stream()), self.handle,
+                       "dmb_forward_debug")
+        h = dbg.cpu().numpy().astype(np.float64)
+        off = lambda n: self.L.dmb_debug_offset(n.encode())
+        nb, nv, nM = self.tables.nbody, self.nv, self.tables.nM
+        out = dict(
+            xpos=h[:, off("xpos"): off("xpos") + nb * 3].reshape(-1, nb, 3),
+            xquat=h[:, off("xquat"): off("xquat") + nb * 4].reshape(-1, nb, 4),
+            xipos=h[:, off("xipos"): off("xipos") + nb * 3].reshape(-1, nb, 3),
+            com=h[:, off("com"): off("com") + 3],
+            qM=h[:, off("qM"): off("qM") + nM], qLD=h[:, off("qLD"): off("qLD") + nM],
+            qfrc_bias=h[:, off("qfrc_bias"): off("qfrc_bias") + nv],
+            qfrc_smooth=h[:, off("qfrc_smooth"): off("qfrc_smooth") + nv],
+            qacc_smooth=h[:, off("qacc_smooth"): off("qacc_smooth") + nv],
+            ncon=h[:, off("ncon")].astype(int), nefc=h[:, off("nefc")].astype(int), iter=h[:, off("iter")].astype(int),
+            z_com=h[:, off("z_com")],
+            contact=h[:, off("contact"): off("contact") + 24 * 16].reshape(-1, 24, 16),
+            efc_pos=h[:, off("efc_pos"): off("efc_pos") + 64], efc_R=h[:, off("efc_R"): off("efc_R") + 64],
+            efc_aref=h[:, off("efc_aref"): off("efc_aref") + 64], efc_b=h[:, off("efc_b"): off("efc_b") + 64],
+            efc_force=h[:, off("efc_force"): off("efc_force") + 64],
+            efc_AR_diag=h[:, off("efc_AR_diag"): off("efc_AR_diag") + 64],
+            qacc=h[:, off("qacc"): off("qacc") + nv],
+            cvel=h[:, off("cvel"): off("cvel") + nb * 6].reshape(-1, nb, 6),
+        )
+        return out

@@ -1,0 +1,121 @@
+/* dmb.h -- C-ABI of libdmb200.so: the B200-native batched DeepMimic/MuJoCo env hot path.
+ *
+ * Drop-in boundary for the per-step path of the reference env
+ *   /root/reference/src/dp_env_v3.py:106-132  DPEnv.step
+ *     -> gym MujocoEnv.do_simulation -> mujoco_py MjSim.step -> mj_step   (dp_env_v3.py:112)
+ *     -> DPEnv._get_obs (62-65), DPEnv.is_done (134-139), calc_config_reward (89-104)
+ *   /root/reference/src/dp_env_v3.py:148-164  reset_model / reset_model_init
+ *     -> MujocoEnv.set_state + sim.forward()
+ * i.e. what a maintainer would bind instead of mujoco_py's Cython `cymj` (see INTEGRATION.md
+ * for the ctypes stub).  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative dmb_status; the text of the last
+ *    error is available from dmb_last_error() (per handle, or global for create failures);
+ *  - all array arguments are DEVICE pointers into caller-owned buffers (PyTorch tensors)
+ *    unless the name ends in _host; the library owns only the opaque handle (constant
+ *    tables, launch configuration);
+ *  - env-major rows, fp32: qpos[N][DMB_QSTRIDE], qvel[N][DMB_VSTRIDE], warm[N][DMB_VSTRIDE]
+ *    (strides padded to 16 B multiples), action[N][nu], obs[N][nq-7 + nv-6];
+ *  - all work is enqueued on the caller's CUDA stream (pass torch.cuda.current_stream()
+ *    .cuda_stream, or NULL for the legacy default stream); calls are asynchronous w.r.t.
+ *    the host except create/destroy;
+ *  - a handle is bound to one CUDA device and is not thread-safe.
+ */
+#ifndef DMB_H_
+#define DMB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "dmb_model.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DMB_VERSION 1
+#define DMB_QSTRIDE 36 /* floats per qpos row (nq = 35 padded) */
+#define DMB_VSTRIDE 36 /* floats per qvel / warmstart row (nv = 34 padded) */
+
+typedef enum dmb_status {
+  DMB_OK = 0,
+  DMB_ERR_ARG = -1,      /* bad argument (null pointer, size, mode) */
+  DMB_ERR_CUDA = -2,     /* a CUDA runtime call failed */
+  DMB_ERR_MODEL = -3,    /* model exceeds compiled capacities / unsupported feature */
+  DMB_ERR_NO_DEVICE = -4 /* no CUDA device: there is NO CPU fallback */
+} dmb_status;
+
+typedef struct dmb_handle_s* dmb_handle_t;
+
+/* Per-env state, caller-owned device buffers (all env-major). Replaces the mjData /
+ * DPEnv attributes the reference keeps per env (sim.data.qpos/qvel/qacc_warmstart,
+ * idx_init, idx_curr: dp_env_v3.py:55-57,67-71). */
+typedef struct dmb_state {
+  float* qpos;           /* [N][DMB_QSTRIDE] */
+  float* qvel;           /* [N][DMB_VSTRIDE] */
+  float* warm;           /* [N][DMB_VSTRIDE]  qacc_warmstart */
+  int32_t* clip;         /* [N] motion clip id of each env */
+  int32_t* idx_init;     /* [N] RSI frame (dp_env_v3.py:68) */
+  int32_t* idx_curr;     /* [N] current mocap frame = phase (dp_env_v3.py:70,101-102) */
+  uint32_t* reset_count; /* [N] Philox counter: number of resets so far */
+  int32_t* ep_len;       /* [N] steps in the current episode */
+  float* ep_ret;         /* [N] return of the current episode */
+  int32_t* flags;        /* [N] bit0 contact overflow, bit1 row overflow, bit2 non-finite state */
+} dmb_state_t;
+
+/* Outputs of one step (caller-owned device buffers). `rec` is optional: the packed
+ * [N][obs_dim + 2] record (obs, reward, done-as-float) that is all-gathered across ranks. */
+typedef struct dmb_step_out {
+  float* obs;       /* [N][obs_dim] post-step (post-reset for auto-reset envs) observation */
+  float* reward;    /* [N] */
+  uint8_t* done;    /* [N] */
+  float* rec;       /* [N][obs_dim + 2] or NULL */
+  float* last_ret;  /* [N] return of the episode that just finished (valid where done) or NULL */
+  int32_t* last_len;/* [N] length of the episode that just finished or NULL */
+} dmb_step_out_t;
+
+int dmb_version(void);
+/* ABI guards for foreign-language bindings (ctypes mirrors in model_blob.py) */
+int32_t dmb_sizeof_model(void);
+int32_t dmb_sizeof_config(void);
+int32_t dmb_sizeof_mocap(void);
+
+/* Build a handle: copies the model / config / mocap tables to `cuda_device` (fp32) and
+ * sizes the launch.  `seed` keys the per-env Philox streams (env e uses (seed, first_env_id + e)). */
+int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_mocap_t* mocap,
+               int32_t num_envs, int32_t cuda_device, uint64_t seed, uint32_t first_env_id,
+               dmb_handle_t* out);
+int dmb_destroy(dmb_handle_t h);
+
+/* (Re)initialise envs.  mask: device uint8[N] or NULL (= all).  mode: 0 mocap RSI
+ * (dp_env_v3.py:148-156), 1 init pose + U(-noise, noise) (dp_env_v3.py:158-164), -1 = config default.
+ * Writes the post-reset observation to obs (may be NULL). */
+int dmb_reset(dmb_handle_t h, const dmb_state_t* st, const uint8_t* mask, int32_t mode, float* obs, void* stream);
+
+/* One env step for all N envs: action -> ctrl (PD optional) -> RK4 mj_step -> obs, reward,
+ * done (+ in-kernel auto reset when config.auto_reset).  dp_env_v3.py:106-132. */
+int dmb_step(dmb_handle_t h, const dmb_state_t* st, const float* action, const dmb_step_out_t* out, void* stream);
+
+/* Observation of the current state (dp_env_v3.py:62-65). */
+int dmb_get_obs(dmb_handle_t h, const dmb_state_t* st, float* obs, void* stream);
+
+/* Stage-level debug: run ONE forward evaluation (mj_forward) at the current state with the
+ * given ctrl[N][nu] and dump stage outputs into dbg[N][dmb_debug_stride()] (layout in
+ * dmb_debug_layout).  Also updates st->warm like MuJoCo's mj_forward.  Used by the parity tests. */
+int dmb_forward_debug(dmb_handle_t h, const dmb_state_t* st, const float* ctrl, float* dbg, void* stream);
+int32_t dmb_debug_stride(void);
+/* offsets (in floats) of the named sections inside one debug row; returns -1 for unknown names.
+ * names: xpos xquat xipos com qM qLD qfrc_bias qfrc_smooth qacc_smooth ncon nefc iter contact
+ *        efc_pos efc_R efc_aref efc_b efc_force efc_AR_diag qacc z_com cvel */
+int32_t dmb_debug_offset(const char* name);
+
+/* launch geometry chosen at create time (for DESIGN.md / bench reporting) */
+int dmb_launch_info(dmb_handle_t h, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* envs_per_cta);
+
+const char* dmb_last_error(dmb_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DMB_H_ */

@@ -407,7 +407,9 @@ static int raw_capsule_box(rawcon_t* c, double margin, const double* cpos, const
       }
     }
   }
-  double ts = 0.5*(tlo + thi);
+  /* a flat stretch of the derivative (axis inside the box, or sliding parallel to a face): take
+   * the end nearer the capsule centre -- a midpoint would sit equidistant from opposite faces */
+  double ts = (thi - tlo > 1e-6*h) ? (fabs(tlo) <= fabs(thi) ? tlo : thi) : 0.5*(tlo + thi);
   int n = 0;
   double sp[3];
   for (int k = 0; k < 3; k++) sp[k] = cpos[k] + ts*axis[k];
@@ -711,9 +713,8 @@ void dmo_fwd_position(const dmb_model_t* m, dmo_data_t* d) {
 }
 
 /* ------------------------------------------------------------------ mj_fwdVelocity */
-void dmo_fwd_velocity(const dmb_model_t* m, dmo_data_t* d) {
-  int nv = m->nv;
-  /* mj_comVel */
+/* mj_comVel */
+static void com_vel(const dmb_model_t* m, dmo_data_t* d) {
   memset(d->cvel[0], 0, sizeof(d->cvel[0]));
   for (int b = 1; b < m->nbody; b++) {
     double cvel[6];
@@ -732,6 +733,11 @@ void dmo_fwd_velocity(const dmb_model_t* m, dmo_data_t* d) {
     }
     memcpy(d->cvel[b], cvel, sizeof(cvel));
   }
+}
+
+void dmo_fwd_velocity(const dmb_model_t* m, dmo_data_t* d) {
+  int nv = m->nv;
+  com_vel(m, d);
   /* mj_passive: joint damping only */
   for (int i = 0; i < nv; i++) d->qfrc_passive[i] = -m->dof_damping[i]*d->qvel[i];
   /* mj_rne(flg_acc = 0) */
@@ -918,4 +924,232 @@ void dmo_step(const dmb_model_t* m, dmo_data_t* d) {
   if (state_bad(m, d)) d->flags |= 4;
 }
 
-/* --- env-level stubs are appended below (dm_oracle_env section) --- */
+/* ====================================================================================
+ * Env logic: restates /root/reference/src/dp_env_v3.py DPEnv (step 106-132, _get_obs 62-65,
+ * is_done 134-139, calc_config_reward 89-104, reset_model 148-156, reset_model_init 158-164)
+ * plus the PD controller intent of mujoco_interface.py:97-107 and the 5-term DeepMimic
+ * reward quoted in code.md:979-1146 (adapted to the hinge model).
+ * ==================================================================================== */
+
+/* Philox4x32-10; same integer arithmetic as csrc/dmb_math.cuh */
+void dmo_philox(uint64_t seed, uint32_t env_id, uint32_t reset_count, uint32_t block, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  uint32_t key0 = (uint32_t)seed, key1 = (uint32_t)(seed >> 32);
+  uint32_t c0 = env_id, c1 = reset_count, c2 = block, c3 = 0;
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    uint32_t n0 = hi1 ^ c1 ^ key0, n1 = lo1, n2 = hi0 ^ c3 ^ key1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    key0 += W0; key1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+static inline float u01f(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+void dmo_env_obs(const dmb_model_t* m, const dmo_env_t* e, double* obs) {
+  int np = m->nq - 7;
+  for (int i = 0; i < np; i++) obs[i] = e->d.qpos[7 + i];
+  for (int i = 0; i < m->nv - 6; i++) obs[np + i] = e->d.qvel[6 + i];
+}
+
+void dmo_env_set_state(const dmb_model_t* m, dmo_env_t* e, const double* qpos, const double* qvel) {
+  memcpy(e->d.qpos, qpos, sizeof(double)*m->nq);
+  memcpy(e->d.qvel, qvel, sizeof(double)*m->nv);
+  memset(e->d.qacc_warmstart, 0, sizeof(e->d.qacc_warmstart));
+}
+
+void dmo_env_reset(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, dmo_env_t* e, int mode) {
+  if (mode < 0) mode = cfg->reset_mode;
+  int len = mc->clip_len[e->clip], start = mc->clip_start[e->clip];
+  uint32_t r[4];
+  dmo_philox(e->seed, e->env_id, e->reset_count, 0, r);
+  int idx = (int)(u01f(r[0]) * (float)len);
+  if (idx >= len) idx = len - 1;
+  if (mode == 0) {
+    /* tables are consumed in fp32 by the CUDA path; round the same way */
+    for (int i = 0; i < m->nq; i++) e->d.qpos[i] = (double)(float)mc->data_config[(size_t)(start + idx)*m->nq + i];
+    for (int i = 0; i < m->nv; i++) e->d.qvel[i] = (double)(float)mc->data_vel[(size_t)(start + idx)*m->nv + i];
+  } else {
+    for (int i = 0; i < m->nq + m->nv; i++) {
+      dmo_philox(e->seed, e->env_id, e->reset_count, 1u + (uint32_t)(i >> 2), r);
+      float nz = (float)cfg->reset_noise * (2.f*u01f(r[i & 3]) - 1.f);
+      if (i < m->nq) e->d.qpos[i] = (double)((float)m->qpos0[i] + nz);
+      else e->d.qvel[i - m->nq] = (double)nz;
+    }
+  }
+  memset(e->d.qacc_warmstart, 0, sizeof(e->d.qacc_warmstart));
+  e->idx_init = idx; e->idx_curr = idx; e->reset_count++;
+  e->ep_len = 0; e->ep_ret = 0;
+}
+
+void dmo_env_init(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, dmo_env_t* e,
+                  uint64_t seed, uint32_t env_id, int32_t clip) {
+  memset(e, 0, sizeof(*e));
+  e->seed = seed; e->env_id = env_id; e->clip = clip;
+  memcpy(e->d.qpos, m->qpos0, sizeof(double)*m->nq);
+}
+
+/* quaternion of a hinge triple: R = Rx(a) Ry(b) Rz(c)  (dp_env_v3.xml hinge stacking) */
+static void quat_from_xyz(double* q, const double* a) {
+  double qx[4] = {cos(0.5*a[0]), sin(0.5*a[0]), 0, 0}, qy[4] = {cos(0.5*a[1]), 0, sin(0.5*a[1]), 0};
+  double qz[4] = {cos(0.5*a[2]), 0, 0, sin(0.5*a[2])}, t[4];
+  mul_quat(t, qx, qy); mul_quat(q, t, qz);
+}
+/* geodesic angle in [0, pi] between two unit quaternions (cMathUtil::QuatDiffTheta), computed
+ * from the difference quaternion with atan2 so that small angles keep their accuracy in fp32 */
+static double quat_diff_theta(const double* a, const double* b) {
+  double ac[4] = {a[0], -a[1], -a[2], -a[3]}, qd[4];
+  mul_quat(qd, ac, b);
+  return 2*atan2(sqrt(qd[1]*qd[1] + qd[2]*qd[2] + qd[3]*qd[3]), fabs(qd[0]));
+}
+/* heading-frame end-effector points + CoM velocity of the pose currently in d (after
+ * dmo_kinematics + com_pos + com_vel) */
+static void pose_features(const dmb_model_t* m, const dmo_data_t* d, double* ee /* nee*3 */, double* vcom) {
+  const double* R = d->xmat[1]; /* root body */
+  double heading = atan2(R[3], R[0]); /* world image of the root x axis */
+  double ch = cos(heading), sh = sin(heading);
+  for (int k = 0; k < m->nee; k++) {
+    int b = m->ee_body[k];
+    double w[3], rel[3];
+    mat_vec(w, d->xmat[b], m->ee_pos[k]);
+    for (int i = 0; i < 3; i++) w[i] += d->xpos[b][i];
+    rel[0] = w[0] - d->xpos[1][0]; rel[1] = w[1] - d->xpos[1][1]; rel[2] = w[2]; /* height above ground */
+    ee[3*k] = ch*rel[0] + sh*rel[1];
+    ee[3*k + 1] = -sh*rel[0] + ch*rel[1];
+    ee[3*k + 2] = rel[2];
+  }
+  double mass = 0, p[3] = {0, 0, 0};
+  for (int b = 1; b < m->nbody; b++) {
+    double r[3] = {d->xipos[b][0] - d->com[0], d->xipos[b][1] - d->com[1], d->xipos[b][2] - d->com[2]}, t[3];
+    cross3(t, d->cvel[b], r);
+    for (int i = 0; i < 3; i++) p[i] += m->body_mass[b]*(d->cvel[b][3 + i] + t[i]);
+    mass += m->body_mass[b];
+  }
+  for (int i = 0; i < 3; i++) vcom[i] = p[i]/mass;
+}
+
+void dmo_ref_aux(const dmb_model_t* m, const double* qpos, const double* qvel, double* aux) {
+  static __thread dmo_data_t d;
+  memcpy(d.qpos, qpos, sizeof(double)*m->nq);
+  memcpy(d.qvel, qvel, sizeof(double)*m->nv);
+  dmo_kinematics(m, &d); com_pos(m, &d); com_vel(m, &d);
+  memset(aux, 0, sizeof(double)*DMB_REF_AUX);
+  pose_features(m, &d, aux, aux + 12);
+  for (int i = 0; i < 4; i++) aux[15 + i] = qpos[3 + i];
+}
+
+static double reward_imitate(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, dmo_env_t* e) {
+  dmo_data_t* d = &e->d;
+  size_t f = (size_t)(mc->clip_start[e->clip] + e->idx_curr);
+  double rq[DMB_MAX_Q], rv[DMB_MAX_DOF], aux[DMB_REF_AUX];
+  for (int i = 0; i < m->nq; i++) rq[i] = (double)(float)mc->data_config[f*m->nq + i];
+  for (int i = 0; i < m->nv; i++) rv[i] = (double)(float)mc->data_vel[f*m->nv + i];
+  for (int i = 0; i < DMB_REF_AUX; i++) aux[i] = (double)(float)mc->ref_aux[f*DMB_REF_AUX + i];
+  /* fresh kinematics at the post-step state */
+  dmo_kinematics(m, d); com_pos(m, d); com_vel(m, d);
+  double ee[3*DMB_MAX_EE], vcom[3];
+  pose_features(m, d, ee, vcom);
+  double pose_err = 0, vel_err = 0;
+  { /* root */
+    double q0[4] = {d->qpos[3], d->qpos[4], d->qpos[5], d->qpos[6]}, q1[4] = {rq[3], rq[4], rq[5], rq[6]};
+    normalize4(q0); normalize4(q1);
+    double th = quat_diff_theta(q0, q1);
+    pose_err += m->dof_weight[3]*th*th;
+  }
+  for (int b = 2; b < m->nbody; b++) {
+    int da = m->body_dofadr[b], nd = m->body_dofnum[b];
+    if (nd == 3) {
+      double q0[4], q1[4];
+      quat_from_xyz(q0, d->qpos + da + 1); quat_from_xyz(q1, rq + da + 1);
+      double th = quat_diff_theta(q0, q1);
+      pose_err += m->dof_weight[da]*th*th;
+    } else if (nd == 1) {
+      double dq = d->qpos[da + 1] - rq[da + 1];
+      pose_err += m->dof_weight[da]*dq*dq;
+    }
+  }
+  for (int i = 3; i < m->nv; i++) { double dv = d->qvel[i] - rv[i]; vel_err += m->dof_weight[i]*dv*dv; }
+  double ee_err = 0;
+  for (int k = 0; k < 3*m->nee; k++) { double t = ee[k] - aux[k]; ee_err += t*t; }
+  if (m->nee > 0) ee_err /= m->nee;
+  double root_err = 0;
+  {
+    double q0[4] = {d->qpos[3], d->qpos[4], d->qpos[5], d->qpos[6]}, q1[4] = {rq[3], rq[4], rq[5], rq[6]};
+    normalize4(q0); normalize4(q1);
+    double th = quat_diff_theta(q0, q1), p = 0, v = 0, w = 0;
+    for (int i = 0; i < 3; i++) {
+      p += (d->qpos[i] - rq[i])*(d->qpos[i] - rq[i]);
+      v += (d->qvel[i] - rv[i])*(d->qvel[i] - rv[i]);
+      w += (d->qvel[3 + i] - rv[3 + i])*(d->qvel[3 + i] - rv[3 + i]);
+    }
+    root_err = p + 0.1*th*th + 0.01*v + 0.001*w;
+  }
+  double com_err = 0;
+  for (int i = 0; i < 3; i++) com_err += (aux[12 + i] - vcom[i])*(aux[12 + i] - vcom[i]);
+  com_err *= 0.1;
+  e->reward_terms[0] = exp(-cfg->s_err*cfg->s_pose*pose_err);
+  e->reward_terms[1] = exp(-cfg->s_err*cfg->s_vel*vel_err);
+  e->reward_terms[2] = exp(-cfg->s_err*cfg->s_end_eff*ee_err);
+  e->reward_terms[3] = exp(-cfg->s_err*cfg->s_root*root_err);
+  e->reward_terms[4] = exp(-cfg->s_err*cfg->s_com*com_err);
+  return cfg->w_pose*e->reward_terms[0] + cfg->w_vel*e->reward_terms[1] + cfg->w_end_eff*e->reward_terms[2] +
+         cfg->w_root*e->reward_terms[3] + cfg->w_com*e->reward_terms[4];
+}
+
+int dmo_env_step(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, dmo_env_t* e,
+                 const double* action, double* obs, double* reward) {
+  dmo_data_t* d = &e->d;
+  /* action -> ctrl */
+  for (int u = 0; u < m->nu; u++) {
+    double a = action[u];
+    int dof = m->act_dofadr[u];
+    if (cfg->ctrl_mode != 0) {
+      double perr = a - d->qpos[dof + 1], tau;
+      if (cfg->ctrl_mode == 1) tau = m->act_kp[u]*perr + m->act_kd[u]*(perr/m->timestep - d->qvel[dof]);
+      else tau = m->act_kp[u]*perr - m->act_kd[u]*d->qvel[dof];
+      a = tau / m->act_gear[u];
+    }
+    if (a != a) a = 0;
+    d->ctrl[u] = a;
+  }
+  dmo_step(m, d);
+  int bad = (d->flags & 4) != 0;
+  double zc = d->com[2]; /* stale CoM of the last RK4 stage, as mjData.xipos is after mj_step */
+  double rew = 1.0;
+  if (cfg->reward_mode == 1) {
+    size_t f = (size_t)(mc->clip_start[e->clip] + e->idx_curr);
+    double err = 0;
+    for (int j = 0; j < m->nq - 7; j++) err += fabs(d->qpos[7 + j] - (double)(float)mc->data_config[f*m->nq + 7 + j]);
+    rew = exp(-err);
+    e->idx_curr = (e->idx_curr + 1) % mc->clip_len[e->clip];
+  } else if (cfg->reward_mode == 4) {
+    rew = reward_imitate(m, cfg, mc, e);
+    e->idx_curr = (e->idx_curr + 1) % mc->clip_len[e->clip];
+  }
+  if (bad) rew = 0;
+  int done = bad || zc < cfg->z_min || zc > cfg->z_max;
+  e->ep_len++; e->ep_ret += rew;
+  *reward = rew;
+  if (done && cfg->auto_reset) dmo_env_reset(m, cfg, mc, e, cfg->reset_mode);
+  else if (bad) { memcpy(d->qpos, m->qpos0, sizeof(double)*m->nq); memset(d->qvel, 0, sizeof(d->qvel)); memset(d->qacc_warmstart, 0, sizeof(d->qacc_warmstart)); }
+  if (obs) dmo_env_obs(m, e, obs);
+  return done;
+}
+
+/* CPU baseline loop: random actions a ~ U(-0.5, 0.5)^nu (action_space.sample()), reset on done */
+long dmo_rollout(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, dmo_env_t* e,
+                 long nsteps, uint64_t action_seed) {
+  double action[DMB_MAX_U], obs[2*DMB_MAX_DOF], rew;
+  uint32_t r[4];
+  dmb_config_t c = *cfg;
+  c.auto_reset = 1;
+  for (long t = 0; t < nsteps; t++) {
+    for (int u = 0; u < m->nu; u += 4) {
+      dmo_philox(action_seed, e->env_id, (uint32_t)t, (uint32_t)(u >> 2), r);
+      for (int k = 0; k < 4 && u + k < m->nu; k++) action[u + k] = (double)(u01f(r[k]) - 0.5f);
+    }
+    dmo_env_step(m, &c, mc, e, action, obs, &rew);
+  }
+  return nsteps;
+}

@@ -1,0 +1,96 @@
+"""Shared helpers for the test-suite: model/mocap loading, oracle wrappers, state generators."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from deepmimic_mujoco_b200.mjcf import load_tables  # noqa: E402
+from deepmimic_mujoco_b200.mocap import concat_clips, load_clip  # noqa: E402
+from deepmimic_mujoco_b200.model_blob import default_config, pack_model  # noqa: E402
+
+ASSETS = os.path.join(ROOT, "deepmimic_mujoco_b200", "assets")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REFERENCE_XML = "/root/reference/src/mujoco/humanoid_deepmimic/envs/asset/dp_env_v3.xml"
+
+_tables = None
+
+
+def tables():
+    global _tables
+    if _tables is None:
+        _tables = load_tables(os.path.join(ASSETS, "dp_env_v3.model.npz"))
+    return _tables
+
+
+def model(max_con=24, max_efc=63):
+    return pack_model(tables(), max_con=max_con, max_efc=max_efc)
+
+
+def clip(name):
+    return load_clip(os.path.join(ASSETS, "motions", name + ".npz"), name=name)
+
+
+def f32(x):
+    """Round to fp32-representable float64 (so oracle and GPU start from identical inputs)."""
+    return np.asarray(x, dtype=np.float32).astype(np.float64)
+
+
+def random_quat(rng):
+    q = rng.normal(size=4)
+    return q / np.linalg.norm(q)
+
+
+def airborne_states(rng, n, z=3.0, frac=0.45, vel=2.0):
+    """Random poses inside the joint ranges, high above the floor."""
+    mt = tables()
+    lo, hi = mt.jnt_range[1:, 0], mt.jnt_range[1:, 1]
+    mid, half = 0.5 * (lo + hi), 0.5 * (hi - lo)
+    qpos = np.tile(mt.qpos0, (n, 1))
+    qvel = rng.normal(size=(n, mt.nv)) * vel
+    for i in range(n):
+        qpos[i, 7:] = mid + half * rng.uniform(-frac, frac, size=mt.nq - 7)
+        qpos[i, 3:7] = random_quat(rng)
+        qpos[i, 2] = z
+    return f32(qpos), f32(qvel)
+
+
+def standing_states(rng, n, noise=0.05, vel=0.3, drop=0.03):
+    """Near the default standing pose, feet at / slightly into the floor."""
+    mt = tables()
+    qpos = np.tile(mt.qpos0, (n, 1))
+    qpos[:, 7:] += rng.uniform(-noise, noise, size=(n, mt.nq - 7))
+    qpos[:, 2] -= rng.uniform(0.0, drop, size=n)  # root height 0.9 puts the soles ~2 cm above the floor
+    for i in range(n):
+        q = np.array([1.0, 0, 0, 0]) + rng.normal(size=4) * noise * 0.5
+        qpos[i, 3:7] = q / np.linalg.norm(q)
+    qvel = rng.normal(size=(n, mt.nv)) * vel
+    return f32(qpos), f32(qvel)
+
+
+def mocap_states(name, idx):
+    c = clip(name)
+    return f32(c.data_config[idx]), f32(np.nan_to_num(c.data_vel[idx]))
+
+
+def rollout_states(rng, n, steps_range=(5, 40)):
+    """States reached by the ORACLE under random torques from the standing pose (contact-rich, falling)."""
+    import oracle.pyoracle as po
+    mt = tables()
+    o = po.Oracle(model())
+    qs, vs, ws = [], [], []
+    for i in range(n):
+        qpos = mt.qpos0 + rng.uniform(-0.01, 0.01, size=mt.nq)
+        qvel = rng.uniform(-0.01, 0.01, size=mt.nv)
+        o.set_state(qpos, qvel)
+        for _ in range(int(rng.integers(*steps_range))):
+            o.d.arr("ctrl")[: mt.nu] = rng.uniform(-0.5, 0.5, size=mt.nu)
+            o.step()
+        qs.append(o.qpos.copy()); vs.append(o.qvel.copy()); ws.append(o.d.arr("qacc_warmstart")[: mt.nv].copy())
+    return f32(np.array(qs)), f32(np.array(vs)), f32(np.array(ws))

@@ -1,0 +1,264 @@
+"""CUDA path vs the float64 oracle, through the C-ABI (run on the B200 box: pytest -m gpu).
+
+Tolerances: single step from identical fp32-representable inputs,
+|dqpos| <= 1e-4, |dqvel| / max(1,|qvel|) <= 1e-4 (contact-rich: 2e-4), reward <= 1e-5 abs,
+FK quantities <= 1e-5, `done` exact away from the threshold.  PARITY UNPINNED against MuJoCo
+itself (no binary, no golden vectors) -- the oracle is the restatement being matched.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+N = 64
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import oracle.pyoracle as po
+    from deepmimic_mujoco_b200.sim import BatchedSim
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    sim = BatchedSim(N, motions=("walk",), seed=11)
+    return sim, po.Oracle(common.model()), common.tables(), po
+
+
+def oracle_forward(o, mt, q, v, c, w):
+    o.set_state(q, v, c, w)
+    o.forward()
+    return o.d
+
+
+def compare_forward(ctx, q, v, ctrl, warm=None, tol_scale=1.0):
+    sim, o, mt, po = ctx
+    n = q.shape[0]
+    warm = np.zeros((n, mt.nv)) if warm is None else warm
+    sim.set_state(q, v, warm)
+    g = sim.forward_debug(torch.tensor(ctrl, dtype=torch.float32))
+    for i in range(n):
+        d = oracle_forward(o, mt, q[i], v[i], ctrl[i], warm[i])
+        assert d.ncon == g["ncon"][i] and d.nefc == g["nefc"][i], (i, d.ncon, g["ncon"][i], d.nefc, g["nefc"][i])
+        nb, nv, ne = mt.nbody, mt.nv, d.nefc
+        assert np.abs(d.arr("xpos")[:nb] - g["xpos"][i]).max() < 1e-5
+        assert np.abs(d.arr("xquat")[:nb] - g["xquat"][i]).max() < 1e-5
+        assert np.abs(d.arr("xipos")[:nb] - g["xipos"][i]).max() < 1e-5
+        assert np.abs(d.arr("com") - g["com"][i]).max() < 1e-5
+        qM = d.arr("qM")[:mt.nM]
+        assert np.abs(qM - g["qM"][i]).max() < 1e-5 * max(1.0, np.abs(qM).max())
+        bias = d.arr("qfrc_bias")[:nv]
+        assert np.abs(bias - g["qfrc_bias"][i]).max() < 2e-5 * max(1.0, np.abs(bias).max())
+        qs = d.arr("qacc_smooth")[:nv]
+        assert np.abs(qs - g["qacc_smooth"][i]).max() < 5e-5 * max(1.0, np.abs(qs).max())
+        if d.ncon:
+            oc = np.array([[c.dist, *c.pos, *c.frame, c.geom1, c.geom2, c.dim] for c in d.contact[:d.ncon]])
+            assert np.abs(oc - g["contact"][i][: d.ncon]).max() < 2e-5
+        if ne:
+            for k, rel in (("efc_pos", 1e-5), ("efc_R", 1e-4), ("efc_aref", 1e-4), ("efc_b", 1e-4)):
+                a = d.arr(k)[:ne]
+                assert np.abs(a - g[k][i][:ne]).max() < rel * tol_scale * max(1.0, np.abs(a).max()), (k, i)
+            f = d.arr("efc_force")[:ne]
+            assert np.abs(f - g["efc_force"][i][:ne]).max() < 1e-3 * tol_scale * max(1.0, np.abs(f).max())
+        qa = d.arr("qacc")[:nv]
+        assert np.abs(qa - g["qacc"][i]).max() < 2e-4 * tol_scale * max(1.0, np.abs(qa).max())
+
+
+def compare_step(ctx, q, v, ctrl, warm=None, vtol=1e-4):
+    sim, o, mt, po = ctx
+    n = q.shape[0]
+    warm = np.zeros((n, mt.nv)) if warm is None else warm
+    sim.set_state(q, v, warm)
+    act = torch.tensor(ctrl, dtype=torch.float32, device=sim.device)
+    obs, rew, done = sim.step(act)
+    gq, gv, gw = sim.get_state()
+    obs = obs.double().cpu().numpy(); done = done.cpu().numpy(); rew = rew.cpu().numpy()
+    for i in range(n):
+        o.set_state(q[i], v[i], ctrl[i], warm[i])
+        o.step()
+        assert np.abs(o.qpos - gq[i]).max() < 1e-4
+        assert (np.abs(o.qvel - gv[i]) / np.maximum(1.0, np.abs(o.qvel))).max() < vtol
+        zc = o.d.arr("com")[2]
+        if min(abs(zc - 0.7), abs(zc - 2.0)) > 1e-4:
+            assert bool(done[i]) == bool(zc < 0.7 or zc > 2.0)
+        assert np.abs(obs[i] - np.concatenate([gq[i][7:], gv[i][6:]])).max() == 0.0
+        assert rew[i] == 1.0
+
+
+def test_forward_airborne(ctx):
+    rng = np.random.default_rng(0)
+    q, v = common.airborne_states(rng, N)
+    compare_forward(ctx, q, v, common.f32(rng.uniform(-0.6, 0.6, (N, 28))))
+
+
+def test_forward_standing_contacts(ctx):
+    rng = np.random.default_rng(1)
+    q, v = common.standing_states(rng, N)
+    compare_forward(ctx, q, v, common.f32(rng.uniform(-0.6, 0.6, (N, 28))))
+
+
+def test_forward_rollout_states_with_warmstart(ctx):
+    rng = np.random.default_rng(2)
+    q, v, w = common.rollout_states(rng, N)
+    compare_forward(ctx, q, v, common.f32(rng.uniform(-0.6, 0.6, (N, 28))), w, tol_scale=2.0)
+
+
+@pytest.mark.parametrize("clip", ["walk", "spinkick", "dance_b"])
+def test_step_from_mocap_frames(ctx, clip):
+    rng = np.random.default_rng(3)
+    c = common.clip(clip)
+    idx = rng.integers(0, len(c), size=N)
+    q, v = common.mocap_states(clip, idx)
+    compare_step(ctx, q, v, common.f32(rng.uniform(-0.5, 0.5, (N, 28))))
+
+
+def test_step_standing_and_rollout(ctx):
+    rng = np.random.default_rng(4)
+    q, v = common.standing_states(rng, N)
+    compare_step(ctx, q, v, common.f32(rng.uniform(-0.7, 0.7, (N, 28))))
+    q, v, w = common.rollout_states(rng, N)
+    compare_step(ctx, q, v, common.f32(rng.normal(size=(N, 28))), w, vtol=2e-4)
+
+
+def test_step_airborne_self_contacts(ctx):
+    rng = np.random.default_rng(5)
+    q, v = common.airborne_states(rng, N, frac=0.35)
+    compare_step(ctx, q, v, common.f32(rng.uniform(-0.5, 0.5, (N, 28))), vtol=3e-4)
+
+
+def _env_pair(po, reward_mode, ctrl_mode, motions=("walk",), n=32, seed=5, auto_reset=1, reset_mode=0):
+    from deepmimic_mujoco_b200.model_blob import default_config
+    from deepmimic_mujoco_b200.refaux import compute_ref_aux
+    from deepmimic_mujoco_b200.sim import BatchedSim, load_motions, make_mocap_struct
+    cfg = default_config(reward_mode=reward_mode, ctrl_mode=ctrl_mode, auto_reset=auto_reset, reset_mode=reset_mode)
+    aux = compute_ref_aux(motions) if reward_mode == 4 else None
+    clip_ids = torch.arange(n, dtype=torch.int32) % len(motions)
+    sim = BatchedSim(n, motions=motions, seed=seed, config=cfg, ref_aux=aux, clip_ids=clip_ids)
+    mcs, keep = make_mocap_struct(load_motions(list(motions)), aux)
+    return sim, cfg, mcs, keep, clip_ids
+
+
+@pytest.mark.parametrize("reward_mode,ctrl_mode", [(0, 0), (1, 0), (4, 0), (4, 1), (1, 2)])
+def test_env_step_rewards_pd_and_reset(ctx, reward_mode, ctrl_mode):
+    """Full env step (PD -> RK4 -> reward -> done -> auto reset) for a few consecutive steps vs the
+    oracle env; RSI frame indices must be bit-identical (same Philox stream)."""
+    _, _, mt, po = ctx
+    n = 32
+    motions = ("walk", "dance_b", "spinkick")
+    sim, cfg, mcs, keep, clip_ids = _env_pair(po, reward_mode, ctrl_mode, motions, n)
+    L = po.lib()
+    m = common.model()
+    envs = [po.DmoEnv() for _ in range(n)]
+    for i, e in enumerate(envs):
+        L.dmo_env_init(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), 5, i, int(clip_ids[i]))
+        L.dmo_env_reset(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), 0)
+    sim.reset()
+    gq, gv, _ = sim.get_state()
+    for i, e in enumerate(envs):
+        assert e.idx_init == int(sim.idx_init[i]) and e.idx_curr == int(sim.idx_curr[i])
+        assert np.abs(np.ctypeslib.as_array(e.d.qpos)[: mt.nq] - gq[i]).max() == 0.0
+    rng = np.random.default_rng(9)
+    obs_o = np.zeros(56); rew_o = C.c_double()
+    for t in range(6):
+        scale = 1.0 if ctrl_mode == 0 else 1.0
+        act = common.f32(rng.uniform(-0.5, 0.5, (n, 28)) * scale)
+        # identical inputs for both: copy the GPU state (fp32) into the oracle envs each step
+        gq, gv, gw = sim.get_state()
+        for i, e in enumerate(envs):
+            np.ctypeslib.as_array(e.d.qpos)[: mt.nq] = gq[i]
+            np.ctypeslib.as_array(e.d.qvel)[: mt.nv] = gv[i]
+            np.ctypeslib.as_array(e.d.qacc_warmstart)[: mt.nv] = gw[i]
+        obs, rew, done = sim.step(torch.tensor(act, dtype=torch.float32, device=sim.device))
+        obs = obs.double().cpu().numpy(); rew = rew.double().cpu().numpy(); done = done.cpu().numpy()
+        for i, e in enumerate(envs):
+            a = np.ascontiguousarray(act[i])
+            od = L.dmo_env_step(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), po.dptr(a), po.dptr(obs_o), C.byref(rew_o))
+            zc = e.d.com[2] if not od else None
+            assert abs(rew_o.value - rew[i]) < 2e-5, (t, i, rew_o.value, rew[i])
+            assert bool(od) == bool(done[i]), (t, i)
+            assert e.idx_curr == int(sim.idx_curr[i]) and e.idx_init == int(sim.idx_init[i])
+            assert np.abs(obs_o - obs[i]).max() < 2e-4 * max(1.0, np.abs(obs_o).max()), (t, i)
+    sim.close()
+
+
+def test_reset_modes_and_determinism(ctx):
+    _, _, mt, po = ctx
+    sim, cfg, mcs, keep, _ = _env_pair(po, 0, 0, ("walk",), 32, seed=77, reset_mode=1)
+    o1 = sim.reset().clone()
+    q1, v1, _ = sim.get_state()
+    assert np.abs(q1 - mt.qpos0).max() <= 0.01 + 1e-6 and np.abs(v1).max() <= 0.01 + 1e-6
+    assert np.abs(q1 - mt.qpos0).max() > 1e-4
+    L = po.lib(); m = common.model()
+    e = po.DmoEnv()
+    L.dmo_env_init(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), 77, 3, 0)
+    L.dmo_env_reset(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), 1)
+    assert np.abs(np.ctypeslib.as_array(e.d.qpos)[: mt.nq] - q1[3]).max() < 1e-6
+    assert np.abs(np.ctypeslib.as_array(e.d.qvel)[: mt.nv] - v1[3]).max() < 1e-6
+    # masked reset only touches the masked envs; a fresh sim with the same seed reproduces the first reset
+    mask = torch.zeros(32, dtype=torch.uint8); mask[5] = 1
+    before = sim.qpos.clone()
+    sim.reset(mask=mask.cuda())
+    changed = (sim.qpos != before).any(dim=1).cpu().numpy()
+    assert changed[5] and changed.sum() == 1
+    sim2, *_ = _env_pair(po, 0, 0, ("walk",), 32, seed=77, reset_mode=1)
+    assert torch.equal(sim2.reset(), o1)
+    sim.close(); sim2.close()
+
+
+def test_gym_surface_dpenv():
+    from deepmimic_mujoco_b200.env import DPEnv
+    env = DPEnv(motion="walk", seed=0)
+    assert env.observation_space.shape == (56,) and env.action_space.shape == (28,)
+    assert np.all(env.action_space.low == -0.5) and np.all(env.action_space.high == 0.5)
+    env.seed(0)
+    ob = env.reset()
+    assert ob.shape == (56,) and ob.dtype == np.float64
+    assert 0 <= env.idx_curr < 39
+    assert np.allclose(ob[:28], np.float32(env.mocap.data_config[env.idx_init][7:]), atol=1e-6)
+    ob2 = env.reset_model_init()
+    assert np.abs(ob2[:28]).max() <= 0.0101
+    n = 0
+    for t in range(300):
+        ob, rew, done, info = env.step(env.action_space.sample())
+        n += 1
+        assert rew == 1.0 and isinstance(done, bool) and info == {}
+        if done:
+            break
+    assert done and 5 < n < 300   # an unactuated humanoid falls (progress.csv:2-4: ~35 steps)
+    assert abs(env.dt - 0.0166 * 6) < 1e-12
+    env.close()
+
+
+def test_full_size_properties():
+    """BASELINE config-2 size (4096 envs, walk): size-independent properties of a rollout."""
+    from deepmimic_mujoco_b200.env import DPVecEnv
+    env = DPVecEnv(4096, motions=("walk",), seed=3, reward_mode=4, auto_reset=True)
+    obs = env.reset()
+    assert obs.shape == (4096, 56) and torch.isfinite(obs).all()
+    g = torch.Generator(device="cuda"); g.manual_seed(0)
+    ndone = 0
+    for t in range(40):
+        act = torch.rand(4096, 28, device="cuda", generator=g) - 0.5
+        obs, rew, done, info = env.step(act)
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        assert (rew >= 0).all() and (rew <= 1.0 + 1e-6).all()
+        qn = env.sim.qpos[:, 3:7].norm(dim=1)
+        assert (qn - 1).abs().max() < 1e-4          # free-joint quaternion stays normalised
+        assert (env.sim.flags & 4).sum() == 0       # no non-finite states
+        ndone += int(done.sum())
+        # auto-reset envs restart their episode counters and sit on a mocap frame
+        d = done.bool()
+        assert (env.sim.ep_len[d] == 0).all() and (env.sim.ep_len[~d] > 0).all()
+    assert ndone > 0
+    # determinism: same seed, same actions -> identical trajectories
+    env2 = DPVecEnv(4096, motions=("walk",), seed=3, reward_mode=4, auto_reset=True)
+    env2.reset()
+    g.manual_seed(0)
+    for t in range(40):
+        act = torch.rand(4096, 28, device="cuda", generator=g) - 0.5
+        o2, r2, d2, _ = env2.step(act)
+    assert torch.equal(o2, obs) and torch.equal(r2, rew)
+    env.close(); env2.close()

@@ -1,0 +1,171 @@
+"""Pins for the CPU float64 oracle (PARITY UNPINNED against MuJoCo itself -- these are the
+independent checks we can make): inertia vs an independent numpy CRB, exact solves, energy and
+momentum balances, contact sanity, PGS invariants, Philox known answer.  CPU only."""
+import ctypes as C
+
+import numpy as np
+
+import common
+import oracle.pyoracle as po
+from deepmimic_mujoco_b200 import mjcf
+
+
+def make():
+    return po.Oracle(common.model())
+
+
+def energy(o, mt):
+    M = o.full_M()
+    v = o.qvel
+    pe = 9.81 * sum(mt.body_mass[b] * o.d.arr("xipos")[b][2] for b in range(mt.nbody))
+    return 0.5 * v @ M @ v + pe
+
+
+def test_mass_matrix_matches_independent_crb():
+    mt, o = common.tables(), make()
+    rng = np.random.default_rng(0)
+    q, v = common.airborne_states(rng, 5)
+    for i in range(5):
+        o.set_state(q[i], v[i]); o.forward()
+        Mn = mjcf.np_mass_matrix(mt, q[i])
+        assert np.abs(o.full_M() - Mn).max() < 1e-12
+        x = rng.normal(size=mt.nv)
+        assert np.abs(Mn @ o.solve_M(x) - x).max() < 1e-11
+
+
+def test_energy_rate_equals_nonconservative_power():
+    """d/dt (KE + PE) = qvel . (passive + actuator + constraint): validates M, the RNE bias
+    (Coriolis + gravity) and the integrator together."""
+    mt = common.tables()
+    rng = np.random.default_rng(1)
+    m = common.model(); m.timestep = 1e-4
+    o = po.Oracle(m)
+    q, v = common.airborne_states(rng, 4, frac=0.3)
+    for i in range(4):
+        o.set_state(q[i], v[i], ctrl=rng.uniform(-0.5, 0.5, mt.nu)); o.forward()
+        e0 = energy(o, mt)
+        pw = lambda: o.qvel @ (o.d.arr("qfrc_passive")[:mt.nv] + o.d.arr("qfrc_actuator")[:mt.nv] + o.d.arr("qfrc_constraint")[:mt.nv])
+        p0 = pw()
+        o.step(); o.forward()
+        e1, p1 = energy(o, mt), pw()
+        assert abs((e1 - e0) / 1e-4 - 0.5 * (p0 + p1)) < 2e-3 * max(1.0, abs(p0))
+
+
+def test_free_flight_momentum():
+    """No contacts: CoM accelerates at exactly g regardless of internal torques/damping."""
+    mt, o = common.tables(), make()
+    rng = np.random.default_rng(2)
+    q, v = common.airborne_states(rng, 3, frac=0.3)
+    for i in range(3):
+        o.set_state(q[i], v[i], ctrl=rng.uniform(-0.5, 0.5, mt.nu)); o.forward()
+        if o.d.ncon:
+            continue
+        # CoM acceleration = (1/M) sum_b m_b J_b qacc + velocity-product terms; check via finite differences
+        c0 = o.d.arr("com").copy()
+        m2 = common.model(); m2.timestep = 1e-3
+        o2 = po.Oracle(m2); o2.set_state(q[i], v[i], ctrl=o.d.arr("ctrl")[:mt.nu].copy())
+        coms = []
+        for _ in range(3):
+            o2.forward(); coms.append(o2.d.arr("com").copy()); o2.step()
+        acc = (coms[2] - 2 * coms[1] + coms[0]) / 1e-6
+        if o2.d.ncon == 0:
+            assert np.abs(acc - [0, 0, -9.81]).max() < 5e-2
+
+
+def test_standing_contacts_support_weight():
+    mt, o = common.tables(), make()
+    qpos = mt.qpos0.copy(); qpos[2] -= 0.0225  # soles 2.5 mm into the floor
+    o.set_state(qpos, np.zeros(mt.nv)); o.forward()
+    d = o.d
+    assert d.ncon == 8 and d.nefc == 32          # 2 feet x 4 corners x 4 pyramid edges
+    f = d.arr("efc_force")[:32]
+    assert np.all(f >= 0)
+    # total normal force (sum of all pyramid edge forces, normal component 1 each) is of the order of the weight
+    assert 0.2 * 45 * 9.81 < f.sum() < 5 * 45 * 9.81
+    for c in d.contact[:8]:
+        assert c.geom1 == 0 and c.dim == 3 and abs(c.frame[2] - 1) < 1e-12 and c.dist < 0
+    # floor frame: t1 = +y, t2 = -x (mju_makeFrame with n = +z)
+    assert np.allclose(np.array(d.contact[0].frame), [0, 0, 1, 0, 1, 0, -1, 0, 0])
+
+
+def test_pgs_invariants_and_warmstart_fixed_point():
+    mt, o = common.tables(), make()
+    rng = np.random.default_rng(3)
+    q, v, w = common.rollout_states(rng, 6)
+    for i in range(6):
+        o.set_state(q[i], v[i], warm=w[i]); o.forward()
+        d = o.d
+        n = d.nefc
+        if n == 0:
+            continue
+        f = d.arr("efc_force")[:n]
+        assert np.all(f >= 0)
+        AR = np.array([[d.efc_AR[r][c] for c in range(n)] for r in range(n)])
+        assert np.allclose(AR, AR.T) and np.all(np.linalg.eigvalsh(AR) > 0)
+        # qacc = qacc_smooth + M^-1 J' f
+        J = d.arr("efc_J")[:n, :mt.nv]
+        qa = d.arr("qacc_smooth")[:mt.nv] + np.linalg.solve(o.full_M(), J.T @ f)
+        assert np.abs(qa - d.arr("qacc")[:mt.nv]).max() < 1e-8 * max(1, np.abs(qa).max())
+        # A = J M^-1 J' + R
+        A = J @ np.linalg.solve(o.full_M(), J.T) + np.diag(d.arr("efc_R")[:n])
+        assert np.abs(A - AR).max() < 1e-9 * max(1.0, np.abs(A).max())
+
+
+def test_limit_rows_and_order():
+    mt, o = common.tables(), make()
+    qpos = mt.qpos0.copy(); qpos[2] = 3.0
+    qpos[7 + 9] = -0.2     # right_elbow below its lower limit 0
+    qpos[7 + 17] = 0.3     # right_knee above its upper limit 0
+    o.set_state(qpos, np.zeros(mt.nv)); o.forward()
+    d = o.d
+    assert d.nefc >= 2 and d.efc_type[0] == 0 and d.efc_type[1] == 0
+    J = d.arr("efc_J")
+    assert J[0, 6 + 9] == 1.0 and abs(d.efc_pos[0] + 0.2) < 1e-12      # lower side: J = +1, pos = q - lo
+    assert J[1, 6 + 17] == -1.0 and abs(d.efc_pos[1] + 0.3) < 1e-12    # upper side: J = -1, pos = hi - q
+    assert d.efc_force[0] > 0 and d.efc_force[1] > 0
+
+
+def test_rk4_convergence_order():
+    """Halving h on a contact-free trajectory shrinks the global error at least ~4x.  (The hinge
+    coordinates are 4th order; the free-joint quaternion is advanced as q0 * exp(h * sum b_i w_i),
+    MuJoCo's mj_integratePos, which is 2nd order when the angular velocity direction changes.)"""
+    mt = common.tables()
+    rng = np.random.default_rng(5)
+    q, v = common.airborne_states(rng, 1, frac=0.2, vel=1.0)
+    def run(h, n):
+        m = common.model(); m.timestep = h
+        o = po.Oracle(m); o.set_state(q[0], v[0])
+        for _ in range(n):
+            o.step()
+        assert o.d.ncon == 0
+        return o.qvel.copy()
+    ref = run(0.0005, 256)
+    e1 = np.abs(run(0.032, 4) - ref).max()
+    e2 = np.abs(run(0.016, 8) - ref).max()
+    assert e2 < 1e-7 and e1 / e2 > 3.0, (e1, e2)
+
+
+def test_philox_known_answer():
+    L = po.lib()
+    out = (C.c_uint32 * 4)()
+    L.dmo_philox(0, 0, 0, 0, out)   # Random123 kat_vectors: philox4x32-10, zero counter and key
+    assert [int(x) for x in out] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+
+
+def test_passive_fall_matches_reference_statistic():
+    """Sanity statistic from the reference's own log (progress.csv:2-4): with N(0,1) actions clamped to
+    +-0.5 from the standing pose +-0.01, episodes last ~33-37 steps.  We only require the same
+    order of magnitude from the oracle (10..120 steps)."""
+    mt, o = common.tables(), make()
+    rng = np.random.default_rng(7)
+    lens = []
+    for ep in range(5):
+        o.set_state(mt.qpos0 + rng.uniform(-0.01, 0.01, mt.nq), rng.uniform(-0.01, 0.01, mt.nv))
+        for t in range(400):
+            o.d.arr("ctrl")[:mt.nu] = rng.normal(size=mt.nu)
+            o.step()
+            z = o.d.arr("com")[2]
+            if z < 0.7 or z > 2.0:
+                break
+        lens.append(t + 1)
+    assert 10 < np.mean(lens) < 120, lens
