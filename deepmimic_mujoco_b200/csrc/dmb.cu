@@ -15,6 +15,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -24,6 +25,7 @@
 namespace dmb {
 
 struct DevPtrs {
+  int* counter;            // dynamic env scheduler (zeroed before every launch)
   const ModelS* model;
   const float* mocap_cfg;  // [F][nq]
   const float* mocap_vel;  // [F][nv]
@@ -108,34 +110,38 @@ __device__ __forceinline__ void integrate_pos(const ModelS& M, EnvS& S, int lane
   }
 }
 
-// mj_step with RK4 (mj_RungeKutta N=4).  Returns the CoM height of the last stage evaluation.
-__device__ float rk4_step(const ModelS& M, EnvS& S, int lane) {
+// mj_step with RK4 (mj_RungeKutta N=4).  X0 velocities and the weighted stage sums live in
+// registers (dof d on lane d & 31).  forward_eval has a single call site (code size matters:
+// the kernel is instruction-fetch bound).  Returns the CoM height of the last stage evaluation.
+template <bool LOCKSTEP>
+__device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bool active) {
   const float h = M.timestep;
-  for (int i = lane; i < M.nq; i += 32) S.x_q0[i] = S.qpos[i];
-  for (int i = lane; i < M.nv; i += 32) S.x_v0[i] = S.qvel[i];
+  const int d0 = lane, d1 = lane + 32;
+  const bool a0 = active && d0 < M.nv, a1 = active && d1 < M.nv;
+  if (active) for (int i = lane; i < M.nq; i += 32) S.x_q0[i] = S.qpos[i];
+  const float v00 = a0 ? S.qvel[d0] : 0.f, v01 = a1 ? S.qvel[d1] : 0.f;
   __syncwarp();
-  float zc = forward_eval(M, S, lane, nullptr);
-  const float Bw[4] = {1.f / 6.f, 1.f / 3.f, 1.f / 3.f, 1.f / 6.f};
-  const float Ac[3] = {0.5f, 0.5f, 1.f};
-  for (int i = lane; i < M.nv; i += 32) { S.x_sv[i] = Bw[0] * S.qvel[i]; S.x_sa[i] = Bw[0] * S.qacc[i]; }
-  __syncwarp();
-  for (int st = 1; st < 4; st++) {
-    const float a = Ac[st - 1];
-    // X[st] = X0 (+) h * a * (V[st-1], F[st-1])
-    for (int i = lane; i < M.nv; i += 32) {
-      S.x_dv[i] = a * S.qvel[i];
-      S.qvel[i] = S.x_v0[i] + h * (a * S.qacc[i]);
+  float zc = 0.f, sv0 = 0.f, sv1 = 0.f, sa0 = 0.f, sa1 = 0.f;
+#pragma unroll 1
+  for (int st = 0; st < 4; st++) {
+    if (st > 0) {
+      // X[st] = X0 (+) h * a * (V[st-1], F[st-1])
+      const float a = st == 3 ? 1.f : 0.5f;
+      if (a0) { S.x_dv[d0] = a * S.qvel[d0]; S.qvel[d0] = v00 + h * (a * S.qacc[d0]); }
+      if (a1) { S.x_dv[d1] = a * S.qvel[d1]; S.qvel[d1] = v01 + h * (a * S.qacc[d1]); }
+      __syncwarp();
+      if (active) integrate_pos(M, S, lane, h);
+      __syncwarp();
     }
-    __syncwarp();
-    integrate_pos(M, S, lane, h);
-    __syncwarp();
-    zc = forward_eval(M, S, lane, nullptr);
-    for (int i = lane; i < M.nv; i += 32) { S.x_sv[i] += Bw[st] * S.qvel[i]; S.x_sa[i] += Bw[st] * S.qacc[i]; }
-    __syncwarp();
+    zc = forward_eval<LOCKSTEP>(M, S, lane, nullptr, active);
+    const float bw = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);
+    if (a0) { sv0 += bw * S.qvel[d0]; sa0 += bw * S.qacc[d0]; }
+    if (a1) { sv1 += bw * S.qvel[d1]; sa1 += bw * S.qacc[d1]; }
   }
-  for (int i = lane; i < M.nv; i += 32) { S.x_dv[i] = S.x_sv[i]; S.qvel[i] = S.x_v0[i] + h * S.x_sa[i]; }
+  if (a0) { S.x_dv[d0] = sv0; S.qvel[d0] = v00 + h * sa0; }
+  if (a1) { S.x_dv[d1] = sv1; S.qvel[d1] = v01 + h * sa1; }
   __syncwarp();
-  integrate_pos(M, S, lane, h);
+  if (active) integrate_pos(M, S, lane, h);
   __syncwarp();
   return zc;
 }
@@ -197,7 +203,7 @@ __device__ float reward_imitate(const ModelS& M, EnvS& S, const DevPtrs& P, int 
   for (int d = lane; d < M.nv; d += 32) {
     const float qv = S.qvel[d];
 #pragma unroll
-    for (int k = 0; k < 6; k++) S.buf6[6 * d + k] = S.cdof[6 * d + k] * qv;
+    for (int k = 0; k < 6; k++) S.u.a.buf6[6 * d + k] = S.cdof[6 * d + k] * qv;
   }
   __syncwarp();
   // CoM velocity: sum_b m_b (v_lin + w x (xipos_b - com)) / M
@@ -210,9 +216,9 @@ __device__ float reward_imitate(const ModelS& M, EnvS& S, const DevPtrs& P, int 
       const int d = __ffsll((long long)mk) - 1;
       mk &= mk - 1;
 #pragma unroll
-      for (int k = 0; k < 6; k++) v[k] += S.buf6[6 * d + k];
+      for (int k = 0; k < 6; k++) v[k] += S.u.a.buf6[6 * d + k];
     }
-    const V3 r = ld3(&S.xipos[3 * b]) - ld3(S.com);
+    const V3 r = ld3(&S.u.a.xipos[3 * b]) - ld3(S.com);
     const V3 vb = v3(v[3], v[4], v[5]) + cross(v3(v[0], v[1], v[2]), r);
     const float ms = M.body_mass[b];
     px = ms * vb.x; py = ms * vb.y; pz = ms * vb.z;
@@ -222,13 +228,13 @@ __device__ float reward_imitate(const ModelS& M, EnvS& S, const DevPtrs& P, int 
   // end effectors in the root heading frame (lane = end effector)
   float ee = 0.f;
   if (lane < M.nee) {
-    const float* R = &S.xmat[9];
+    const float* R = &S.u.a.xmat[9];
     const float heading = atan2f(R[3], R[0]);
     float sh, ch;
     sincosf(heading, &sh, &ch);
     const int b = M.ee_body[lane];
-    const V3 w = ld3(&S.xpos[3 * b]) + mat_vec(&S.xmat[9 * b], ld3(M.ee_pos[lane]));
-    const float rx = w.x - S.xpos[3], ry = w.y - S.xpos[4];
+    const V3 w = ld3(&S.u.a.xpos[3 * b]) + mat_vec(&S.u.a.xmat[9 * b], ld3(M.ee_pos[lane]));
+    const float rx = w.x - S.u.a.xpos[3], ry = w.y - S.u.a.xpos[4];
     const float e0 = ch * rx + sh * ry - aux[3 * lane], e1 = -sh * rx + ch * ry - aux[3 * lane + 1],
                 e2 = w.z - aux[3 * lane + 2];
     ee = e0 * e0 + e1 * e1 + e2 * e2;
@@ -290,6 +296,7 @@ __device__ __forceinline__ void stage_model(ModelS* dst, const ModelS* src) {
 
 constexpr size_t MODEL_BYTES = (sizeof(ModelS) + 15) & ~(size_t)15;
 
+template <bool LOCKSTEP>
 __global__ void k_step(DevPtrs P, dmb_state_t st, const float* __restrict__ action, dmb_step_out_t out, int N,
                        unsigned long long seed, unsigned first_env_id) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -299,15 +306,24 @@ __global__ void k_step(DevPtrs P, dmb_state_t st, const float* __restrict__ acti
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
   EnvS& S = tiles[warp];
   const int od = (M.nq - 7) + (M.nv - 6);
-  for (int env = blockIdx.x * W + warp; env < N; env += gridDim.x * W) {
-    load_state(M, S, st, env, lane);
-    bool bad = state_bad(M, S, lane);
-    float zc = 0.f;
-    if (!bad) {
-      set_ctrl(M, S, action, env, lane);
-      zc = rk4_step(M, S, lane);
+  (void)W;
+  for (;;) {
+    // dynamic scheduling: env cost varies 2-3x with the number of active constraints
+    int env = 0;
+    if (lane == 0) env = atomicAdd(P.counter, 1);
+    env = __shfl_sync(DMB_FULL, env, 0);
+    const bool have = env < N;
+    if (LOCKSTEP) { if (!__syncthreads_or(have ? 1 : 0)) break; }
+    else if (!have) break;
+    bool bad = false;
+    if (have) {
+      load_state(M, S, st, env, lane);
       bad = state_bad(M, S, lane);
+      if (!bad) set_ctrl(M, S, action, env, lane);
     }
+    const float zc = rk4_step<LOCKSTEP>(M, S, lane, have && !bad);
+    if (!have) continue;
+    if (!bad) bad = state_bad(M, S, lane);
     // reward (dp_env_v3.py:117 / 89-104)
     float rew = 1.0f;
     int idx_curr = st.idx_curr[env];
@@ -405,9 +421,7 @@ __global__ void k_forward_debug(DevPtrs P, dmb_state_t st, const float* __restri
     float* row = dbgout + (size_t)env * dbg::stride;
     for (int i = lane; i < dbg::stride; i += 32) row[i] = 0.f;
     __syncwarp();
-    const float zc = forward_eval(M, S, lane, row);
-    for (int i = lane; i < M.nbody * 3; i += 32) { row[dbg::xpos + i] = S.xpos[i]; row[dbg::xipos + i] = S.xipos[i]; }
-    for (int i = lane; i < M.nbody * 4; i += 32) row[dbg::xquat + i] = S.xquat[i];
+    const float zc = forward_eval<false>(M, S, lane, row, true);
     for (int i = lane; i < M.nbody * 6; i += 32) row[dbg::cvel + i] = S.cvel[i];
     for (int i = lane; i < M.nv; i += 32) row[dbg::qacc + i] = S.qacc[i];
     for (int r = lane; r < S.nefc; r += 32) row[dbg::efc_force + r] = S.e_f[r];
@@ -445,8 +459,10 @@ struct dmb_handle_s {
   ModelS hmodel;
   ModelS* dmodel = nullptr;
   float *d_cfg = nullptr, *d_vel = nullptr, *d_aux = nullptr;
+  int* d_counter = nullptr;
   int grid = 0, block = 0, smem = 0, envs_per_cta = 0;
   int nu = 0, obs_dim = 0;
+  int lockstep = 1;
   std::string err;
 };
 
@@ -466,8 +482,8 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
   memset(&S, 0, sizeof(S));
   if (m->nv > NVC || m->nq > NQC || m->nbody > NB || m->njnt > NJ || m->ngeom > NG || m->npair > NP || m->nu > NU ||
       m->nM > NMX || m->nv > 64) { why = "model exceeds kernel capacities"; return DMB_ERR_MODEL; }
-  if (m->max_efc > MAXROW - 1 || m->max_con > MAXC || m->max_con > 32 || m->max_efc < m->njnt) {
-    why = "max_efc must be <= 63 and >= njnt, max_con <= 24"; return DMB_ERR_MODEL;
+  if (m->max_efc > MAXROW || m->max_con > MAXC || m->max_con > 32 || m->max_efc < m->njnt) {
+    why = "max_efc must be <= 48 and >= njnt, max_con <= 16 (kernel capacities)"; return DMB_ERR_MODEL;
   }
   S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.nbody = m->nbody; S.njnt = m->njnt; S.ngeom = m->ngeom;
   S.npair = m->npair; S.nM = m->nM; S.iterations = m->iterations; S.max_con = m->max_con; S.max_efc = m->max_efc;
@@ -543,6 +559,7 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
     if (S.dof_kind[d] == DOF_HINGE) for (int a = m->dof_parentid[d]; a >= 0; a = m->dof_parentid[a]) mk |= 1ull << a;
     else if (S.dof_kind[d] == DOF_FREE_ROT) for (int k = 0; k < 3; k++) mk |= 1ull << (m->jnt_dofadr[j] + k);
     S.dof_velmask[d] = mk;
+    { unsigned long long am = 0; for (int a = m->dof_parentid[d]; a >= 0; a = m->dof_parentid[a]) am |= 1ull << a; S.dof_ancmask[d] = am; }
     int e = m->dof_Madr[d];
     for (int a = d; a >= 0; a = m->dof_parentid[a]) { S.M_i[e] = (uint8_t)d; S.M_j[e] = (uint8_t)a; e++; }
   }
@@ -588,6 +605,7 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
 extern "C" {
 
 int dmb_version(void) { return DMB_VERSION; }
+int32_t dmb_sizeof_tile(void) { return (int32_t)sizeof(EnvS); }
 int32_t dmb_sizeof_model(void) { return (int32_t)sizeof(dmb_model_t); }
 int32_t dmb_sizeof_config(void) { return (int32_t)sizeof(dmb_config_t); }
 int32_t dmb_sizeof_mocap(void) { return (int32_t)sizeof(dmb_mocap_t); }
@@ -637,6 +655,7 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
   };
   e = cudaMalloc((void**)&h->dmodel, sizeof(ModelS));
   if (e == cudaSuccess) e = cudaMemcpy(h->dmodel, &h->hmodel, sizeof(ModelS), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_counter, sizeof(int));
   if (e == cudaSuccess) e = upload(mocap->data_config, ncfg, &h->d_cfg);
   if (e == cudaSuccess) e = upload(mocap->data_vel, nvel, &h->d_vel);
   if (e == cudaSuccess) e = upload(mocap->ref_aux, naux, &h->d_aux);
@@ -649,12 +668,22 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
   const size_t maxsmem = prop.sharedMemPerBlockOptin;
   int W = (int)((maxsmem - MODEL_BYTES) / sizeof(EnvS));
   if (W > 16) W = 16;
+  {  // the register file bounds the resident warps as well
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, (const void*)k_step<true>);
+    if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, cudaGetErrorString(e)); }
+    const int regs = ((fa.numRegs + 7) / 8) * 8;
+    const int wreg = prop.regsPerMultiprocessor / (32 * (regs > 0 ? regs : 1));
+    if (W > wreg) W = wreg;
+  }
+  if (const char* lenv = getenv("DMB_LOCKSTEP")) h->lockstep = atoi(lenv) != 0;
+  if (const char* wenv = getenv("DMB_ENVS_PER_CTA")) { int w = atoi(wenv); if (w >= 1 && w < W) W = w; }
   if (W < 1) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, "not enough shared memory for one env tile"); }
   h->envs_per_cta = W; h->block = 32 * W;
   h->smem = (int)(MODEL_BYTES + (size_t)W * sizeof(EnvS));
   int need = (num_envs + W - 1) / W;
   h->grid = need < prop.multiProcessorCount ? need : prop.multiProcessorCount;
-  for (auto fn : {(const void*)k_step, (const void*)k_reset, (const void*)k_forward_debug}) {
+  for (auto fn : {(const void*)k_step<false>, (const void*)k_step<true>, (const void*)k_reset, (const void*)k_forward_debug}) {
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
     if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
   }
@@ -665,7 +694,7 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
 int dmb_destroy(dmb_handle_t h) {
   if (!h) return DMB_ERR_ARG;
   cudaSetDevice(h->device);
-  cudaFree(h->dmodel); cudaFree(h->d_cfg); cudaFree(h->d_vel); cudaFree(h->d_aux);
+  cudaFree(h->d_counter); cudaFree(h->dmodel); cudaFree(h->d_cfg); cudaFree(h->d_vel); cudaFree(h->d_aux);
   delete h;
   return DMB_OK;
 }
@@ -674,7 +703,7 @@ static bool state_ok(const dmb_state_t* st) {
   return st && st->qpos && st->qvel && st->warm && st->clip && st->idx_init && st->idx_curr && st->reset_count &&
          st->ep_len && st->ep_ret && st->flags;
 }
-static DevPtrs devptrs(dmb_handle_t h) { DevPtrs P; P.model = h->dmodel; P.mocap_cfg = h->d_cfg; P.mocap_vel = h->d_vel; P.ref_aux = h->d_aux; return P; }
+static DevPtrs devptrs(dmb_handle_t h) { DevPtrs P; P.counter = h->d_counter; P.model = h->dmodel; P.mocap_cfg = h->d_cfg; P.mocap_vel = h->d_vel; P.ref_aux = h->d_aux; return P; }
 
 int dmb_reset(dmb_handle_t h, const dmb_state_t* st, const uint8_t* mask, int32_t mode, float* obs, void* stream) {
   if (!h) return DMB_ERR_ARG;
@@ -689,7 +718,9 @@ int dmb_step(dmb_handle_t h, const dmb_state_t* st, const float* action, const d
   if (!h) return DMB_ERR_ARG;
   if (!state_ok(st) || !action || !out || !out->obs || !out->reward || !out->done) return fail(h, DMB_ERR_ARG, "dmb_step: bad argument");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  k_step<<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
+  CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), (cudaStream_t)stream));
+  if (h->lockstep) k_step<true><<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
+  else k_step<false><<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
   CUDA_TRY(h, cudaGetLastError());
   return DMB_OK;
 }

@@ -15,15 +15,15 @@ namespace dmb {
 // mj_kinematics: lane = body, one tree level per round.  Also writes the world-frame hinge
 // axes into cdof[.][0:3] (the angular part of cdof) and the geom poses (lane = geom).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void kinematics(const ModelS& M, EnvS& S, int lane) {
+__device__ __noinline__ void kinematics(const ModelS& M, EnvS& S, int lane) {
   const int b = lane;
   const bool act = b >= 1 && b < M.nbody;
   if (lane == 0) {
-    S.xpos[0] = S.xpos[1] = S.xpos[2] = 0.f;
-    S.xquat[0] = 1.f; S.xquat[1] = S.xquat[2] = S.xquat[3] = 0.f;
-    S.xmat[0] = 1.f; S.xmat[1] = 0.f; S.xmat[2] = 0.f; S.xmat[3] = 0.f; S.xmat[4] = 1.f; S.xmat[5] = 0.f;
-    S.xmat[6] = 0.f; S.xmat[7] = 0.f; S.xmat[8] = 1.f;
-    S.xipos[0] = S.xipos[1] = S.xipos[2] = 0.f;
+    S.u.a.xpos[0] = S.u.a.xpos[1] = S.u.a.xpos[2] = 0.f;
+    S.u.a.xquat[0] = 1.f; S.u.a.xquat[1] = S.u.a.xquat[2] = S.u.a.xquat[3] = 0.f;
+    S.u.a.xmat[0] = 1.f; S.u.a.xmat[1] = 0.f; S.u.a.xmat[2] = 0.f; S.u.a.xmat[3] = 0.f; S.u.a.xmat[4] = 1.f; S.u.a.xmat[5] = 0.f;
+    S.u.a.xmat[6] = 0.f; S.u.a.xmat[7] = 0.f; S.u.a.xmat[8] = 1.f;
+    S.u.a.xipos[0] = S.u.a.xipos[1] = S.u.a.xipos[2] = 0.f;
   }
   // half-angle sin/cos of this body's hinge joints (independent of the parent pose)
   float sn[JPB], cs[JPB];
@@ -43,8 +43,8 @@ __device__ __forceinline__ void kinematics(const ModelS& M, EnvS& S, int lane) {
   for (int lev = 1; lev <= M.maxdepth; lev++) {
     if (act && depth == lev) {
       const int p = M.body_parent[b];
-      V3 pos = ld3(&S.xpos[3 * p]) + mat_vec(&S.xmat[9 * p], ld3(M.body_pos[b]));
-      Q4 qp; qp.w = S.xquat[4 * p]; qp.x = S.xquat[4 * p + 1]; qp.y = S.xquat[4 * p + 2]; qp.z = S.xquat[4 * p + 3];
+      V3 pos = ld3(&S.u.a.xpos[3 * p]) + mat_vec(&S.u.a.xmat[9 * p], ld3(M.body_pos[b]));
+      Q4 qp; qp.w = S.u.a.xquat[4 * p]; qp.x = S.u.a.xquat[4 * p + 1]; qp.y = S.u.a.xquat[4 * p + 2]; qp.z = S.u.a.xquat[4 * p + 3];
       Q4 qb; qb.w = M.body_quat[b][0]; qb.x = M.body_quat[b][1]; qb.y = M.body_quat[b][2]; qb.z = M.body_quat[b][3];
       Q4 quat = qmul(qp, qb);
 #pragma unroll
@@ -65,57 +65,40 @@ __device__ __forceinline__ void kinematics(const ModelS& M, EnvS& S, int lane) {
         }
       }
       quat = qnormalize(quat);
-      st3(&S.xpos[3 * b], pos);
-      S.xquat[4 * b] = quat.w; S.xquat[4 * b + 1] = quat.x; S.xquat[4 * b + 2] = quat.y; S.xquat[4 * b + 3] = quat.z;
+      st3(&S.u.a.xpos[3 * b], pos);
+      S.u.a.xquat[4 * b] = quat.w; S.u.a.xquat[4 * b + 1] = quat.x; S.u.a.xquat[4 * b + 2] = quat.y; S.u.a.xquat[4 * b + 3] = quat.z;
       float m[9];
       quat2mat(m, quat);
 #pragma unroll
-      for (int k = 0; k < 9; k++) S.xmat[9 * b + k] = m[k];
-      st3(&S.xipos[3 * b], pos + mat_vec(m, ld3(M.body_ipos[b])));
+      for (int k = 0; k < 9; k++) S.u.a.xmat[9 * b + k] = m[k];
+      st3(&S.u.a.xipos[3 * b], pos + mat_vec(m, ld3(M.body_ipos[b])));
     }
     __syncwarp();
   }
-  // geoms
-  if (lane < M.ngeom) {
-    const int g = lane, gb = M.geom_bodyid[g];
-    st3(&S.gpos[3 * g], ld3(&S.xpos[3 * gb]) + mat_vec(&S.xmat[9 * gb], ld3(M.geom_pos[g])));
-    if (M.geom_identq[g]) {
-#pragma unroll
-      for (int k = 0; k < 9; k++) S.gmat[9 * g + k] = S.xmat[9 * gb + k];
-    } else {
-      Q4 qb; qb.w = S.xquat[4 * gb]; qb.x = S.xquat[4 * gb + 1]; qb.y = S.xquat[4 * gb + 2]; qb.z = S.xquat[4 * gb + 3];
-      Q4 qg; qg.w = M.geom_quat[g][0]; qg.x = M.geom_quat[g][1]; qg.y = M.geom_quat[g][2]; qg.z = M.geom_quat[g][3];
-      float m[9];
-      quat2mat(m, qmul(qb, qg));
-#pragma unroll
-      for (int k = 0; k < 9; k++) S.gmat[9 * g + k] = m[k];
-    }
-  }
-  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
 // mj_comPos: whole-model CoM (warp-shuffle reduction over bodies), cinert (lane = body),
 // cdof (lane = dof).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void com_pos(const ModelS& M, EnvS& S, int lane) {
+__device__ __noinline__ void com_pos(const ModelS& M, EnvS& S, int lane) {
   const int b = lane;
   const bool act = b >= 1 && b < M.nbody;
   float ms = act ? M.body_mass[b] : 0.f;
-  V3 xi = act ? ld3(&S.xipos[3 * b]) : v3(0.f, 0.f, 0.f);
+  V3 xi = act ? ld3(&S.u.a.xipos[3 * b]) : v3(0.f, 0.f, 0.f);
   float cx = warp_sum(ms * xi.x) * M.inv_total_mass;
   float cy = warp_sum(ms * xi.y) * M.inv_total_mass;
   float cz = warp_sum(ms * xi.z) * M.inv_total_mass;
   if (lane == 0) { S.com[0] = cx; S.com[1] = cy; S.com[2] = cz; }
   const V3 com = v3(cx, cy, cz);
   if (lane < M.nbody) {
-    float* ci = &S.cinert[10 * b];
+    float* ci = &S.u.a.cinert[10 * b];
     if (!act) {
 #pragma unroll
       for (int k = 0; k < 10; k++) ci[k] = 0.f;
     } else {
       const float* I = M.body_inertia[b];
-      const float* R = &S.xmat[9 * b];
+      const float* R = &S.u.a.xmat[9 * b];
       // W = R * Ib * R'
       float Ib[9] = {I[0], I[3], I[4], I[3], I[1], I[5], I[4], I[5], I[2]};
       float RI[9], W[9];
@@ -139,7 +122,7 @@ __device__ __forceinline__ void com_pos(const ModelS& M, EnvS& S, int lane) {
   }
   for (int d = lane; d < M.nv; d += 32) {
     const int db = M.dof_bodyid[d];
-    const V3 off = com - ld3(&S.xpos[3 * db]);
+    const V3 off = com - ld3(&S.u.a.xpos[3 * db]);
     float* cd = &S.cdof[6 * d];
     const int kind = M.dof_kind[d], k = M.dof_axisk[d];
     if (kind == DOF_FREE_TRANS) {
@@ -147,7 +130,7 @@ __device__ __forceinline__ void com_pos(const ModelS& M, EnvS& S, int lane) {
       cd[3] = k == 0 ? 1.f : 0.f; cd[4] = k == 1 ? 1.f : 0.f; cd[5] = k == 2 ? 1.f : 0.f;
     } else {
       V3 ax;
-      if (kind == DOF_FREE_ROT) { ax = v3(S.xmat[9 * db + k], S.xmat[9 * db + 3 + k], S.xmat[9 * db + 6 + k]); st3(cd, ax); }
+      if (kind == DOF_FREE_ROT) { ax = v3(S.u.a.xmat[9 * db + k], S.u.a.xmat[9 * db + 3 + k], S.u.a.xmat[9 * db + 6 + k]); st3(cd, ax); }
       else ax = ld3(cd);  // written by kinematics()
       st3(cd + 3, cross(ax, off));
     }
@@ -159,11 +142,11 @@ __device__ __forceinline__ void com_pos(const ModelS& M, EnvS& S, int lane) {
 // mj_crb + mj_factorM: composite inertias (parents gather children, level by level), the
 // nM sparse inertia entries (lane = entry) and the in-place sparse L'DL factorisation.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, float* dbg_qM) {
+__device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, float* dbg_qM) {
   const int b = lane;
   if (lane < M.nbody) {
 #pragma unroll
-    for (int k = 0; k < 10; k++) S.crb[10 * b + k] = S.cinert[10 * b + k];
+    for (int k = 0; k < 10; k++) S.u.a.crb[10 * b + k] = S.u.a.cinert[10 * b + k];
   }
   __syncwarp();
   for (int lev = M.maxdepth - 1; lev >= 1; lev--) {
@@ -172,17 +155,17 @@ __device__ __forceinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, f
       for (int c = 0; c < nc; c++) {
         const int ch = M.body_child[b][c];
 #pragma unroll
-        for (int k = 0; k < 10; k++) S.crb[10 * b + k] += S.crb[10 * ch + k];
+        for (int k = 0; k < 10; k++) S.u.a.crb[10 * b + k] += S.u.a.crb[10 * ch + k];
       }
     }
     __syncwarp();
   }
-  for (int d = lane; d < M.nv; d += 32) mul_inert_vec(&S.buf6[6 * d], &S.crb[10 * M.dof_bodyid[d]], &S.cdof[6 * d]);
+  for (int d = lane; d < M.nv; d += 32) mul_inert_vec(&S.u.a.buf6[6 * d], &S.u.a.crb[10 * M.dof_bodyid[d]], &S.cdof[6 * d]);
   __syncwarp();
   for (int e = lane; e < M.nM; e += 32) {
     const int i = M.M_i[e], j = M.M_j[e];
     const float* a = &S.cdof[6 * j];
-    const float* bf = &S.buf6[6 * i];
+    const float* bf = &S.u.a.buf6[6 * i];
     float s = a[0] * bf[0] + a[1] * bf[1] + a[2] * bf[2] + a[3] * bf[3] + a[4] * bf[4] + a[5] * bf[5];
     if (i == j) s += M.dof_armature[i];
     S.qLD[e] = s;
@@ -217,12 +200,12 @@ __device__ __forceinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, f
 // mj_comVel + mj_rne(flg_acc=0) + passive + actuation: leaves the smooth generalised force
 // qfrc_smooth = passive - bias + actuator in S.vec0.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void smooth_forces(const ModelS& M, EnvS& S, int lane, float* dbg_bias) {
+__device__ __noinline__ void smooth_forces(const ModelS& M, EnvS& S, int lane, float* dbg_bias) {
   // w[a] = cdof[a] * qvel[a]
   for (int d = lane; d < M.nv; d += 32) {
     const float qv = S.qvel[d];
 #pragma unroll
-    for (int k = 0; k < 6; k++) S.buf6[6 * d + k] = S.cdof[6 * d + k] * qv;
+    for (int k = 0; k < 6; k++) S.u.a.buf6[6 * d + k] = S.cdof[6 * d + k] * qv;
   }
   __syncwarp();
   // cdof_dot[d] = crossMotion(velocity seen by dof d, cdof[d])
@@ -233,13 +216,13 @@ __device__ __forceinline__ void smooth_forces(const ModelS& M, EnvS& S, int lane
       const int a = __ffsll((long long)mk) - 1;
       mk &= mk - 1;
 #pragma unroll
-      for (int k = 0; k < 6; k++) v[k] += S.buf6[6 * a + k];
+      for (int k = 0; k < 6; k++) v[k] += S.u.a.buf6[6 * a + k];
     }
     if (M.dof_kind[d] == DOF_FREE_TRANS) {
 #pragma unroll
-      for (int k = 0; k < 6; k++) S.cdofd[6 * d + k] = 0.f;
+      for (int k = 0; k < 6; k++) S.u.a.cdofd[6 * d + k] = 0.f;
     } else {
-      cross_motion(&S.cdofd[6 * d], v, &S.cdof[6 * d]);
+      cross_motion(&S.u.a.cdofd[6 * d], v, &S.cdof[6 * d]);
     }
   }
   __syncwarp();
@@ -254,21 +237,21 @@ __device__ __forceinline__ void smooth_forces(const ModelS& M, EnvS& S, int lane
       mk &= mk - 1;
       const float qv = S.qvel[d];
 #pragma unroll
-      for (int k = 0; k < 6; k++) { v[k] += S.buf6[6 * d + k]; a[k] += S.cdofd[6 * d + k] * qv; }
+      for (int k = 0; k < 6; k++) { v[k] += S.u.a.buf6[6 * d + k]; a[k] += S.u.a.cdofd[6 * d + k] * qv; }
     }
     float f[6], t1[6], t2[6];
     if (b == 0) {
 #pragma unroll
       for (int k = 0; k < 6; k++) { f[k] = 0.f; v[k] = 0.f; }
     } else {
-      mul_inert_vec(f, &S.cinert[10 * b], a);
-      mul_inert_vec(t1, &S.cinert[10 * b], v);
+      mul_inert_vec(f, &S.u.a.cinert[10 * b], a);
+      mul_inert_vec(t1, &S.u.a.cinert[10 * b], v);
       cross_force(t2, v, t1);
 #pragma unroll
       for (int k = 0; k < 6; k++) f[k] += t2[k];
     }
 #pragma unroll
-    for (int k = 0; k < 6; k++) { S.cvel[6 * b + k] = v[k]; S.cfrc[6 * b + k] = f[k]; }
+    for (int k = 0; k < 6; k++) { S.cvel[6 * b + k] = v[k]; S.u.a.cfrc[6 * b + k] = f[k]; }
   }
   __syncwarp();
   for (int lev = M.maxdepth - 1; lev >= 1; lev--) {
@@ -278,17 +261,37 @@ __device__ __forceinline__ void smooth_forces(const ModelS& M, EnvS& S, int lane
       for (int c = 0; c < nc; c++) {
         const int ch = M.body_child[b][c];
 #pragma unroll
-        for (int k = 0; k < 6; k++) S.cfrc[6 * b + k] += S.cfrc[6 * ch + k];
+        for (int k = 0; k < 6; k++) S.u.a.cfrc[6 * b + k] += S.u.a.cfrc[6 * ch + k];
       }
     }
     __syncwarp();
   }
   for (int d = lane; d < M.nv; d += 32) {
     const float* cd = &S.cdof[6 * d];
-    const float* cf = &S.cfrc[6 * M.dof_bodyid[d]];
+    const float* cf = &S.u.a.cfrc[6 * M.dof_bodyid[d]];
     const float bias = cd[0] * cf[0] + cd[1] * cf[1] + cd[2] * cf[2] + cd[3] * cf[3] + cd[4] * cf[4] + cd[5] * cf[5];
     if (dbg_bias) dbg_bias[d] = bias;
     S.vec0[d] = -M.dof_damping[d] * S.qvel[d] - bias + S.ctrlf[d];
+  }
+  __syncwarp();
+}
+
+// geom poses (lane = geom); runs after the smooth stage, writing over dead phase-A arrays
+__device__ __forceinline__ void geom_poses(const ModelS& M, EnvS& S, int lane) {
+  if (lane < M.ngeom) {
+    const int g = lane, gb = M.geom_bodyid[g];
+    st3(&S.u.b.gpos[3 * g], ld3(&S.u.b.xpos[3 * gb]) + mat_vec(&S.u.b.xmat[9 * gb], ld3(M.geom_pos[g])));
+    if (M.geom_identq[g]) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) S.u.b.gmat[9 * g + k] = S.u.b.xmat[9 * gb + k];
+    } else {
+      Q4 qb; qb.w = S.u.b.xquat[4 * gb]; qb.x = S.u.b.xquat[4 * gb + 1]; qb.y = S.u.b.xquat[4 * gb + 2]; qb.z = S.u.b.xquat[4 * gb + 3];
+      Q4 qg; qg.w = M.geom_quat[g][0]; qg.x = M.geom_quat[g][1]; qg.y = M.geom_quat[g][2]; qg.z = M.geom_quat[g][3];
+      float m[9];
+      quat2mat(m, qmul(qb, qg));
+#pragma unroll
+      for (int k = 0; k < 9; k++) S.u.b.gmat[9 * g + k] = m[k];
+    }
   }
   __syncwarp();
 }
@@ -483,7 +486,7 @@ __device__ __forceinline__ void make_frame(float* f, V3 n, V3 y) {
 // mj_collision: broad phase (lane = candidate pair, 4 rounds) -> compacted survivor list ->
 // narrow phase (lane = survivor) -> contacts compacted in pair order by warp prefix sums.
 // ------------------------------------------------------------------------------------------
-__device__ void collision(const ModelS& M, EnvS& S, int lane) {
+__device__ __noinline__ void collision(const ModelS& M, EnvS& S, int lane) {
   const float margin = M.margin;
   int nsurv = 0;
   for (int base = 0; base < M.npair; base += 32) {
@@ -491,9 +494,9 @@ __device__ void collision(const ModelS& M, EnvS& S, int lane) {
     bool keep = false;
     if (p < M.npair) {
       const int g1 = M.pair_g1[p], g2 = M.pair_g2[p];
-      const V3 dif = ld3(&S.gpos[3 * g2]) - ld3(&S.gpos[3 * g1]);
+      const V3 dif = ld3(&S.u.b.gpos[3 * g2]) - ld3(&S.u.b.gpos[3 * g1]);
       if (M.geom_type[g1] == DMB_GEOM_PLANE) {
-        const V3 nrm = v3(S.gmat[9 * g1 + 2], S.gmat[9 * g1 + 5], S.gmat[9 * g1 + 8]);
+        const V3 nrm = v3(S.u.b.gmat[9 * g1 + 2], S.u.b.gmat[9 * g1 + 5], S.u.b.gmat[9 * g1 + 8]);
         keep = !(dot(dif, nrm) > M.geom_rbound[g2] + margin);
       } else {
         const float bound = M.geom_rbound[g1] + M.geom_rbound[g2] + margin;
@@ -501,7 +504,7 @@ __device__ void collision(const ModelS& M, EnvS& S, int lane) {
       }
     }
     const unsigned bal = __ballot_sync(DMB_FULL, keep);
-    if (keep) S.surv[nsurv + __popc(bal & ((1u << lane) - 1u))] = p;
+    if (keep) S.u.b.surv[nsurv + __popc(bal & ((1u << lane) - 1u))] = p;
     nsurv += __popc(bal);
   }
   __syncwarp();
@@ -510,12 +513,12 @@ __device__ void collision(const ModelS& M, EnvS& S, int lane) {
     RawCon rc[4];
     int n = 0, g1 = 0, g2 = 0;
     if (base + lane < nsurv) {
-      const int p = S.surv[base + lane];
+      const int p = S.u.b.surv[base + lane];
       g1 = M.pair_g1[p]; g2 = M.pair_g2[p];
       const int t1 = M.geom_type[g1], t2 = M.geom_type[g2];
-      const V3 pos1 = ld3(&S.gpos[3 * g1]), pos2 = ld3(&S.gpos[3 * g2]);
-      const float* mat1 = &S.gmat[9 * g1];
-      const float* mat2 = &S.gmat[9 * g2];
+      const V3 pos1 = ld3(&S.u.b.gpos[3 * g1]), pos2 = ld3(&S.u.b.gpos[3 * g2]);
+      const float* mat1 = &S.u.b.gmat[9 * g1];
+      const float* mat2 = &S.u.b.gmat[9 * g2];
       const V3 s1 = ld3(M.geom_size[g1]), s2 = ld3(M.geom_size[g2]);
       if (t1 == DMB_GEOM_PLANE) {
         const V3 nrm = v3(mat1[2], mat1[5], mat1[8]);
@@ -585,7 +588,7 @@ __device__ void collision(const ModelS& M, EnvS& S, int lane) {
 // Limit rows come first (joint order, lower then upper), then contacts in contact order:
 // 1 frictionless row (condim 1) or 4 pyramid edges (condim 3).
 // ------------------------------------------------------------------------------------------
-__device__ void make_constraint(const ModelS& M, EnvS& S, int lane) {
+__device__ __noinline__ void make_constraint(const ModelS& M, EnvS& S, int lane) {
   int* e_src = S.e_src;
   // ---- joint limits: lane = joint
   int cnt = 0;
@@ -663,7 +666,6 @@ __device__ void make_constraint(const ModelS& M, EnvS& S, int lane) {
         S.Y[(a + 3) * YS + d] = jn - mu * j2;
       }
     }
-    S.Y[nefc * YS + d] = S.vec0[d];  // smooth force rides along as the last row
   }
   // ---- per-row impedance, R, aref: lane = row
   for (int r = lane; r < nefc; r += 32) {
@@ -720,73 +722,35 @@ __device__ void make_constraint(const ModelS& M, EnvS& S, int lane) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Half solve  Y_r <- D^-1/2 L^-T Y_r  for all rows at once: lane = row, serial over dofs with
-// warp-uniform loop bounds (L entries are broadcast reads).  Dofs on which no row of the pass
-// has support are skipped with one vote.  Also builds the per-row support masks.
+// Single-vector operations on the sparse factor M = L' D L with the vector held in REGISTERS
+// (dof d on lane d & 31, register `lo` for d < 32 and `hi` for d >= 32).  One broadcast shuffle
+// and one FFMA per dof: ~30 cycles of latency per dof instead of a shared-memory round trip.
 // ------------------------------------------------------------------------------------------
-__device__ void half_solve_rows(const ModelS& M, EnvS& S, int lane, int nrows) {
-  for (int base = 0; base < nrows; base += 32) {
-    const int r = base + lane;
-    const bool act = r < nrows;
-    float* y = &S.Y[(act ? r : 0) * YS];
-    for (int i = M.nv - 1; i >= 0; i--) {
-      const float yi = act ? y[i] : 0.f;
-      if (!__any_sync(DMB_FULL, yi != 0.f)) continue;
-      const int c = M.dof_nanc[i], adr = M.dof_Madr[i] + 1;
-      if (act) {
-        for (int k = 0; k < c; k++) y[M.dof_anc[i][k]] -= S.qLD[adr + k] * yi;
-      }
-    }
-    unsigned long long mask = 0ull;
-    if (act) {
-      for (int i = 0; i < M.nv; i++) {
-        const float v = y[i] * S.dsq[i];
-        y[i] = v;
-        if (v != 0.f) mask |= 1ull << i;
-      }
-      S.rowmask[r] = mask;
-    }
+// x <- L^-T x   (leaves -> root: every dof pushes its value to its ancestors)
+__device__ __forceinline__ void reg_solve_LT(const ModelS& M, const EnvS& S, int lane, float& lo, float& hi) {
+  for (int i = M.nv - 1; i > 0; i--) {
+    const unsigned long long am = M.dof_ancmask[i];
+    if (am == 0ull) continue;
+    const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
+    if (xi == 0.f) continue;
+    const int adr = M.dof_Madr[i] + 1;
+    if ((am >> lane) & 1ull) lo -= S.qLD[adr + __popcll(am >> (lane + 1))] * xi;
+    if ((am >> 32) != 0ull && ((am >> (lane + 32)) & 1ull)) hi -= S.qLD[adr + __popcll(am >> (lane + 33))] * xi;
   }
-  __syncwarp();
 }
-
-__device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
-
-// Gram matrix AR = Y Y' + diag(R) (packed lower triangle), b = Y y_s - aref.  lane = row.
-__device__ void gram(const ModelS& M, EnvS& S, int lane, int nefc) {
-  for (int base = 0; base < nefc; base += 32) {
-    const int r = base + lane;
-    const bool act = r < nefc;
-    const float* yr = &S.Y[(act ? r : 0) * YS];
-    const int smax = min(nefc - 1, base + 31);
-    for (int s = 0; s <= smax; s++) {
-      unsigned long long mk = S.rowmask[s];
-      const float* ys = &S.Y[s * YS];
-      float acc = 0.f;
-      while (mk) {
-        const int k = __ffsll((long long)mk) - 1;
-        mk &= mk - 1;
-        acc += yr[k] * ys[k];
-      }
-      if (act && s <= r) S.AR[tri(r) + s] = (s == r) ? acc + S.e_R[r] : acc;
-    }
-    {  // b
-      unsigned long long mk = S.rowmask[nefc];
-      const float* ys = &S.Y[nefc * YS];
-      float acc = 0.f;
-      while (mk) {
-        const int k = __ffsll((long long)mk) - 1;
-        mk &= mk - 1;
-        acc += yr[k] * ys[k];
-      }
-      if (act) S.e_b[r] = acc - S.e_aref[r];
-    }
+// x <- L^-1 x   (root -> leaves: every dof pulls from its ancestors, one ancestor per step)
+__device__ __forceinline__ void reg_solve_L(const ModelS& M, const EnvS& S, int lane, float& lo, float& hi) {
+  const unsigned long long alo = lane < M.nv ? M.dof_ancmask[lane] : 0ull;
+  const unsigned long long ahi = lane + 32 < M.nv ? M.dof_ancmask[lane + 32] : 0ull;
+  const int adrlo = lane < M.nv ? M.dof_Madr[lane] + 1 : 0, adrhi = lane + 32 < M.nv ? M.dof_Madr[lane + 32] + 1 : 0;
+  for (int i = 0; i < M.nv - 1; i++) {
+    const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
+    if (xi == 0.f) continue;
+    if ((alo >> i) & 1ull) lo -= S.qLD[adrlo + __popcll(alo >> (i + 1))] * xi;
+    if ((ahi >> i) & 1ull) hi -= S.qLD[adrhi + __popcll(ahi >> (i + 1))] * xi;
   }
-  __syncwarp();
 }
-
-// single-vector ops on the sparse factor, lane = ancestor slot
-// x <- D^1/2 L x   (z-space image of an acceleration)
+// z <- D^1/2 L x  (image of an acceleration in the half-solved space), smem in / smem out
 __device__ void mul_L_sqrtD(const ModelS& M, EnvS& S, int lane, const float* x, float* z) {
   for (int i = lane; i < M.nv; i += 32) {
     const int c = M.dof_nanc[i], adr = M.dof_Madr[i] + 1;
@@ -796,100 +760,166 @@ __device__ void mul_L_sqrtD(const ModelS& M, EnvS& S, int lane, const float* x, 
   }
   __syncwarp();
 }
-// x <- L^-1 D^-1/2 t   (back substitution root -> leaves; reduction over <= MAXANC ancestors)
-__device__ void back_solve(const ModelS& M, EnvS& S, int lane, float* t) {
-  for (int i = lane; i < M.nv; i += 32) t[i] *= S.dsq[i];
-  __syncwarp();
-  for (int i = 0; i < M.nv; i++) {
-    const int c = M.dof_nanc[i];
-    if (c == 0) continue;
-    float part = 0.f;
-    if (lane < c) part = S.qLD[M.dof_Madr[i] + 1 + lane] * t[M.dof_anc[i][lane]];
-    // c <= 12 < 16: reduce over the low half-warp
-    part += __shfl_xor_sync(DMB_FULL, part, 8);
-    part += __shfl_xor_sync(DMB_FULL, part, 4);
-    part += __shfl_xor_sync(DMB_FULL, part, 2);
-    part += __shfl_xor_sync(DMB_FULL, part, 1);
-    if (lane == 0) t[i] -= part;
-    __syncwarp();
+
+// ------------------------------------------------------------------------------------------
+// Half solve  Y_r <- D^-1/2 L^-T Y_r  for all constraint rows at once: lane = row, serial over
+// dofs with warp-uniform loop bounds (L entries are broadcast reads).  The <= 12 ancestor
+// updates of one dof are independent: loads are batched ahead of the FMAs and stores.  Dofs on
+// which no row of the pass has support are skipped with one vote.  Also builds the support masks.
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ void half_solve_rows(const ModelS& M, EnvS& S, int lane, int nrows) {
+  for (int base = 0; base < nrows; base += 32) {
+    const int r = base + lane;
+    const bool act = r < nrows;
+    float* y = &S.Y[(act ? r : 0) * YS];
+    for (int i = M.nv - 1; i >= 0; i--) {
+      const float yi = act ? y[i] : 0.f;
+      if (!__any_sync(DMB_FULL, yi != 0.f)) continue;
+      const int c = M.dof_nanc[i], adr = M.dof_Madr[i] + 1;
+      if (act && yi != 0.f) {
+        float tmp[MAXANC];
+#pragma unroll
+        for (int k = 0; k < MAXANC; k++) if (k < c) tmp[k] = y[M.dof_anc[i][k]];
+#pragma unroll
+        for (int k = 0; k < MAXANC; k++) if (k < c) y[M.dof_anc[i][k]] = tmp[k] - S.qLD[adr + k] * yi;
+      }
+    }
+    if (act) {
+      unsigned long long mask = 0ull;
+      for (int i = 0; i < M.nv; i++) {
+        const float v = y[i] * S.dsq[i];
+        y[i] = v;
+        if (v != 0.f) mask |= 1ull << i;
+      }
+      S.u.c.rowmask[r] = mask;
+    }
   }
+  __syncwarp();
+}
+
+__device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
+
+// Gram matrix AR = Y Y' + diag(R) (packed lower triangle), b = Y y_s - aref.  lane = row.
+__device__ __noinline__ void gram(const ModelS& M, EnvS& S, int lane, int nefc) {
+  for (int base = 0; base < nefc; base += 32) {
+    const int r = base + lane;
+    const bool act = r < nefc;
+    const float* yr = &S.Y[(act ? r : 0) * YS];
+    const int smax = min(nefc - 1, base + 31);
+    for (int s = 0; s <= smax; s++) {
+      unsigned long long mk = S.u.c.rowmask[s];
+      const float* ys = &S.Y[s * YS];
+      float acc = 0.f;
+      while (mk) {
+        const int k = __ffsll((long long)mk) - 1;
+        mk &= mk - 1;
+        acc += yr[k] * ys[k];
+      }
+      if (act && s <= r) S.u.c.AR[tri(r) + s] = (s == r) ? acc + S.e_R[r] : acc;
+    }
+    if (act) {
+      float acc = 0.f;
+      for (int k = 0; k < M.nv; k++) acc += yr[k] * S.ys[k];
+      S.e_b[r] = acc - S.e_aref[r];
+    }
+  }
+  __syncwarp();
+}
+
+// PGS sweeps over rows [0, nefc): residuals res = AR f + b live in registers (lane = row, and
+// row + 32 when HI); a row update broadcasts its force increment and every lane applies one
+// column of AR.  All rows are scalar with force >= 0 (limits, frictionless normals, pyramid edges).
+template <bool HI>
+__device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, int nefc, float& f0, float& f1,
+                                          float& res0, float& res1) {
+  const int r0 = lane, r1 = lane + 32;
+  const bool a0 = r0 < nefc, a1 = HI && r1 < nefc;
+  const float d0 = a0 ? S.u.c.AR[tri(r0) + r0] : 1.f, d1 = a1 ? S.u.c.AR[tri(r1) + r1] : 1.f;
+  const float inv0 = 1.0f / d0, inv1 = 1.0f / d1;
+  const int t0 = tri(r0), t1 = tri(r1);
+  const int nlo = HI ? 32 : nefc;
+  int iter = 0;
+  while (iter < M.iterations) {
+    float imp = 0.f;
+    for (int i = 0; i < nlo; i++) {
+      const float fnew = fmaxf(0.f, f0 - res0 * inv0);
+      const float delta = __shfl_sync(DMB_FULL, fnew - f0, i);
+      if (delta != 0.f) {
+        if (lane == i) { imp -= 0.5f * delta * delta * d0 + delta * res0; f0 = fnew; }
+        res0 += S.u.c.AR[r0 >= i ? t0 + i : tri(i) + r0] * delta;
+        if (HI && a1) res1 += S.u.c.AR[t1 + i] * delta;   // r1 >= 32 > i
+      }
+    }
+    if (HI) {
+      for (int i = 32; i < nefc; i++) {
+        const float fnew = fmaxf(0.f, f1 - res1 * inv1);
+        const float delta = __shfl_sync(DMB_FULL, fnew - f1, i - 32);
+        if (delta != 0.f) {
+          if (lane == i - 32) { imp -= 0.5f * delta * delta * d1 + delta * res1; f1 = fnew; }
+          res0 += S.u.c.AR[tri(i) + r0] * delta;     // i >= 32 > r0
+          if (a1) res1 += S.u.c.AR[r1 >= i ? t1 + i : tri(i) + r1] * delta;
+        }
+      }
+    }
+    iter++;
+    imp = warp_sum(imp) * M.pgs_scale;
+    if (imp < M.tolerance) break;
+  }
+  return iter;
 }
 
 // ------------------------------------------------------------------------------------------
-// mj_fwdConstraint: warmstart + PGS on the dual (all rows are scalar, force >= 0), then
-// qacc = L^-1 D^-1/2 (y_s + Y' f).  Residuals res = AR f + b live in registers (lane = row and
-// row+32); a row update broadcasts its force increment and every lane applies one column of AR.
+// mj_fwdConstraint: warmstart + PGS on the dual, then qacc = L^-1 D^-1/2 (y_s + Y' f).
 // ------------------------------------------------------------------------------------------
-__device__ void solve_constraints(const ModelS& M, EnvS& S, int lane, int nefc) {
-  const int r0 = lane, r1 = lane + 32;
-  const bool a0 = r0 < nefc, a1 = r1 < nefc;
-  float f0 = 0.f, f1 = 0.f, res0 = 0.f, res1 = 0.f;
+__device__ __noinline__ void solve_constraints(const ModelS& M, EnvS& S, int lane, int nefc) {
   int iter = 0;
   if (nefc > 0) {
+    const int r0 = lane, r1 = lane + 32;
+    const bool a0 = r0 < nefc, a1 = r1 < nefc;
     // warmstart forces from qacc_warmstart: jar = J qacc_w - aref = Y (D^1/2 L qacc_w) - aref
     mul_L_sqrtD(M, S, lane, S.warm, S.vec1);
     float jar0 = 0.f, jar1 = 0.f;
     if (a0) { const float* y = &S.Y[r0 * YS]; for (int k = 0; k < M.nv; k++) jar0 += y[k] * S.vec1[k]; jar0 -= S.e_aref[r0]; }
     if (a1) { const float* y = &S.Y[r1 * YS]; for (int k = 0; k < M.nv; k++) jar1 += y[k] * S.vec1[k]; jar1 -= S.e_aref[r1]; }
-    f0 = (a0 && jar0 < 0.f) ? -jar0 / S.e_R[r0] : 0.f;
-    f1 = (a1 && jar1 < 0.f) ? -jar1 / S.e_R[r1] : 0.f;
+    float f0 = (a0 && jar0 < 0.f) ? -jar0 / S.e_R[r0] : 0.f;
+    float f1 = (a1 && jar1 < 0.f) ? -jar1 / S.e_R[r1] : 0.f;
     if (a0) S.e_f[r0] = f0;
     if (a1) S.e_f[r1] = f1;
     __syncwarp();
-    // res = AR f + b ; cost = sum f (0.5 (res - b) + b)
+    // res = AR f + b ; dual cost = sum f (0.5 (res - b) + b); a positive cost falls back to f = 0
     const float b0 = a0 ? S.e_b[r0] : 0.f, b1 = a1 ? S.e_b[r1] : 0.f;
-    res0 = b0; res1 = b1;
+    float res0 = b0, res1 = b1;
     for (int s = 0; s < nefc; s++) {
       const float fs = S.e_f[s];
       if (fs != 0.f) {
-        if (a0) res0 += S.AR[r0 >= s ? tri(r0) + s : tri(s) + r0] * fs;
-        if (a1) res1 += S.AR[r1 >= s ? tri(r1) + s : tri(s) + r1] * fs;
+        if (a0) res0 += S.u.c.AR[r0 >= s ? tri(r0) + s : tri(s) + r0] * fs;
+        if (a1) res1 += S.u.c.AR[r1 >= s ? tri(r1) + s : tri(s) + r1] * fs;
       }
     }
     float cost = f0 * 0.5f * (res0 + b0) + f1 * 0.5f * (res1 + b1);
     cost = warp_sum(cost);
     if (cost > 0.f) { f0 = 0.f; f1 = 0.f; res0 = b0; res1 = b1; }
-    const float d0 = a0 ? S.AR[tri(r0) + r0] : 1.f, d1 = a1 ? S.AR[tri(r1) + r1] : 1.f;
-    const float inv0 = 1.0f / d0, inv1 = 1.0f / d1;
-    // PGS sweeps
-    while (iter < M.iterations) {
-      float imp = 0.f;
-      for (int i = 0; i < nefc; i++) {
-        const int ol = i & 31;
-        const bool hi = i >= 32;
-        const float myres = hi ? res1 : res0, myf = hi ? f1 : f0, myinv = hi ? inv1 : inv0;
-        const float fnew = fmaxf(0.f, myf - myres * myinv);
-        const float delta = __shfl_sync(DMB_FULL, fnew - myf, ol);
-        if (delta != 0.f) {
-          if (lane == ol) {
-            imp -= 0.5f * delta * delta * (hi ? d1 : d0) + delta * myres;
-            if (hi) f1 = fnew; else f0 = fnew;
-          }
-          res0 += S.AR[r0 >= i ? tri(r0) + i : tri(i) + r0] * delta;
-          if (nefc > 32) res1 += S.AR[r1 >= i ? tri(r1) + i : tri(i) + r1] * delta;
-        }
-      }
-      iter++;
-      imp = warp_sum(imp) * M.pgs_scale;
-      if (imp < M.tolerance) break;
-    }
+    iter = nefc > 32 ? pgs_sweeps<true>(M, S, lane, nefc, f0, f1, res0, res1)
+                     : pgs_sweeps<false>(M, S, lane, nefc, f0, f1, res0, res1);
     if (a0) S.e_f[r0] = f0;
     if (a1) S.e_f[r1] = f1;
     __syncwarp();
   }
   if (lane == 0) S.iter = iter;
-  // t = y_s + sum_r Y_r f_r  (lane = dof)
-  for (int d = lane; d < M.nv; d += 32) {
-    float t = S.Y[nefc * YS + d];
-    for (int r = 0; r < nefc; r++) {
-      const float fr = S.e_f[r];
-      if (fr != 0.f) t += S.Y[r * YS + d] * fr;
+  // t = y_s + sum_r Y_r f_r  (lane = dof), then qacc = L^-1 D^-1/2 t in registers
+  float tlo = lane < M.nv ? S.ys[lane] : 0.f, thi = lane + 32 < M.nv ? S.ys[lane + 32] : 0.f;
+  for (int r = 0; r < nefc; r++) {
+    const float fr = S.e_f[r];
+    if (fr != 0.f) {
+      if (lane < M.nv) tlo += S.Y[r * YS + lane] * fr;
+      if (lane + 32 < M.nv) thi += S.Y[r * YS + lane + 32] * fr;
     }
-    S.qacc[d] = t;
   }
-  __syncwarp();
-  back_solve(M, S, lane, S.qacc);
-  for (int d = lane; d < M.nv; d += 32) S.warm[d] = S.qacc[d];
+  if (lane < M.nv) tlo *= S.dsq[lane];
+  if (lane + 32 < M.nv) thi *= S.dsq[lane + 32];
+  reg_solve_L(M, S, lane, tlo, thi);
+  if (lane < M.nv) { S.qacc[lane] = tlo; S.warm[lane] = tlo; }
+  if (lane + 32 < M.nv) { S.qacc[lane + 32] = thi; S.warm[lane + 32] = thi; }
   __syncwarp();
 }
 
@@ -898,32 +928,68 @@ __device__ void solve_constraints(const ModelS& M, EnvS& S, int lane, int nefc) 
 // Returns the whole-body CoM height of this evaluation (what DPEnv.is_done reads from the
 // stale mjData.xipos after mj_step, dp_env_v3.py:134-139).
 // ------------------------------------------------------------------------------------------
-__device__ float forward_eval(const ModelS& M, EnvS& S, int lane, float* dbgrow) {
-  kinematics(M, S, lane);
-  com_pos(M, S, lane);
-  crb_factor(M, S, lane, dbgrow ? dbgrow + dbg::qM : nullptr);
-  smooth_forces(M, S, lane, dbgrow ? dbgrow + dbg::qfrc_bias : nullptr);
-  collision(M, S, lane);
-  make_constraint(M, S, lane);
-  const int nefc = S.nefc;
-  half_solve_rows(M, S, lane, nefc + 1);
-  gram(M, S, lane, nefc);
-  if (dbgrow) {
+// LOCKSTEP: all warps of the CTA walk the phases together (one __syncthreads per phase), so the
+// ~100 KB instruction stream of a stage is fetched once per CTA instead of once per warp --
+// the v2 profile showed 60% of warp stalls were instruction-fetch (stall_no_inst).  Warps with
+// no env (`active` false) only take part in the barriers.
+template <bool LOCKSTEP>
+__device__ __noinline__ float forward_eval(const ModelS& M, EnvS& S, int lane, float* dbgrow, bool active) {
+#define DMB_PHASE_SYNC() do { if (LOCKSTEP) __syncthreads(); } while (0)
+  DMB_PHASE_SYNC();
+  if (active) {
+    kinematics(M, S, lane);
+    com_pos(M, S, lane);
+    if (dbgrow) {
+      for (int i = lane; i < M.nbody * 3; i += 32) { dbgrow[dbg::xpos + i] = S.u.a.xpos[i]; dbgrow[dbg::xipos + i] = S.u.a.xipos[i]; }
+      for (int i = lane; i < M.nbody * 4; i += 32) dbgrow[dbg::xquat + i] = S.u.a.xquat[i];
+    }
+  }
+  DMB_PHASE_SYNC();
+  if (active) crb_factor(M, S, lane, dbgrow ? dbgrow + dbg::qM : nullptr);
+  DMB_PHASE_SYNC();
+  if (active) {
+    smooth_forces(M, S, lane, dbgrow ? dbgrow + dbg::qfrc_bias : nullptr);
+    // y_s = D^-1/2 L^-T qfrc_smooth (registers)
+    float lo = lane < M.nv ? S.vec0[lane] : 0.f, hi = lane + 32 < M.nv ? S.vec0[lane + 32] : 0.f;
+    reg_solve_LT(M, S, lane, lo, hi);
+    if (lane < M.nv) S.ys[lane] = lo * S.dsq[lane];
+    if (lane + 32 < M.nv) S.ys[lane + 32] = hi * S.dsq[lane + 32];
+  }
+  DMB_PHASE_SYNC();
+  if (active) {
+    geom_poses(M, S, lane);
+    collision(M, S, lane);
+  }
+  DMB_PHASE_SYNC();
+  int nefc = 0;
+  if (active) {
+    make_constraint(M, S, lane);
+    nefc = S.nefc;
+  }
+  DMB_PHASE_SYNC();
+  if (active && nefc > 0) {
+    half_solve_rows(M, S, lane, nefc);
+    gram(M, S, lane, nefc);
+  }
+  if (active && dbgrow) {
     // qacc_smooth = L^-1 D^-1/2 y_s for the dump (not needed by the solver)
-    for (int d = lane; d < M.nv; d += 32) S.vec1[d] = S.Y[nefc * YS + d];
-    __syncwarp();
-    back_solve(M, S, lane, S.vec1);
-    for (int d = lane; d < M.nv; d += 32) { dbgrow[dbg::qacc_smooth + d] = S.vec1[d]; dbgrow[dbg::qfrc_smooth + d] = S.vec0[d]; }
+    float lo = lane < M.nv ? S.ys[lane] * S.dsq[lane] : 0.f, hi = lane + 32 < M.nv ? S.ys[lane + 32] * S.dsq[lane + 32] : 0.f;
+    reg_solve_L(M, S, lane, lo, hi);
+    if (lane < M.nv) dbgrow[dbg::qacc_smooth + lane] = lo;
+    if (lane + 32 < M.nv) dbgrow[dbg::qacc_smooth + lane + 32] = hi;
+    for (int d = lane; d < M.nv; d += 32) dbgrow[dbg::qfrc_smooth + d] = S.vec0[d];
     for (int e = lane; e < M.nM; e += 32) dbgrow[dbg::qLD + e] = S.qLD[e];
     for (int r = lane; r < nefc; r += 32) {
       dbgrow[dbg::efc_pos + r] = S.e_pos[r]; dbgrow[dbg::efc_R + r] = S.e_R[r];
       dbgrow[dbg::efc_aref + r] = S.e_aref[r]; dbgrow[dbg::efc_b + r] = S.e_b[r];
-      dbgrow[dbg::efc_AR_diag + r] = S.AR[tri(r) + r];
+      dbgrow[dbg::efc_AR_diag + r] = S.u.c.AR[tri(r) + r];
     }
     __syncwarp();
   }
-  solve_constraints(M, S, lane, nefc);
-  return S.com[2];
+  DMB_PHASE_SYNC();
+  if (active) solve_constraints(M, S, lane, nefc);
+#undef DMB_PHASE_SYNC
+  return active ? S.com[2] : 0.f;
 }
 
 }  // namespace dmb

@@ -20,10 +20,10 @@ constexpr int NP = DMB_MAX_PAIR;  // 128
 constexpr int NU = DMB_MAX_U;     // 32
 constexpr int NMX = DMB_MAX_M;    // 320
 constexpr int MAXANC = 12;        // longest dof ancestor chain (humanoid: 12)
-constexpr int MAXROW = 64;        // constraint rows (<= 63) + 1 row for the smooth force
-constexpr int MAXC = 24;          // contact capacity per env
-constexpr int YS = 37;            // row stride of Y (odd -> conflict-free lane=row access)
-constexpr int NTRI = (MAXROW - 1) * MAXROW / 2;  // packed lower triangle of AR (63 rows)
+constexpr int MAXROW = 48;        // constraint-row capacity of the kernel (max_efc <= 48)
+constexpr int MAXC = 16;          // contact capacity per env (max_con <= 16)
+constexpr int YS = 37;            // row stride of Y (odd -> conflict-free lane=row access; >= NVC)
+constexpr int NTRI = MAXROW * (MAXROW + 1) / 2;  // packed lower triangle of AR
 constexpr int JPB = 3;            // joints per body capacity
 
 enum DofKind : int8_t { DOF_FREE_TRANS = 0, DOF_FREE_ROT = 1, DOF_HINGE = 2 };
@@ -49,6 +49,7 @@ struct ModelS {
   int8_t dof_bodyid[NVC], dof_kind[NVC], dof_axisk[NVC], dof_nanc[NVC], dof_anc[NVC][MAXANC], dof_act[NVC];
   int16_t dof_Madr[NVC];
   unsigned long long dof_velmask[NVC];  // dofs summed into the velocity seen by cdof_dot (mj_comVel)
+  unsigned long long dof_ancmask[NVC];  // strict ancestors of each dof
   float dof_armature[NVC], dof_damping[NVC], dof_invw[NVC], dof_gear[NVC], dof_ctrl_lo[NVC], dof_ctrl_hi[NVC];
   float dof_kp[NVC], dof_kd[NVC], dof_weight[NVC];
   // inertia entries
@@ -72,31 +73,44 @@ struct ModelS {
   int clip_start[DMB_MAX_CLIP], clip_len[DMB_MAX_CLIP];
 };
 
-// Per-env tile.  fp32.  Layout notes: Y rows have an odd stride so that lane=row accesses hit
-// 32 different banks; AR is the packed lower triangle (row r starts at r(r+1)/2).
-struct EnvS {
-  float qpos[NQC], qvel[NQC], ctrlf[NQC];
+// Per-env tile (fp32).  Arrays that are dead by the time the constraint stage starts share
+// storage with the Delassus matrix through the union `u` ("shared-memory tile"):
+//   phase A  kinematics / inertia / RNE temporaries
+//   phase B  geom poses + broad-phase survivor list (xpos/xmat stay where phase A put them)
+//   phase C  packed lower triangle of AR = J M^-1 J' + R and the per-row support masks
+// Y rows have an odd stride so that lane=row accesses hit 32 different banks.
+struct PhaseA {
   float xpos[NB * 3], xquat[NB * 4], xmat[NB * 9], xipos[NB * 3];
-  float com[4];
   float cinert[NB * 10], crb[NB * 10];
-  float cdof[NVC * 6], cdofd[NVC * 6], buf6[NVC * 6];
-  float qLD[NMX], dinv[NVC], dsq[NVC];
-  float cvel[NB * 6], cacc[NB * 6], cfrc[NB * 6];
+  float cdofd[NVC * 6], buf6[NVC * 6], cfrc[NB * 6];
+};
+struct PhaseB {
+  float xpos[NB * 3], xquat[NB * 4], xmat[NB * 9];
   float gpos[NG * 3], gmat[NG * 9];
-  float vec0[NQC], vec1[NQC], qacc[NQC], warm[NQC];
+  int surv[NP];
+};
+struct PhaseC {
+  float AR[NTRI];
+  unsigned long long rowmask[MAXROW];
+};
+union PhaseU { PhaseA a; PhaseB b; PhaseC c; };
+
+struct EnvS {
+  float qpos[NQC], qvel[NQC], ctrlf[NQC], warm[NQC], qacc[NQC];
+  float x_q0[NQC], x_dv[NQC];          // RK4: X0 positions, stage velocity increment
+  float vec0[NQC], vec1[NQC], ys[NQC];  // qfrc_smooth / scratch / y_s = D^-1/2 L^-T qfrc_smooth
+  float com[4];
+  float cdof[NVC * 6], cvel[NB * 6];
+  float qLD[NMX], dinv[NVC], dsq[NVC];
   // contacts
   float c_dist[MAXC], c_pos[MAXC * 3], c_frame[MAXC * 9], c_mu[MAXC];
   int c_g1[MAXC], c_g2[MAXC], c_dim[MAXC], c_adr[MAXC];
   // constraint rows
-  float Y[MAXROW * YS];
-  float AR[NTRI + MAXROW];
   float e_pos[MAXROW], e_margin[MAXROW], e_R[MAXROW], e_aref[MAXROW], e_b[MAXROW], e_f[MAXROW];
-  unsigned long long rowmask[MAXROW];
-  int surv[NP];  // surviving broad-phase pairs
   int e_src[MAXROW];  // row source: >=0 contact*4+edge, <0 joint limit (see make_constraint)
-  // RK4 bookkeeping: X0, weighted sums of stage velocities / accelerations, stage increment
-  float x_q0[NQC], x_v0[NQC], x_sv[NQC], x_sa[NQC], x_dv[NQC];
   int ncon, nefc, nlimit, flags, iter, nsurv, pad0, pad1;
+  float Y[MAXROW * YS];
+  PhaseU u;
 };
 
 // Debug row layout (floats) for dmb_forward_debug

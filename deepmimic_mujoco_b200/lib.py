@@ -48,7 +48,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 _lib: Optional[C.CDLL] = None
 
-EXPORTS = ("dmb_version", "dmb_sizeof_model", "dmb_sizeof_config", "dmb_sizeof_mocap", "dmb_create", "dmb_destroy", "dmb_reset", "dmb_step", "dmb_get_obs", "dmb_forward_debug",
+EXPORTS = ("dmb_version", "dmb_sizeof_model", "dmb_sizeof_config", "dmb_sizeof_mocap", "dmb_sizeof_tile", "dmb_create", "dmb_destroy", "dmb_reset", "dmb_step", "dmb_get_obs", "dmb_forward_debug",
            "dmb_debug_stride", "dmb_debug_offset", "dmb_launch_info", "dmb_last_error")
 
 

@@ -57,7 +57,7 @@ class BatchedSim:
     def __init__(self, num_envs: int, motions: Sequence[str] = ("walk",), device: Optional[torch.device] = None,
                  seed: int = 0, first_env_id: int = 0, config: Optional[DmbConfig] = None,
                  model_tables: Optional[ModelTables] = None, clip_ids: Optional[torch.Tensor] = None,
-                 max_con: int = 24, max_efc: int = 63, ref_aux: Optional[np.ndarray] = None):
+                 max_con: int = 16, max_efc: int = 48, ref_aux: Optional[np.ndarray] = None):
         if not torch.cuda.is_available():
             raise _lib.DmbError("BatchedSim needs a CUDA device: the hot path has no CPU fallback")
         self.L = _lib.load()
@@ -181,6 +181,7 @@ class BatchedSim:
         h = dbg.cpu().numpy().astype(np.float64)
         off = lambda n: self.L.dmb_debug_offset(n.encode())
         nb, nv, nM = self.tables.nbody, self.nv, self.tables.nM
+        ne = off("efc_R") - off("efc_pos")
         out = dict(
             xpos=h[:, off("xpos"): off("xpos") + nb * 3].reshape(-1, nb, 3),
             xquat=h[:, off("xquat"): off("xquat") + nb * 4].reshape(-1, nb, 4),
@@ -192,11 +193,11 @@ class BatchedSim:
             qacc_smooth=h[:, off("qacc_smooth"): off("qacc_smooth") + nv],
             ncon=h[:, off("ncon")].astype(int), nefc=h[:, off("nefc")].astype(int), iter=h[:, off("iter")].astype(int),
             z_com=h[:, off("z_com")],
-            contact=h[:, off("contact"): off("contact") + 24 * 16].reshape(-1, 24, 16),
-            efc_pos=h[:, off("efc_pos"): off("efc_pos") + 64], efc_R=h[:, off("efc_R"): off("efc_R") + 64],
-            efc_aref=h[:, off("efc_aref"): off("efc_aref") + 64], efc_b=h[:, off("efc_b"): off("efc_b") + 64],
-            efc_force=h[:, off("efc_force"): off("efc_force") + 64],
-            efc_AR_diag=h[:, off("efc_AR_diag"): off("efc_AR_diag") + 64],
+            contact=h[:, off("contact"): off("efc_pos")].reshape(h.shape[0], -1, 16),
+            efc_pos=h[:, off("efc_pos"): off("efc_pos") + ne], efc_R=h[:, off("efc_R"): off("efc_R") + ne],
+            efc_aref=h[:, off("efc_aref"): off("efc_aref") + ne], efc_b=h[:, off("efc_b"): off("efc_b") + ne],
+            efc_force=h[:, off("efc_force"): off("efc_force") + ne],
+            efc_AR_diag=h[:, off("efc_AR_diag"): off("efc_AR_diag") + ne],
             qacc=h[:, off("qacc"): off("qacc") + nv],
             cvel=h[:, off("cvel"): off("cvel") + nb * 6].reshape(-1, nb, 6),
         )

@@ -80,6 +80,7 @@ int dmb_version(void);
 int32_t dmb_sizeof_model(void);
 int32_t dmb_sizeof_config(void);
 int32_t dmb_sizeof_mocap(void);
+int32_t dmb_sizeof_tile(void); /* bytes of shared memory per env (one warp) */
 
 /* Build a handle: copies the model / config / mocap tables to `cuda_device` (fp32) and
  * sizes the launch.  `seed` keys the per-env Philox streams (env e uses (seed, first_env_id + e)). */
