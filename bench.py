@@ -103,7 +103,7 @@ def _worker_init(motion, reward_mode):
     from deepmimic_mujoco_b200.sim import default_model_tables, load_motions, make_mocap_struct
     ident = mp.current_process()._identity
     wid = ident[0] if ident else 0
-    m = pack_model(default_model_tables(), max_con=16, max_efc=48)
+    m = pack_model(default_model_tables(), max_con=16, max_efc=40)
     cfg = default_config(reward_mode=reward_mode, auto_reset=1)
     aux = compute_ref_aux([motion]) if reward_mode == 4 else None
     mcs, keep = make_mocap_struct(load_motions([motion]), aux)

@@ -25,7 +25,9 @@
 namespace dmb {
 
 struct DevPtrs {
-  int* counter;            // dynamic env scheduler (zeroed before every launch)
+  int* counter;            // dynamic env scheduler (zeroed by k_order before every step)
+  int* cost;               // [N] constraint-work estimate of each env's last step (scheduler key)
+  const int* order;        // [N] env ids sorted by decreasing cost
   const ModelS* model;
   const float* mocap_cfg;  // [F][nq]
   const float* mocap_vel;  // [F][nv]
@@ -41,7 +43,7 @@ __device__ __forceinline__ void load_state(const ModelS& M, EnvS& S, const dmb_s
     S.qvel[i] = st.qvel[(size_t)env * DMB_VSTRIDE + i];
     S.warm[i] = st.warm[(size_t)env * DMB_VSTRIDE + i];
   }
-  if (lane == 0) S.flags = 0;
+  if (lane == 0) { S.flags = 0; S.cost = 0; }
   __syncwarp();
 }
 __device__ __forceinline__ void store_state(const ModelS& M, EnvS& S, const dmb_state_t& st, int env, int lane) {
@@ -294,10 +296,11 @@ __device__ __forceinline__ void stage_model(ModelS* dst, const ModelS* src) {
   __syncthreads();
 }
 
+static_assert(YS % 2 == 1, "odd row stride");
 constexpr size_t MODEL_BYTES = (sizeof(ModelS) + 15) & ~(size_t)15;
 
 template <bool LOCKSTEP>
-__global__ void k_step(DevPtrs P, dmb_state_t st, const float* __restrict__ action, dmb_step_out_t out, int N,
+__global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, const float* __restrict__ action, dmb_step_out_t out, int N,
                        unsigned long long seed, unsigned first_env_id) {
   extern __shared__ __align__(16) unsigned char smem[];
   ModelS& M = *reinterpret_cast<ModelS*>(smem);
@@ -306,14 +309,26 @@ __global__ void k_step(DevPtrs P, dmb_state_t st, const float* __restrict__ acti
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
   EnvS& S = tiles[warp];
   const int od = (M.nq - 7) + (M.nv - 6);
-  (void)W;
+  __shared__ int s_base;
   for (;;) {
-    // dynamic scheduling: env cost varies 2-3x with the number of active constraints
-    int env = 0;
-    if (lane == 0) env = atomicAdd(P.counter, 1);
-    env = __shfl_sync(DMB_FULL, env, 0);
+    // Scheduling: envs are handed out in order of decreasing constraint work (k_order), a CTA
+    // takes W consecutive entries at a time so that its warps see similar work between the
+    // lockstep barriers; without lockstep every warp pulls for itself.
+    int env = N;
+    if (LOCKSTEP) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_base = atomicAdd(P.counter, W);
+      __syncthreads();
+      const int idx = s_base + warp;
+      if (idx < N) env = P.order[idx];
+    } else {
+      int idx = 0;
+      if (lane == 0) idx = atomicAdd(P.counter, 1);
+      idx = __shfl_sync(DMB_FULL, idx, 0);
+      if (idx < N) env = P.order[idx];
+    }
     const bool have = env < N;
-    if (LOCKSTEP) { if (!__syncthreads_or(have ? 1 : 0)) break; }
+    if (LOCKSTEP) { if (s_base >= N) break; }
     else if (!have) break;
     bool bad = false;
     if (have) {
@@ -353,6 +368,7 @@ __global__ void k_step(DevPtrs P, dmb_state_t st, const float* __restrict__ acti
       if (out.last_ret) out.last_ret[env] = ep_ret;
       if (out.last_len) out.last_len[env] = ep_len;
       st.flags[env] = flags;
+      P.cost[env] = min(63, S.cost >> 6);
       st.idx_curr[env] = idx_curr;
       st.ep_len[env] = ep_len;
       st.ep_ret[env] = ep_ret;
@@ -368,6 +384,24 @@ __global__ void k_step(DevPtrs P, dmb_state_t st, const float* __restrict__ acti
     store_state(M, S, st, env, lane);
     __syncwarp();
   }
+}
+
+// Counting sort of the envs by the constraint work of their previous step (64 buckets,
+// heaviest first) + reset of the scheduler counter.  One CTA; order inside a bucket is arbitrary
+// (envs are independent, so results do not depend on the schedule).
+__global__ void k_order(const int* __restrict__ cost, int* __restrict__ order, int* counter, int N) {
+  __shared__ int hist[64], cursor[64];
+  if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&hist[min(63, max(0, cost[i]))], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = 63; b >= 0; b--) { cursor[b] = acc; acc += hist[b]; }
+    *counter = 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < N; i += blockDim.x) order[atomicAdd(&cursor[min(63, max(0, cost[i]))], 1)] = i;
 }
 
 __global__ void k_reset(DevPtrs P, dmb_state_t st, const unsigned char* __restrict__ mask, int mode, float* obs, int N,
@@ -459,7 +493,7 @@ struct dmb_handle_s {
   ModelS hmodel;
   ModelS* dmodel = nullptr;
   float *d_cfg = nullptr, *d_vel = nullptr, *d_aux = nullptr;
-  int* d_counter = nullptr;
+  int *d_counter = nullptr, *d_cost = nullptr, *d_order = nullptr;
   int grid = 0, block = 0, smem = 0, envs_per_cta = 0;
   int nu = 0, obs_dim = 0;
   int lockstep = 1;
@@ -480,10 +514,10 @@ static int fail(dmb_handle_t h, int code, const std::string& msg) {
 
 static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mocap_t* mc, ModelS& S, std::string& why) {
   memset(&S, 0, sizeof(S));
-  if (m->nv > NVC || m->nq > NQC || m->nbody > NB || m->njnt > NJ || m->ngeom > NG || m->npair > NP || m->nu > NU ||
+  if (m->nv > YS || m->nv > NVC || m->nq > NQC || m->nbody > NB || m->njnt > NJ || m->ngeom > NG || m->npair > NP || m->nu > NU ||
       m->nM > NMX || m->nv > 64) { why = "model exceeds kernel capacities"; return DMB_ERR_MODEL; }
   if (m->max_efc > MAXROW || m->max_con > MAXC || m->max_con > 32 || m->max_efc < m->njnt) {
-    why = "max_efc must be <= 48 and >= njnt, max_con <= 16 (kernel capacities)"; return DMB_ERR_MODEL;
+    why = "max_efc must be <= 40 and >= njnt, max_con <= 16 (kernel capacities)"; return DMB_ERR_MODEL;
   }
   S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.nbody = m->nbody; S.njnt = m->njnt; S.ngeom = m->ngeom;
   S.npair = m->npair; S.nM = m->nM; S.iterations = m->iterations; S.max_con = m->max_con; S.max_efc = m->max_efc;
@@ -656,6 +690,9 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
   e = cudaMalloc((void**)&h->dmodel, sizeof(ModelS));
   if (e == cudaSuccess) e = cudaMemcpy(h->dmodel, &h->hmodel, sizeof(ModelS), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_counter, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_cost, sizeof(int) * (size_t)num_envs);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_order, sizeof(int) * (size_t)num_envs);
+  if (e == cudaSuccess) e = cudaMemset(h->d_cost, 0, sizeof(int) * (size_t)num_envs);
   if (e == cudaSuccess) e = upload(mocap->data_config, ncfg, &h->d_cfg);
   if (e == cudaSuccess) e = upload(mocap->data_vel, nvel, &h->d_vel);
   if (e == cudaSuccess) e = upload(mocap->ref_aux, naux, &h->d_aux);
@@ -694,7 +731,7 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
 int dmb_destroy(dmb_handle_t h) {
   if (!h) return DMB_ERR_ARG;
   cudaSetDevice(h->device);
-  cudaFree(h->d_counter); cudaFree(h->dmodel); cudaFree(h->d_cfg); cudaFree(h->d_vel); cudaFree(h->d_aux);
+  cudaFree(h->d_counter); cudaFree(h->d_cost); cudaFree(h->d_order); cudaFree(h->dmodel); cudaFree(h->d_cfg); cudaFree(h->d_vel); cudaFree(h->d_aux);
   delete h;
   return DMB_OK;
 }
@@ -703,7 +740,7 @@ static bool state_ok(const dmb_state_t* st) {
   return st && st->qpos && st->qvel && st->warm && st->clip && st->idx_init && st->idx_curr && st->reset_count &&
          st->ep_len && st->ep_ret && st->flags;
 }
-static DevPtrs devptrs(dmb_handle_t h) { DevPtrs P; P.counter = h->d_counter; P.model = h->dmodel; P.mocap_cfg = h->d_cfg; P.mocap_vel = h->d_vel; P.ref_aux = h->d_aux; return P; }
+static DevPtrs devptrs(dmb_handle_t h) { DevPtrs P; P.counter = h->d_counter; P.cost = h->d_cost; P.order = h->d_order; P.model = h->dmodel; P.mocap_cfg = h->d_cfg; P.mocap_vel = h->d_vel; P.ref_aux = h->d_aux; return P; }
 
 int dmb_reset(dmb_handle_t h, const dmb_state_t* st, const uint8_t* mask, int32_t mode, float* obs, void* stream) {
   if (!h) return DMB_ERR_ARG;
@@ -718,7 +755,7 @@ int dmb_step(dmb_handle_t h, const dmb_state_t* st, const float* action, const d
   if (!h) return DMB_ERR_ARG;
   if (!state_ok(st) || !action || !out || !out->obs || !out->reward || !out->done) return fail(h, DMB_ERR_ARG, "dmb_step: bad argument");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  CUDA_TRY(h, cudaMemsetAsync(h->d_counter, 0, sizeof(int), (cudaStream_t)stream));
+  k_order<<<1, 1024, 0, (cudaStream_t)stream>>>(h->d_cost, h->d_order, h->d_counter, h->num_envs);
   if (h->lockstep) k_step<true><<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
   else k_step<false><<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
   CUDA_TRY(h, cudaGetLastError());

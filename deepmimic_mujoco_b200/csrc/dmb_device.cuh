@@ -640,7 +640,7 @@ __device__ __noinline__ void make_constraint(const ModelS& M, EnvS& S, int lane)
     for (int r = 0; r < nlimit; r++) {
       const int src = -e_src[r];          // 2*(1+dof) or 2*(1+dof)+1
       const int dof = (src >> 1) - 1;
-      S.Y[r * YS + d] = (dof == d) ? ((src & 1) ? -1.f : 1.f) : 0.f;
+      S.u.Y[r * YS + d] = (dof == d) ? ((src & 1) ? -1.f : 1.f) : 0.f;
     }
     const V3 ca = ld3(&S.cdof[6 * d]), cl = ld3(&S.cdof[6 * d + 3]);
     for (int c = 0; c < ncon; c++) {
@@ -652,7 +652,7 @@ __device__ __noinline__ void make_constraint(const ModelS& M, EnvS& S, int lane)
       if (S.c_dim[c] == 1) {
         float jn = 0.f;
         if (sg != 0.f) { const V3 p = cl + cross(ca, ld3(&S.c_pos[3 * c]) - com); jn = sg * dot(ld3(fr), p); }
-        S.Y[a * YS + d] = jn;
+        S.u.Y[a * YS + d] = jn;
       } else {
         float jn = 0.f, j1 = 0.f, j2 = 0.f;
         if (sg != 0.f) {
@@ -660,10 +660,10 @@ __device__ __noinline__ void make_constraint(const ModelS& M, EnvS& S, int lane)
           jn = sg * dot(ld3(fr), p); j1 = sg * dot(ld3(fr + 3), p); j2 = sg * dot(ld3(fr + 6), p);
         }
         const float mu = S.c_mu[c];
-        S.Y[a * YS + d] = jn + mu * j1;
-        S.Y[(a + 1) * YS + d] = jn - mu * j1;
-        S.Y[(a + 2) * YS + d] = jn + mu * j2;
-        S.Y[(a + 3) * YS + d] = jn - mu * j2;
+        S.u.Y[a * YS + d] = jn + mu * j1;
+        S.u.Y[(a + 1) * YS + d] = jn - mu * j1;
+        S.u.Y[(a + 2) * YS + d] = jn + mu * j2;
+        S.u.Y[(a + 3) * YS + d] = jn - mu * j2;
       }
     }
   }
@@ -771,7 +771,7 @@ __device__ __noinline__ void half_solve_rows(const ModelS& M, EnvS& S, int lane,
   for (int base = 0; base < nrows; base += 32) {
     const int r = base + lane;
     const bool act = r < nrows;
-    float* y = &S.Y[(act ? r : 0) * YS];
+    float* y = &S.u.Y[(act ? r : 0) * YS];
     for (int i = M.nv - 1; i >= 0; i--) {
       const float yi = act ? y[i] : 0.f;
       if (!__any_sync(DMB_FULL, yi != 0.f)) continue;
@@ -791,7 +791,7 @@ __device__ __noinline__ void half_solve_rows(const ModelS& M, EnvS& S, int lane,
         y[i] = v;
         if (v != 0.f) mask |= 1ull << i;
       }
-      S.u.c.rowmask[r] = mask;
+      S.rowmask[r] = mask;
     }
   }
   __syncwarp();
@@ -804,18 +804,18 @@ __device__ __noinline__ void gram(const ModelS& M, EnvS& S, int lane, int nefc) 
   for (int base = 0; base < nefc; base += 32) {
     const int r = base + lane;
     const bool act = r < nefc;
-    const float* yr = &S.Y[(act ? r : 0) * YS];
+    const float* yr = &S.u.Y[(act ? r : 0) * YS];
     const int smax = min(nefc - 1, base + 31);
     for (int s = 0; s <= smax; s++) {
-      unsigned long long mk = S.u.c.rowmask[s];
-      const float* ys = &S.Y[s * YS];
+      unsigned long long mk = S.rowmask[s];
+      const float* ys = &S.u.Y[s * YS];
       float acc = 0.f;
       while (mk) {
         const int k = __ffsll((long long)mk) - 1;
         mk &= mk - 1;
         acc += yr[k] * ys[k];
       }
-      if (act && s <= r) S.u.c.AR[tri(r) + s] = (s == r) ? acc + S.e_R[r] : acc;
+      if (act && s <= r) S.AR[tri(r) + s] = (s == r) ? acc + S.e_R[r] : acc;
     }
     if (act) {
       float acc = 0.f;
@@ -834,7 +834,7 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
                                           float& res0, float& res1) {
   const int r0 = lane, r1 = lane + 32;
   const bool a0 = r0 < nefc, a1 = HI && r1 < nefc;
-  const float d0 = a0 ? S.u.c.AR[tri(r0) + r0] : 1.f, d1 = a1 ? S.u.c.AR[tri(r1) + r1] : 1.f;
+  const float d0 = a0 ? S.AR[tri(r0) + r0] : 1.f, d1 = a1 ? S.AR[tri(r1) + r1] : 1.f;
   const float inv0 = 1.0f / d0, inv1 = 1.0f / d1;
   const int t0 = tri(r0), t1 = tri(r1);
   const int nlo = HI ? 32 : nefc;
@@ -846,8 +846,8 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
       const float delta = __shfl_sync(DMB_FULL, fnew - f0, i);
       if (delta != 0.f) {
         if (lane == i) { imp -= 0.5f * delta * delta * d0 + delta * res0; f0 = fnew; }
-        res0 += S.u.c.AR[r0 >= i ? t0 + i : tri(i) + r0] * delta;
-        if (HI && a1) res1 += S.u.c.AR[t1 + i] * delta;   // r1 >= 32 > i
+        res0 += S.AR[r0 >= i ? t0 + i : tri(i) + r0] * delta;
+        if (HI && a1) res1 += S.AR[t1 + i] * delta;   // r1 >= 32 > i
       }
     }
     if (HI) {
@@ -856,8 +856,8 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
         const float delta = __shfl_sync(DMB_FULL, fnew - f1, i - 32);
         if (delta != 0.f) {
           if (lane == i - 32) { imp -= 0.5f * delta * delta * d1 + delta * res1; f1 = fnew; }
-          res0 += S.u.c.AR[tri(i) + r0] * delta;     // i >= 32 > r0
-          if (a1) res1 += S.u.c.AR[r1 >= i ? t1 + i : tri(i) + r1] * delta;
+          res0 += S.AR[tri(i) + r0] * delta;     // i >= 32 > r0
+          if (a1) res1 += S.AR[r1 >= i ? t1 + i : tri(i) + r1] * delta;
         }
       }
     }
@@ -879,8 +879,8 @@ __device__ __noinline__ void solve_constraints(const ModelS& M, EnvS& S, int lan
     // warmstart forces from qacc_warmstart: jar = J qacc_w - aref = Y (D^1/2 L qacc_w) - aref
     mul_L_sqrtD(M, S, lane, S.warm, S.vec1);
     float jar0 = 0.f, jar1 = 0.f;
-    if (a0) { const float* y = &S.Y[r0 * YS]; for (int k = 0; k < M.nv; k++) jar0 += y[k] * S.vec1[k]; jar0 -= S.e_aref[r0]; }
-    if (a1) { const float* y = &S.Y[r1 * YS]; for (int k = 0; k < M.nv; k++) jar1 += y[k] * S.vec1[k]; jar1 -= S.e_aref[r1]; }
+    if (a0) { const float* y = &S.u.Y[r0 * YS]; for (int k = 0; k < M.nv; k++) jar0 += y[k] * S.vec1[k]; jar0 -= S.e_aref[r0]; }
+    if (a1) { const float* y = &S.u.Y[r1 * YS]; for (int k = 0; k < M.nv; k++) jar1 += y[k] * S.vec1[k]; jar1 -= S.e_aref[r1]; }
     float f0 = (a0 && jar0 < 0.f) ? -jar0 / S.e_R[r0] : 0.f;
     float f1 = (a1 && jar1 < 0.f) ? -jar1 / S.e_R[r1] : 0.f;
     if (a0) S.e_f[r0] = f0;
@@ -892,8 +892,8 @@ __device__ __noinline__ void solve_constraints(const ModelS& M, EnvS& S, int lan
     for (int s = 0; s < nefc; s++) {
       const float fs = S.e_f[s];
       if (fs != 0.f) {
-        if (a0) res0 += S.u.c.AR[r0 >= s ? tri(r0) + s : tri(s) + r0] * fs;
-        if (a1) res1 += S.u.c.AR[r1 >= s ? tri(r1) + s : tri(s) + r1] * fs;
+        if (a0) res0 += S.AR[r0 >= s ? tri(r0) + s : tri(s) + r0] * fs;
+        if (a1) res1 += S.AR[r1 >= s ? tri(r1) + s : tri(s) + r1] * fs;
       }
     }
     float cost = f0 * 0.5f * (res0 + b0) + f1 * 0.5f * (res1 + b1);
@@ -905,14 +905,14 @@ __device__ __noinline__ void solve_constraints(const ModelS& M, EnvS& S, int lan
     if (a1) S.e_f[r1] = f1;
     __syncwarp();
   }
-  if (lane == 0) S.iter = iter;
+  if (lane == 0) { S.iter = iter; S.cost += nefc * iter; }
   // t = y_s + sum_r Y_r f_r  (lane = dof), then qacc = L^-1 D^-1/2 t in registers
   float tlo = lane < M.nv ? S.ys[lane] : 0.f, thi = lane + 32 < M.nv ? S.ys[lane + 32] : 0.f;
   for (int r = 0; r < nefc; r++) {
     const float fr = S.e_f[r];
     if (fr != 0.f) {
-      if (lane < M.nv) tlo += S.Y[r * YS + lane] * fr;
-      if (lane + 32 < M.nv) thi += S.Y[r * YS + lane + 32] * fr;
+      if (lane < M.nv) tlo += S.u.Y[r * YS + lane] * fr;
+      if (lane + 32 < M.nv) thi += S.u.Y[r * YS + lane + 32] * fr;
     }
   }
   if (lane < M.nv) tlo *= S.dsq[lane];
@@ -982,7 +982,7 @@ __device__ __noinline__ float forward_eval(const ModelS& M, EnvS& S, int lane, f
     for (int r = lane; r < nefc; r += 32) {
       dbgrow[dbg::efc_pos + r] = S.e_pos[r]; dbgrow[dbg::efc_R + r] = S.e_R[r];
       dbgrow[dbg::efc_aref + r] = S.e_aref[r]; dbgrow[dbg::efc_b + r] = S.e_b[r];
-      dbgrow[dbg::efc_AR_diag + r] = S.u.c.AR[tri(r) + r];
+      dbgrow[dbg::efc_AR_diag + r] = S.AR[tri(r) + r];
     }
     __syncwarp();
   }

@@ -20,9 +20,9 @@ constexpr int NP = DMB_MAX_PAIR;  // 128
 constexpr int NU = DMB_MAX_U;     // 32
 constexpr int NMX = DMB_MAX_M;    // 320
 constexpr int MAXANC = 12;        // longest dof ancestor chain (humanoid: 12)
-constexpr int MAXROW = 48;        // constraint-row capacity of the kernel (max_efc <= 48)
+constexpr int MAXROW = 40;        // constraint-row capacity of the kernel (max_efc <= 40)
 constexpr int MAXC = 16;          // contact capacity per env (max_con <= 16)
-constexpr int YS = 37;            // row stride of Y (odd -> conflict-free lane=row access; >= NVC)
+constexpr int YS = 35;            // row stride of Y (odd -> conflict-free lane=row access; >= nv)
 constexpr int NTRI = MAXROW * (MAXROW + 1) / 2;  // packed lower triangle of AR
 constexpr int JPB = 3;            // joints per body capacity
 
@@ -77,7 +77,7 @@ struct ModelS {
 // storage with the Delassus matrix through the union `u` ("shared-memory tile"):
 //   phase A  kinematics / inertia / RNE temporaries
 //   phase B  geom poses + broad-phase survivor list (xpos/xmat stay where phase A put them)
-//   phase C  packed lower triangle of AR = J M^-1 J' + R and the per-row support masks
+//   then     the half-solved constraint Jacobian Y (the Delassus matrix AR has its own storage)
 // Y rows have an odd stride so that lane=row accesses hit 32 different banks.
 struct PhaseA {
   float xpos[NB * 3], xquat[NB * 4], xmat[NB * 9], xipos[NB * 3];
@@ -89,11 +89,11 @@ struct PhaseB {
   float gpos[NG * 3], gmat[NG * 9];
   int surv[NP];
 };
-struct PhaseC {
-  float AR[NTRI];
-  unsigned long long rowmask[MAXROW];
+union PhaseU {
+  PhaseA a;
+  PhaseB b;
+  float Y[MAXROW * YS];  // half-solved constraint Jacobian, written after the collision stage
 };
-union PhaseU { PhaseA a; PhaseB b; PhaseC c; };
 
 struct EnvS {
   float qpos[NQC], qvel[NQC], ctrlf[NQC], warm[NQC], qacc[NQC];
@@ -108,8 +108,9 @@ struct EnvS {
   // constraint rows
   float e_pos[MAXROW], e_margin[MAXROW], e_R[MAXROW], e_aref[MAXROW], e_b[MAXROW], e_f[MAXROW];
   int e_src[MAXROW];  // row source: >=0 contact*4+edge, <0 joint limit (see make_constraint)
-  int ncon, nefc, nlimit, flags, iter, nsurv, pad0, pad1;
-  float Y[MAXROW * YS];
+  int ncon, nefc, nlimit, flags, iter, cost, pad0, pad1;
+  unsigned long long rowmask[MAXROW];  // dof support of each half-solved row
+  float AR[NTRI];                      // packed lower triangle of J M^-1 J' + R
   PhaseU u;
 };
 

@@ -90,7 +90,7 @@ def _fill(dst, src):
             _fill(dst[i], a[i])
 
 
-def pack_model(mt: ModelTables, max_con: int = 16, max_efc: int = 48) -> DmbModel:
+def pack_model(mt: ModelTables, max_con: int = 16, max_efc: int = 40) -> DmbModel:
     """ModelTables -> dmb_model_t (adds PD gains, reward weights and end-effector points)."""
     for cap, n, what in ((MAX_BODY, mt.nbody, "bodies"), (MAX_JNT, mt.njnt, "joints"), (MAX_DOF, mt.nv, "dofs"),
                          (MAX_Q, mt.nq, "qpos"), (MAX_GEOM, mt.ngeom, "geoms"), (MAX_PAIR, mt.npair, "pairs"),

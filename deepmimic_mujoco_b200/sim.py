@@ -57,7 +57,7 @@ class BatchedSim:
     def __init__(self, num_envs: int, motions: Sequence[str] = ("walk",), device: Optional[torch.device] = None,
                  seed: int = 0, first_env_id: int = 0, config: Optional[DmbConfig] = None,
                  model_tables: Optional[ModelTables] = None, clip_ids: Optional[torch.Tensor] = None,
-                 max_con: int = 16, max_efc: int = 48, ref_aux: Optional[np.ndarray] = None):
+                 max_con: int = 16, max_efc: int = 40, ref_aux: Optional[np.ndarray] = None):
         if not torch.cuda.is_available():
             raise _lib.DmbError("BatchedSim needs a CUDA device: the hot path has no CPU fallback")
         self.L = _lib.load()

@@ -29,7 +29,7 @@ def tables():
     return _tables
 
 
-def model(max_con=16, max_efc=48):
+def model(max_con=16, max_efc=40):
     return pack_model(tables(), max_con=max_con, max_efc=max_efc)
 
 
