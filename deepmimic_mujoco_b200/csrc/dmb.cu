@@ -631,6 +631,8 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
   if (c->reward_mode != 0 && c->reward_mode != 1 && c->reward_mode != 4) { why = "reward_mode must be 0, 1 or 4"; return DMB_ERR_ARG; }
   if (c->ctrl_mode < 0 || c->ctrl_mode > 2) { why = "ctrl_mode must be 0, 1 or 2"; return DMB_ERR_ARG; }
   S.nclip = mc->nclip; S.nframe_total = mc->nframe_total;
+  S.sync_mask = 0x01;  // one barrier per RK stage (sweep on B200: best of 0x7f..0x01)
+  if (const char* sm = getenv("DMB_SYNC_MASK")) S.sync_mask = (int)strtol(sm, nullptr, 0);
   if (mc->nclip < 1 || mc->nclip > DMB_MAX_CLIP) { why = "need 1..16 motion clips"; return DMB_ERR_ARG; }
   for (int k = 0; k < mc->nclip; k++) { S.clip_start[k] = mc->clip_start[k]; S.clip_len[k] = mc->clip_len[k]; }
   return DMB_OK;

@@ -676,9 +676,11 @@ __device__ __noinline__ void make_constraint(const ModelS& M, EnvS& S, int lane)
       const int s2 = -src, dof = (s2 >> 1) - 1;
       dA = M.dof_invw[dof];
       vel = (s2 & 1) ? -S.qvel[dof] : S.qvel[dof];
+      S.rowmask[r] = M.dof_ancmask[dof] | (1ull << dof);
     } else {
       const int c = src >> 2, k = src & 3;
       const int b1 = M.geom_bodyid[S.c_g1[c]], b2 = M.geom_bodyid[S.c_g2[c]];
+      S.rowmask[r] = M.body_dofmask[b1] | M.body_dofmask[b2];
       const float tran = M.body_invw[b1] + M.body_invw[b2];
       const V3 off = ld3(&S.c_pos[3 * c]) - com;
       const V3 v2 = ld3(&S.cvel[6 * b2 + 3]) + cross(ld3(&S.cvel[6 * b2]), off);
@@ -762,12 +764,38 @@ __device__ void mul_L_sqrtD(const ModelS& M, EnvS& S, int lane, const float* x, 
 }
 
 // ------------------------------------------------------------------------------------------
-// Half solve  Y_r <- D^-1/2 L^-T Y_r  for all constraint rows at once: lane = row, serial over
-// dofs with warp-uniform loop bounds (L entries are broadcast reads).  The <= 12 ancestor
-// updates of one dof are independent: loads are batched ahead of the FMAs and stores.  Dofs on
-// which no row of the pass has support are skipped with one vote.  Also builds the support masks.
+// Half solve  Y_r <- D^-1/2 L^-T Y_r.  S.rowmask[r] holds the ancestor-closed dof support of
+// row r (chains of the bodies in contact / of the limited joint), which the elimination keeps.
+// Two schedules with identical arithmetic per entry:
+//  * few rows  -> one row at a time in registers (lane = dof), visiting only the dofs of the
+//    row's support, deepest first (one broadcast shuffle + one FFMA per dof);
+//  * many rows -> all rows at once (lane = row), serial over dofs with warp-uniform bounds; the
+//    <= 12 ancestor updates of one dof are independent, so loads are batched ahead of the FMAs.
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void half_solve_rows(const ModelS& M, EnvS& S, int lane, int nrows) {
+  if (nrows <= 12) {
+    const float dlo = lane < M.nv ? S.dsq[lane] : 0.f, dhi = lane + 32 < M.nv ? S.dsq[lane + 32] : 0.f;
+    for (int r = 0; r < nrows; r++) {
+      float* y = &S.u.Y[r * YS];
+      float lo = lane < M.nv ? y[lane] : 0.f, hi = lane + 32 < M.nv ? y[lane + 32] : 0.f;
+      unsigned long long sup = S.rowmask[r];
+      while (sup) {
+        const int i = 63 - __clzll((long long)sup);
+        sup &= ~(1ull << i);
+        const unsigned long long am = M.dof_ancmask[i];
+        if (am == 0ull) continue;
+        const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
+        if (xi == 0.f) continue;
+        const int adr = M.dof_Madr[i] + 1;
+        if ((am >> lane) & 1ull) lo -= S.qLD[adr + __popcll(am >> (lane + 1))] * xi;
+        if ((am >> 32) != 0ull && ((am >> (lane + 32)) & 1ull)) hi -= S.qLD[adr + __popcll(am >> (lane + 33))] * xi;
+      }
+      if (lane < M.nv) y[lane] = lo * dlo;
+      if (lane + 32 < M.nv) y[lane + 32] = hi * dhi;
+    }
+    __syncwarp();
+    return;
+  }
   for (int base = 0; base < nrows; base += 32) {
     const int r = base + lane;
     const bool act = r < nrows;
@@ -784,42 +812,44 @@ __device__ __noinline__ void half_solve_rows(const ModelS& M, EnvS& S, int lane,
         for (int k = 0; k < MAXANC; k++) if (k < c) y[M.dof_anc[i][k]] = tmp[k] - S.qLD[adr + k] * yi;
       }
     }
-    if (act) {
-      unsigned long long mask = 0ull;
-      for (int i = 0; i < M.nv; i++) {
-        const float v = y[i] * S.dsq[i];
-        y[i] = v;
-        if (v != 0.f) mask |= 1ull << i;
-      }
-      S.rowmask[r] = mask;
-    }
+    if (act) for (int i = 0; i < M.nv; i++) y[i] *= S.dsq[i];
   }
   __syncwarp();
 }
 
 __device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
 
-// Gram matrix AR = Y Y' + diag(R) (packed lower triangle), b = Y y_s - aref.  lane = row.
+// Gram matrix AR = Y Y' + diag(R) (packed lower triangle) and b = Y y_s - aref.
+// lane = matrix entry: the nefc(nefc+1)/2 pairs (+ nefc entries for b) are dealt out 32 at a time;
+// each lane runs the sparse dot product over the intersection of the two row supports.
 __device__ __noinline__ void gram(const ModelS& M, EnvS& S, int lane, int nefc) {
-  for (int base = 0; base < nefc; base += 32) {
-    const int r = base + lane;
-    const bool act = r < nefc;
-    const float* yr = &S.u.Y[(act ? r : 0) * YS];
-    const int smax = min(nefc - 1, base + 31);
-    for (int s = 0; s <= smax; s++) {
-      unsigned long long mk = S.rowmask[s];
-      const float* ys = &S.u.Y[s * YS];
+  const int npair = tri(nefc), ntask = npair + nefc;
+  for (int t = lane; t < ntask; t += 32) {
+    if (t < npair) {
+      int r = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+      if (tri(r + 1) <= t) r++;
+      if (tri(r) > t) r--;
+      const int c = t - tri(r);
+      const float* yr = &S.u.Y[r * YS];
+      const float* yc = &S.u.Y[c * YS];
+      unsigned long long mk = S.rowmask[r] & S.rowmask[c];
       float acc = 0.f;
       while (mk) {
         const int k = __ffsll((long long)mk) - 1;
         mk &= mk - 1;
-        acc += yr[k] * ys[k];
+        acc += yr[k] * yc[k];
       }
-      if (act && s <= r) S.AR[tri(r) + s] = (s == r) ? acc + S.e_R[r] : acc;
-    }
-    if (act) {
+      S.AR[t] = (c == r) ? acc + S.e_R[r] : acc;
+    } else {
+      const int r = t - npair;
+      const float* yr = &S.u.Y[r * YS];
+      unsigned long long mk = S.rowmask[r];
       float acc = 0.f;
-      for (int k = 0; k < M.nv; k++) acc += yr[k] * S.ys[k];
+      while (mk) {
+        const int k = __ffsll((long long)mk) - 1;
+        mk &= mk - 1;
+        acc += yr[k] * S.ys[k];
+      }
       S.e_b[r] = acc - S.e_aref[r];
     }
   }
@@ -840,28 +870,37 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
   const int nlo = HI ? 32 : nefc;
   int iter = 0;
   while (iter < M.iterations) {
-    float imp = 0.f;
+    // the owner of a row remembers its increment and the residual it was computed from; the
+    // cost decrease  -(0.5 delta^2 AR_ii + delta res_i)  is summed once per sweep
+    float dm0 = 0.f, rm0 = 0.f, dm1 = 0.f, rm1 = 0.f;
+    int tri_i = 0;
     for (int i = 0; i < nlo; i++) {
       const float fnew = fmaxf(0.f, f0 - res0 * inv0);
-      const float delta = __shfl_sync(DMB_FULL, fnew - f0, i);
+      const float mine = fnew - f0;
+      const float delta = __shfl_sync(DMB_FULL, mine, i);
+      if (lane == i) { dm0 = mine; rm0 = res0; f0 = fnew; }
       if (delta != 0.f) {
-        if (lane == i) { imp -= 0.5f * delta * delta * d0 + delta * res0; f0 = fnew; }
-        res0 += S.AR[r0 >= i ? t0 + i : tri(i) + r0] * delta;
+        res0 += S.AR[r0 >= i ? t0 + i : tri_i + r0] * delta;
         if (HI && a1) res1 += S.AR[t1 + i] * delta;   // r1 >= 32 > i
       }
+      tri_i += i + 1;
     }
     if (HI) {
       for (int i = 32; i < nefc; i++) {
         const float fnew = fmaxf(0.f, f1 - res1 * inv1);
-        const float delta = __shfl_sync(DMB_FULL, fnew - f1, i - 32);
+        const float mine = fnew - f1;
+        const float delta = __shfl_sync(DMB_FULL, mine, i - 32);
+        if (lane == i - 32) { dm1 = mine; rm1 = res1; f1 = fnew; }
         if (delta != 0.f) {
-          if (lane == i - 32) { imp -= 0.5f * delta * delta * d1 + delta * res1; f1 = fnew; }
-          res0 += S.AR[tri(i) + r0] * delta;     // i >= 32 > r0
-          if (a1) res1 += S.AR[r1 >= i ? t1 + i : tri(i) + r1] * delta;
+          res0 += S.AR[tri_i + r0] * delta;          // i >= 32 > r0
+          if (a1) res1 += S.AR[r1 >= i ? t1 + i : tri_i + r1] * delta;
         }
+        tri_i += i + 1;
       }
     }
     iter++;
+    float imp = -(dm0 * (0.5f * dm0 * d0 + rm0));
+    if (HI) imp -= dm1 * (0.5f * dm1 * d1 + rm1);
     imp = warp_sum(imp) * M.pgs_scale;
     if (imp < M.tolerance) break;
   }
@@ -934,8 +973,8 @@ __device__ __noinline__ void solve_constraints(const ModelS& M, EnvS& S, int lan
 // no env (`active` false) only take part in the barriers.
 template <bool LOCKSTEP>
 __device__ __noinline__ float forward_eval(const ModelS& M, EnvS& S, int lane, float* dbgrow, bool active) {
-#define DMB_PHASE_SYNC() do { if (LOCKSTEP) __syncthreads(); } while (0)
-  DMB_PHASE_SYNC();
+#define DMB_PHASE_SYNC(bit) do { if (LOCKSTEP && (M.sync_mask & (bit))) __syncthreads(); } while (0)
+  DMB_PHASE_SYNC(1);
   if (active) {
     kinematics(M, S, lane);
     com_pos(M, S, lane);
@@ -944,9 +983,9 @@ __device__ __noinline__ float forward_eval(const ModelS& M, EnvS& S, int lane, f
       for (int i = lane; i < M.nbody * 4; i += 32) dbgrow[dbg::xquat + i] = S.u.a.xquat[i];
     }
   }
-  DMB_PHASE_SYNC();
+  DMB_PHASE_SYNC(2);
   if (active) crb_factor(M, S, lane, dbgrow ? dbgrow + dbg::qM : nullptr);
-  DMB_PHASE_SYNC();
+  DMB_PHASE_SYNC(4);
   if (active) {
     smooth_forces(M, S, lane, dbgrow ? dbgrow + dbg::qfrc_bias : nullptr);
     // y_s = D^-1/2 L^-T qfrc_smooth (registers)
@@ -955,18 +994,18 @@ __device__ __noinline__ float forward_eval(const ModelS& M, EnvS& S, int lane, f
     if (lane < M.nv) S.ys[lane] = lo * S.dsq[lane];
     if (lane + 32 < M.nv) S.ys[lane + 32] = hi * S.dsq[lane + 32];
   }
-  DMB_PHASE_SYNC();
+  DMB_PHASE_SYNC(8);
   if (active) {
     geom_poses(M, S, lane);
     collision(M, S, lane);
   }
-  DMB_PHASE_SYNC();
+  DMB_PHASE_SYNC(16);
   int nefc = 0;
   if (active) {
     make_constraint(M, S, lane);
     nefc = S.nefc;
   }
-  DMB_PHASE_SYNC();
+  DMB_PHASE_SYNC(32);
   if (active && nefc > 0) {
     half_solve_rows(M, S, lane, nefc);
     gram(M, S, lane, nefc);
@@ -986,7 +1025,7 @@ __device__ __noinline__ float forward_eval(const ModelS& M, EnvS& S, int lane, f
     }
     __syncwarp();
   }
-  DMB_PHASE_SYNC();
+  DMB_PHASE_SYNC(64);
   if (active) solve_constraints(M, S, lane, nefc);
 #undef DMB_PHASE_SYNC
   return active ? S.com[2] : 0.f;

@@ -32,7 +32,7 @@ struct ModelS {
   // sizes / options
   int nq, nv, nu, nbody, njnt, ngeom, npair, nM;
   int iterations, max_con, max_efc, maxdepth;
-  int nclip, nframe_total, nee, pad_i;
+  int nclip, nframe_total, nee, sync_mask;  // sync_mask: which lockstep phase barriers are active
   float timestep, tolerance, pgs_scale, margin;
   float gravity[3], inv_total_mass;
   float imp_k, imp_b;        // reference spring constants after refsafe (mj_makeImpedance)
