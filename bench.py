@@ -289,7 +289,8 @@ def run_ours(a):
                              "note": "compute/latency-bound fp32 kernel: ~1e3 FLOP/B, see DESIGN.md"},
                 "e2e": {"value": n_global * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": E * sim.nu * 4,
                         "d2h_bytes_per_step": h_rec.numel() * 4},
-                "gpu_launches": K, "clocks": clocks}
+                "gpu_launches": 2 * K,  # k_order (scheduler sort) + k_step (fused env step) per step
+                "clocks": clocks}
         if not a.no_cpu_baseline:
             cpu = CpuRollout(1, a.motion, a.reward_mode)
             v, n, w = cpu.run(150000)

@@ -279,3 +279,35 @@ def test_full_size_properties():
         o2, r2, d2, _ = env2.step(act)
     assert torch.equal(o2, obs) and torch.equal(r2, rew)
     env.close(); env2.close()
+
+
+def test_config3_spinkick_16384_and_config5_mixed():
+    """BASELINE configs[2] (16384-env spinkick, early termination + auto-reset) and configs[4]
+    (mixed walk/dance_b/spinkick with per-env phase) at full per-GPU size: size-independent properties."""
+    from deepmimic_mujoco_b200.dist import mixed_clip_ids
+    from deepmimic_mujoco_b200.env import DPVecEnv
+    g = torch.Generator(device="cuda"); g.manual_seed(1)
+    env = DPVecEnv(16384, motions=("spinkick",), seed=1, reward_mode=4, auto_reset=True)
+    obs = env.reset()
+    assert (env.sim.idx_init >= 0).all() and (env.sim.idx_init < 78).all()
+    assert env.sim.idx_init.float().std() > 10          # RSI spreads over the clip
+    tot_done = 0
+    for t in range(12):
+        obs, rew, done, info = env.step(torch.rand(16384, 28, device="cuda", generator=g) - 0.5)
+        tot_done += int(done.sum())
+        assert torch.isfinite(obs).all() and (rew >= 0).all() and (rew <= 1 + 1e-6).all()
+    assert tot_done > 0 and int((env.sim.flags & 4).sum()) == 0
+    env.close()
+    clip_ids = mixed_clip_ids(0, 4096, 3)
+    env = DPVecEnv(4096, motions=("walk", "dance_b", "spinkick"), seed=2, reward_mode=4, auto_reset=True, clip_ids=clip_ids)
+    env.reset()
+    lens = torch.tensor([39, 153, 78], device="cuda")[clip_ids.cuda().long()]
+    for t in range(8):
+        obs, rew, done, info = env.step(torch.rand(4096, 28, device="cuda", generator=g) - 0.5)
+        assert (env.sim.idx_curr >= 0).all() and (env.sim.idx_curr < lens).all()   # phase stays inside each env's own clip
+        assert torch.isfinite(obs).all()
+    # phase advanced by one frame per step for envs that did not reset (dp_env_v3.py:101-102)
+    alive = env.sim.ep_len == 8
+    assert alive.any()
+    assert ((env.sim.idx_init[alive] + 8) % lens[alive] == env.sim.idx_curr[alive]).all()
+    env.close()

@@ -169,3 +169,52 @@ def test_passive_fall_matches_reference_statistic():
                 break
         lens.append(t + 1)
     assert 10 < np.mean(lens) < 120, lens
+
+
+def test_ref_aux_matches_independent_numpy():
+    """Reference-pose features (end effectors in the heading frame, CoM velocity): the oracle's C routine
+    vs the product's host numpy implementation (independent code paths)."""
+    from deepmimic_mujoco_b200.refaux import compute_ref_aux
+    mt = common.tables()
+    aux = compute_ref_aux(["walk"])
+    c = common.clip("walk")
+    L = po.lib(); m = common.model()
+    out = np.zeros(24)
+    for f in (0, 7, 20, 38):
+        q = np.ascontiguousarray(c.data_config[f]); v = np.ascontiguousarray(np.nan_to_num(c.data_vel[f]))
+        L.dmo_ref_aux(C.byref(m), po.dptr(q), po.dptr(v), po.dptr(out))
+        assert np.abs(out - aux[f]).max() < 1e-10
+
+
+def test_env_reset_modes_and_reward_bounds():
+    from deepmimic_mujoco_b200.model_blob import default_config
+    from deepmimic_mujoco_b200.refaux import compute_ref_aux
+    from deepmimic_mujoco_b200.sim import load_motions, make_mocap_struct
+    mt = common.tables()
+    L = po.lib(); m = common.model()
+    cfg = default_config(reward_mode=4, auto_reset=1)
+    aux = compute_ref_aux(["walk"])
+    mcs, keep = make_mocap_struct(load_motions(["walk"]), aux)
+    e = po.DmoEnv()
+    L.dmo_env_init(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), 3, 0, 0)
+    L.dmo_env_reset(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), 0)
+    assert 0 <= e.idx_init < 39 and e.idx_curr == e.idx_init
+    q = np.ctypeslib.as_array(e.d.qpos)[:35]
+    assert np.abs(q - np.float32(common.clip("walk").data_config[e.idx_init])).max() == 0
+    obs = np.zeros(56); rew = C.c_double()
+    rng = np.random.default_rng(0)
+    # a step from the exact reference pose with zero action scores a high imitation reward
+    a = np.zeros(28)
+    L.dmo_env_step(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), po.dptr(a), po.dptr(obs), C.byref(rew))
+    assert 0.3 < rew.value <= 1.0
+    ndone = 0
+    for t in range(300):
+        a = rng.uniform(-0.5, 0.5, 28)
+        ndone += L.dmo_env_step(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), po.dptr(a), po.dptr(obs), C.byref(rew))
+        assert 0.0 <= rew.value <= 1.0 and np.all(np.isfinite(obs))
+    assert ndone >= 3
+    e2 = po.DmoEnv()
+    L.dmo_env_init(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e2), 3, 0, 0)
+    L.dmo_env_reset(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e2), 1)
+    q2 = np.ctypeslib.as_array(e2.d.qpos)[:35]
+    assert 1e-4 < np.abs(q2 - mt.qpos0).max() <= 0.01 + 1e-7
