@@ -59,6 +59,14 @@ def measured_peak_hbm():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def host_cores():
+    """Cores this process may actually run on (cgroup/affinity aware)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -151,7 +159,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     per_step = 1000  # env-steps per core per bench "step": a bounded sample of the same workload
     cpu = CpuRollout(cores, a.motion, a.reward_mode)
     t_all, n_all, nst = 0.0, 0, 0
@@ -296,7 +304,7 @@ def run_ours(a):
             v, n, w = cpu.run(150000)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{n} env-steps of the same workload on 1 env (float64 oracle port), {w:.1f} s",
-                                    "host_cores": os.cpu_count()}
+                                    "host_cores": host_cores()}
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:

@@ -582,6 +582,8 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
       S.dof_anc[d][c++] = (int8_t)a;
     }
     S.dof_nanc[d] = (int8_t)c;
+    for (int a = 0; a < NVC; a++) S.anc_rank[d][a] = 255;
+    for (int k = 0; k < c; k++) S.anc_rank[d][S.dof_anc[d][k]] = (uint8_t)k;
     S.dof_Madr[d] = (int16_t)m->dof_Madr[d];
     S.dof_armature[d] = (float)m->dof_armature[d]; S.dof_damping[d] = (float)m->dof_damping[d];
     S.dof_invw[d] = (float)m->dof_invweight0[d];

@@ -728,28 +728,33 @@ __device__ __noinline__ void make_constraint(const ModelS& M, EnvS& S, int lane)
 // (dof d on lane d & 31, register `lo` for d < 32 and `hi` for d >= 32).  One broadcast shuffle
 // and one FFMA per dof: ~30 cycles of latency per dof instead of a shared-memory round trip.
 // ------------------------------------------------------------------------------------------
-// x <- L^-T x   (leaves -> root: every dof pushes its value to its ancestors)
+// x <- L^-T x   (leaves -> root: every dof pushes its value to its ancestors).  anc_rank[i][a]
+// is the position of ancestor a in row i of the factor (255 = not an ancestor): one byte load
+// replaces the 64-bit mask arithmetic.
 __device__ __forceinline__ void reg_solve_LT(const ModelS& M, const EnvS& S, int lane, float& lo, float& hi) {
+  const bool has_hi = lane + 32 < M.nv;
   for (int i = M.nv - 1; i > 0; i--) {
-    const unsigned long long am = M.dof_ancmask[i];
-    if (am == 0ull) continue;
+    if (M.dof_nanc[i] == 0) continue;
     const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
     if (xi == 0.f) continue;
-    const int adr = M.dof_Madr[i] + 1;
-    if ((am >> lane) & 1ull) lo -= S.qLD[adr + __popcll(am >> (lane + 1))] * xi;
-    if ((am >> 32) != 0ull && ((am >> (lane + 32)) & 1ull)) hi -= S.qLD[adr + __popcll(am >> (lane + 33))] * xi;
+    const float* Lrow = &S.qLD[M.dof_Madr[i] + 1];
+    const unsigned r = M.anc_rank[i][lane];
+    if (r != 255u) lo -= Lrow[r] * xi;
+    if (i > 32 && has_hi) { const unsigned rh = M.anc_rank[i][lane + 32]; if (rh != 255u) hi -= Lrow[rh] * xi; }
   }
 }
 // x <- L^-1 x   (root -> leaves: every dof pulls from its ancestors, one ancestor per step)
 __device__ __forceinline__ void reg_solve_L(const ModelS& M, const EnvS& S, int lane, float& lo, float& hi) {
-  const unsigned long long alo = lane < M.nv ? M.dof_ancmask[lane] : 0ull;
-  const unsigned long long ahi = lane + 32 < M.nv ? M.dof_ancmask[lane + 32] : 0ull;
-  const int adrlo = lane < M.nv ? M.dof_Madr[lane] + 1 : 0, adrhi = lane + 32 < M.nv ? M.dof_Madr[lane + 32] + 1 : 0;
+  const bool has_lo = lane < M.nv, has_hi = lane + 32 < M.nv;
+  const float* Llo = &S.qLD[has_lo ? M.dof_Madr[lane] + 1 : 0];
+  const float* Lhi = &S.qLD[has_hi ? M.dof_Madr[lane + 32] + 1 : 0];
+  const uint8_t* rlo = M.anc_rank[has_lo ? lane : 0];
+  const uint8_t* rhi = M.anc_rank[has_hi ? lane + 32 : 0];
   for (int i = 0; i < M.nv - 1; i++) {
     const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
     if (xi == 0.f) continue;
-    if ((alo >> i) & 1ull) lo -= S.qLD[adrlo + __popcll(alo >> (i + 1))] * xi;
-    if ((ahi >> i) & 1ull) hi -= S.qLD[adrhi + __popcll(ahi >> (i + 1))] * xi;
+    if (has_lo) { const unsigned r = rlo[i]; if (r != 255u) lo -= Llo[r] * xi; }
+    if (has_hi) { const unsigned r = rhi[i]; if (r != 255u) hi -= Lhi[r] * xi; }
   }
 }
 // z <- D^1/2 L x  (image of an acceleration in the half-solved space), smem in / smem out
@@ -782,13 +787,13 @@ __device__ __noinline__ void half_solve_rows(const ModelS& M, EnvS& S, int lane,
       while (sup) {
         const int i = 63 - __clzll((long long)sup);
         sup &= ~(1ull << i);
-        const unsigned long long am = M.dof_ancmask[i];
-        if (am == 0ull) continue;
+        if (M.dof_nanc[i] == 0) continue;
         const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
         if (xi == 0.f) continue;
-        const int adr = M.dof_Madr[i] + 1;
-        if ((am >> lane) & 1ull) lo -= S.qLD[adr + __popcll(am >> (lane + 1))] * xi;
-        if ((am >> 32) != 0ull && ((am >> (lane + 32)) & 1ull)) hi -= S.qLD[adr + __popcll(am >> (lane + 33))] * xi;
+        const float* Lrow = &S.qLD[M.dof_Madr[i] + 1];
+        const unsigned rk = M.anc_rank[i][lane];
+        if (rk != 255u) lo -= Lrow[rk] * xi;
+        if (i > 32 && lane + 32 < M.nv) { const unsigned rh = M.anc_rank[i][lane + 32]; if (rh != 255u) hi -= Lrow[rh] * xi; }
       }
       if (lane < M.nv) y[lane] = lo * dlo;
       if (lane + 32 < M.nv) y[lane + 32] = hi * dhi;

@@ -50,6 +50,7 @@ struct ModelS {
   int16_t dof_Madr[NVC];
   unsigned long long dof_velmask[NVC];  // dofs summed into the velocity seen by cdof_dot (mj_comVel)
   unsigned long long dof_ancmask[NVC];  // strict ancestors of each dof
+  uint8_t anc_rank[NVC][NVC];           // anc_rank[d][a] = k if a is the k-th ancestor of d (nearest first), else 255
   float dof_armature[NVC], dof_damping[NVC], dof_invw[NVC], dof_gear[NVC], dof_ctrl_lo[NVC], dof_ctrl_hi[NVC];
   float dof_kp[NVC], dof_kd[NVC], dof_weight[NVC];
   // inertia entries
