@@ -116,7 +116,7 @@ __device__ __forceinline__ void integrate_pos(const ModelS& M, EnvS& S, int lane
 // registers (dof d on lane d & 31).  forward_eval has a single call site (code size matters:
 // the kernel is instruction-fetch bound).  Returns the CoM height of the last stage evaluation.
 template <bool LOCKSTEP>
-__device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bool active) {
+__device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bool active, int bar_id, int bar_n, int* arrive) {
   const float h = M.timestep;
   const int d0 = lane, d1 = lane + 32;
   const bool a0 = active && d0 < M.nv, a1 = active && d1 < M.nv;
@@ -135,7 +135,7 @@ __device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bo
       if (active) integrate_pos(M, S, lane, h);
       __syncwarp();
     }
-    zc = forward_eval<LOCKSTEP>(M, S, lane, nullptr, active);
+    zc = forward_eval<LOCKSTEP>(M, S, lane, nullptr, active, bar_id, bar_n, arrive + st);
     const float bw = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);
     if (a0) { sv0 += bw * S.qvel[d0]; sa0 += bw * S.qacc[d0]; }
     if (a1) { sv1 += bw * S.qvel[d1]; sa1 += bw * S.qacc[d1]; }
@@ -309,17 +309,23 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
   EnvS& S = tiles[warp];
   const int od = (M.nq - 7) + (M.nv - 6);
-  __shared__ int s_base;
+  __shared__ int s_base[8];
+  __shared__ int s_arrive[4];
+  // lockstep groups: the CTA's warps are split into M.ngroups groups, each with its own named
+  // barrier and its own pull from the scheduler
+  const int gsz = LOCKSTEP ? W / M.ngroups : 1, grp = LOCKSTEP ? warp / gsz : 0, gw = LOCKSTEP ? warp % gsz : 0;
+  const int bar_id = 1 + grp, bar_n = gsz * 32;
   for (;;) {
-    // Scheduling: envs are handed out in order of decreasing constraint work (k_order), a CTA
-    // takes W consecutive entries at a time so that its warps see similar work between the
+    // Scheduling: envs are handed out in order of decreasing constraint work (k_order); a group
+    // takes gsz consecutive entries at a time so that its warps see similar work between the
     // lockstep barriers; without lockstep every warp pulls for itself.
     int env = N;
     if (LOCKSTEP) {
-      __syncthreads();
-      if (threadIdx.x == 0) s_base = atomicAdd(P.counter, W);
-      __syncthreads();
-      const int idx = s_base + warp;
+      group_barrier(bar_id, bar_n);
+      if (threadIdx.x < 4) s_arrive[threadIdx.x] = 0;   // per-stage arrival counters (soft barrier)
+      if (gw == 0 && lane == 0) s_base[grp] = atomicAdd(P.counter, gsz);
+      group_barrier(bar_id, bar_n);
+      const int idx = s_base[grp] + gw;
       if (idx < N) env = P.order[idx];
     } else {
       int idx = 0;
@@ -328,7 +334,7 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
       if (idx < N) env = P.order[idx];
     }
     const bool have = env < N;
-    if (LOCKSTEP) { if (s_base >= N) break; }
+    if (LOCKSTEP) { if (s_base[grp] >= N) break; }
     else if (!have) break;
     bool bad = false;
     if (have) {
@@ -336,7 +342,7 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
       bad = state_bad(M, S, lane);
       if (!bad) set_ctrl(M, S, action, env, lane);
     }
-    const float zc = rk4_step<LOCKSTEP>(M, S, lane, have && !bad);
+    const float zc = rk4_step<LOCKSTEP>(M, S, lane, have && !bad, bar_id, bar_n, s_arrive);
     if (!have) continue;
     if (!bad) bad = state_bad(M, S, lane);
     // reward (dp_env_v3.py:117 / 89-104)
@@ -368,7 +374,7 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
       if (out.last_ret) out.last_ret[env] = ep_ret;
       if (out.last_len) out.last_len[env] = ep_len;
       st.flags[env] = flags;
-      P.cost[env] = min(63, S.cost >> 6);
+      P.cost[env] = min(255, S.cost >> 4);
       st.idx_curr[env] = idx_curr;
       st.ep_len[env] = ep_len;
       st.ep_ret[env] = ep_ret;
@@ -386,22 +392,22 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
   }
 }
 
-// Counting sort of the envs by the constraint work of their previous step (64 buckets,
+// Counting sort of the envs by the constraint work of their previous step (256 buckets,
 // heaviest first) + reset of the scheduler counter.  One CTA; order inside a bucket is arbitrary
 // (envs are independent, so results do not depend on the schedule).
 __global__ void k_order(const int* __restrict__ cost, int* __restrict__ order, int* counter, int N) {
-  __shared__ int hist[64], cursor[64];
-  if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+  __shared__ int hist[256], cursor[256];
+  if (threadIdx.x < 256) hist[threadIdx.x] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&hist[min(63, max(0, cost[i]))], 1);
+  for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&hist[min(255, max(0, cost[i]))], 1);
   __syncthreads();
   if (threadIdx.x == 0) {
     int acc = 0;
-    for (int b = 63; b >= 0; b--) { cursor[b] = acc; acc += hist[b]; }
+    for (int b = 255; b >= 0; b--) { cursor[b] = acc; acc += hist[b]; }
     *counter = 0;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < N; i += blockDim.x) order[atomicAdd(&cursor[min(63, max(0, cost[i]))], 1)] = i;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) order[atomicAdd(&cursor[min(255, max(0, cost[i]))], 1)] = i;
 }
 
 __global__ void k_reset(DevPtrs P, dmb_state_t st, const unsigned char* __restrict__ mask, int mode, float* obs, int N,
@@ -455,7 +461,7 @@ __global__ void k_forward_debug(DevPtrs P, dmb_state_t st, const float* __restri
     float* row = dbgout + (size_t)env * dbg::stride;
     for (int i = lane; i < dbg::stride; i += 32) row[i] = 0.f;
     __syncwarp();
-    const float zc = forward_eval<false>(M, S, lane, row, true);
+    const float zc = forward_eval<false>(M, S, lane, row, true, 0, 0, nullptr);
     for (int i = lane; i < M.nbody * 6; i += 32) row[dbg::cvel + i] = S.cvel[i];
     for (int i = lane; i < M.nv; i += 32) row[dbg::qacc + i] = S.qacc[i];
     for (int r = lane; r < S.nefc; r += 32) row[dbg::efc_force + r] = S.e_f[r];
@@ -633,6 +639,9 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
   if (c->reward_mode != 0 && c->reward_mode != 1 && c->reward_mode != 4) { why = "reward_mode must be 0, 1 or 4"; return DMB_ERR_ARG; }
   if (c->ctrl_mode < 0 || c->ctrl_mode > 2) { why = "ctrl_mode must be 0, 1 or 2"; return DMB_ERR_ARG; }
   S.nclip = mc->nclip; S.nframe_total = mc->nframe_total;
+  S.ngroups = 1;
+  S.arrive_k = 0;
+  if (const char* ak = getenv("DMB_ARRIVE_K")) S.arrive_k = atoi(ak);
   S.sync_mask = 0x01;  // one barrier per RK stage (sweep on B200: best of 0x7f..0x01)
   if (const char* sm = getenv("DMB_SYNC_MASK")) S.sync_mask = (int)strtol(sm, nullptr, 0);
   if (mc->nclip < 1 || mc->nclip > DMB_MAX_CLIP) { why = "need 1..16 motion clips"; return DMB_ERR_ARG; }
@@ -720,6 +729,14 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
   if (const char* lenv = getenv("DMB_LOCKSTEP")) h->lockstep = atoi(lenv) != 0;
   if (const char* wenv = getenv("DMB_ENVS_PER_CTA")) { int w = atoi(wenv); if (w >= 1 && w < W) W = w; }
   if (W < 1) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, "not enough shared memory for one env tile"); }
+  {  // lockstep groups: DMB_GROUPS (default 1); must divide the warps of a CTA
+    int G = 1;
+    if (const char* genv = getenv("DMB_GROUPS")) G = atoi(genv);
+    if (G < 1 || G > 7 || W % G != 0) G = 1;
+    h->hmodel.ngroups = G;
+    e = cudaMemcpy(h->dmodel, &h->hmodel, sizeof(ModelS), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, cudaGetErrorString(e)); }
+  }
   h->envs_per_cta = W; h->block = 32 * W;
   h->smem = (int)(MODEL_BYTES + (size_t)W * sizeof(EnvS));
   int need = (num_envs + W - 1) / W;

@@ -177,7 +177,7 @@ __device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, floa
     const int c = M.dof_nanc[k];
     if (c == 0) continue;
     const int adrk = M.dof_Madr[k];
-    const float inv = 1.0f / S.qLD[adrk];
+    const float inv = __frcp_rn(S.qLD[adrk]);
     const int npair = c * (c + 1) / 2;
     for (int t = lane; t < npair; t += 32) {
       const int p = M.tri_p[t], q = M.tri_q[t];  // p <= q
@@ -189,9 +189,9 @@ __device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, floa
     __syncwarp();
   }
   for (int d = lane; d < M.nv; d += 32) {
-    float di = 1.0f / S.qLD[M.dof_Madr[d]];
-    S.dinv[d] = di;
-    S.dsq[d] = sqrtf(di);
+    const float dd = S.qLD[M.dof_Madr[d]];
+    S.dinv[d] = __frcp_rn(dd);
+    S.dsq[d] = rsqrtf(dd);
   }
   __syncwarp();
 }
@@ -976,9 +976,26 @@ __device__ __noinline__ void solve_constraints(const ModelS& M, EnvS& S, int lan
 // ~100 KB instruction stream of a stage is fetched once per CTA instead of once per warp --
 // the v2 profile showed 60% of warp stalls were instruction-fetch (stall_no_inst).  Warps with
 // no env (`active` false) only take part in the barriers.
+__device__ __forceinline__ void group_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// Soft stage barrier with arrival-order grouping: every warp of the CTA arrives once per RK stage
+// (`cnt` is that stage's counter, zeroed between env steps); warps are released in groups of K in
+// order of arrival -- early finishers leave together, stragglers form their own group -- so warps
+// that run the same code stay together without everybody waiting for the slowest env.
+__device__ __forceinline__ void arrival_barrier(int* cnt, int W, int K, int lane) {
+  if (lane == 0) {
+    const int a = atomicAdd(cnt, 1);
+    const int target = min(W, (a / K + 1) * K);
+    while (*(volatile int*)cnt < target) __nanosleep(64);
+  }
+  __syncwarp();
+}
+
 template <bool LOCKSTEP>
-__device__ __noinline__ float forward_eval(const ModelS& M, EnvS& S, int lane, float* dbgrow, bool active) {
-#define DMB_PHASE_SYNC(bit) do { if (LOCKSTEP && (M.sync_mask & (bit))) __syncthreads(); } while (0)
+__device__ __noinline__ float forward_eval(const ModelS& M, EnvS& S, int lane, float* dbgrow, bool active, int bar_id,
+                                         int bar_n, int* arrive) {
+#define DMB_PHASE_SYNC(bit) do { if (LOCKSTEP && (M.sync_mask & (bit))) { if (M.arrive_k > 0) arrival_barrier(arrive, bar_n >> 5, M.arrive_k, lane); else group_barrier(bar_id, bar_n); } } while (0)
   DMB_PHASE_SYNC(1);
   if (active) {
     kinematics(M, S, lane);

@@ -25,10 +25,11 @@ __device__ __forceinline__ V3 cross(V3 a, V3 b) {
 __device__ __forceinline__ float norm(V3 a) { return sqrtf(dot(a, a)); }
 // mju_normalize3: tiny vectors become (1,0,0); returns the norm
 __device__ __forceinline__ float normalize(V3& a) {
-  float n = norm(a);
-  if (n < DMB_MINVAL) { a = v3(1.f, 0.f, 0.f); }
-  else { float s = 1.0f / n; a = s * a; }
-  return n;
+  const float d2 = dot(a, a);
+  if (d2 < DMB_MINVAL * DMB_MINVAL) { a = v3(1.f, 0.f, 0.f); return sqrtf(d2); }
+  const float s = rsqrtf(d2);   // 2 ulp; one MUFU instead of sqrt + IEEE divide
+  a = s * a;
+  return d2 * s;
 }
 __device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
   Q4 r;
@@ -39,9 +40,9 @@ __device__ __forceinline__ Q4 qmul(Q4 a, Q4 b) {
   return r;
 }
 __device__ __forceinline__ Q4 qnormalize(Q4 q) {
-  float n = sqrtf(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
-  if (n < DMB_MINVAL) { q.w = 1.f; q.x = q.y = q.z = 0.f; }
-  else { float s = 1.0f / n; q.w *= s; q.x *= s; q.y *= s; q.z *= s; }
+  const float d2 = q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z;
+  if (d2 < DMB_MINVAL * DMB_MINVAL) { q.w = 1.f; q.x = q.y = q.z = 0.f; }
+  else { const float s = rsqrtf(d2); q.w *= s; q.x *= s; q.y *= s; q.z *= s; }
   return q;
 }
 __device__ __forceinline__ void quat2mat(float* m, Q4 q) {
