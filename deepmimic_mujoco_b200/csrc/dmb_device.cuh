@@ -735,12 +735,15 @@ __device__ __forceinline__ void reg_solve_LT(const ModelS& M, const EnvS& S, int
   const bool has_hi = lane + 32 < M.nv;
   for (int i = M.nv - 1; i > 0; i--) {
     if (M.dof_nanc[i] == 0) continue;
-    const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
-    if (xi == 0.f) continue;
+    // factor entries first (independent of x): the serial chain per dof is one shuffle + one FFMA
     const float* Lrow = &S.qLD[M.dof_Madr[i] + 1];
     const unsigned r = M.anc_rank[i][lane];
-    if (r != 255u) lo -= Lrow[r] * xi;
-    if (i > 32 && has_hi) { const unsigned rh = M.anc_rank[i][lane + 32]; if (rh != 255u) hi -= Lrow[rh] * xi; }
+    const float Lv = r != 255u ? Lrow[r] : 0.f;
+    float Lh = 0.f;
+    if (i > 32 && has_hi) { const unsigned rh = M.anc_rank[i][lane + 32]; if (rh != 255u) Lh = Lrow[rh]; }
+    const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
+    lo = fmaf(-Lv, xi, lo);
+    hi = fmaf(-Lh, xi, hi);
   }
 }
 // x <- L^-1 x   (root -> leaves: every dof pulls from its ancestors, one ancestor per step)
@@ -751,10 +754,11 @@ __device__ __forceinline__ void reg_solve_L(const ModelS& M, const EnvS& S, int 
   const uint8_t* rlo = M.anc_rank[has_lo ? lane : 0];
   const uint8_t* rhi = M.anc_rank[has_hi ? lane + 32 : 0];
   for (int i = 0; i < M.nv - 1; i++) {
+    const unsigned r = has_lo ? rlo[i] : 255u, rh = has_hi ? rhi[i] : 255u;
+    const float Lv = r != 255u ? Llo[r] : 0.f, Lh = rh != 255u ? Lhi[rh] : 0.f;
     const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
-    if (xi == 0.f) continue;
-    if (has_lo) { const unsigned r = rlo[i]; if (r != 255u) lo -= Llo[r] * xi; }
-    if (has_hi) { const unsigned r = rhi[i]; if (r != 255u) hi -= Lhi[r] * xi; }
+    lo = fmaf(-Lv, xi, lo);
+    hi = fmaf(-Lh, xi, hi);
   }
 }
 // z <- D^1/2 L x  (image of an acceleration in the half-solved space), smem in / smem out
@@ -788,12 +792,14 @@ __device__ __noinline__ void half_solve_rows(const ModelS& M, EnvS& S, int lane,
         const int i = 63 - __clzll((long long)sup);
         sup &= ~(1ull << i);
         if (M.dof_nanc[i] == 0) continue;
-        const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
-        if (xi == 0.f) continue;
         const float* Lrow = &S.qLD[M.dof_Madr[i] + 1];
         const unsigned rk = M.anc_rank[i][lane];
-        if (rk != 255u) lo -= Lrow[rk] * xi;
-        if (i > 32 && lane + 32 < M.nv) { const unsigned rh = M.anc_rank[i][lane + 32]; if (rh != 255u) hi -= Lrow[rh] * xi; }
+        const float Lv = rk != 255u ? Lrow[rk] : 0.f;
+        float Lh = 0.f;
+        if (i > 32 && lane + 32 < M.nv) { const unsigned rh = M.anc_rank[i][lane + 32]; if (rh != 255u) Lh = Lrow[rh]; }
+        const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
+        lo = fmaf(-Lv, xi, lo);
+        hi = fmaf(-Lh, xi, hi);
       }
       if (lane < M.nv) y[lane] = lo * dlo;
       if (lane + 32 < M.nv) y[lane + 32] = hi * dhi;
@@ -878,29 +884,39 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
     // the owner of a row remembers its increment and the residual it was computed from; the
     // cost decrease  -(0.5 delta^2 AR_ii + delta res_i)  is summed once per sweep
     float dm0 = 0.f, rm0 = 0.f, dm1 = 0.f, rm1 = 0.f;
+    // branch-free row updates; the AR column of row i+1 is loaded while row i is in flight, so the
+    // serial chain per row is FFMA -> FMNMX -> FADD -> SHFL -> FFMA
     int tri_i = 0;
+    float acol0 = a0 ? S.AR[t0] : 0.f;                       // column 0: AR[r0][0]
+    float acol1 = (HI && a1) ? S.AR[t1] : 0.f;
     for (int i = 0; i < nlo; i++) {
+      const int in = i + 1;                                   // next column (clamped reads stay in range)
+      const int tri_n = tri_i + in;
+      const float an0 = (a0 && in < nefc) ? S.AR[r0 >= in ? t0 + in : tri_n + r0] : 0.f;
+      const float an1 = (HI && a1 && in < nefc) ? S.AR[r1 >= in ? t1 + in : tri_n + r1] : 0.f;
       const float fnew = fmaxf(0.f, f0 - res0 * inv0);
       const float mine = fnew - f0;
       const float delta = __shfl_sync(DMB_FULL, mine, i);
       if (lane == i) { dm0 = mine; rm0 = res0; f0 = fnew; }
-      if (delta != 0.f) {
-        res0 += S.AR[r0 >= i ? t0 + i : tri_i + r0] * delta;
-        if (HI && a1) res1 += S.AR[t1 + i] * delta;   // r1 >= 32 > i
-      }
-      tri_i += i + 1;
+      res0 = fmaf(acol0, delta, res0);
+      if (HI) res1 = fmaf(acol1, delta, res1);
+      acol0 = an0; acol1 = an1;
+      tri_i = tri_n;
     }
     if (HI) {
       for (int i = 32; i < nefc; i++) {
+        const int in = i + 1;
+        const int tri_n = tri_i + in;
+        const float an0 = (a0 && in < nefc) ? S.AR[tri_n + r0] : 0.f;   // in > 32 > r0
+        const float an1 = (a1 && in < nefc) ? S.AR[r1 >= in ? t1 + in : tri_n + r1] : 0.f;
         const float fnew = fmaxf(0.f, f1 - res1 * inv1);
         const float mine = fnew - f1;
         const float delta = __shfl_sync(DMB_FULL, mine, i - 32);
         if (lane == i - 32) { dm1 = mine; rm1 = res1; f1 = fnew; }
-        if (delta != 0.f) {
-          res0 += S.AR[tri_i + r0] * delta;          // i >= 32 > r0
-          if (a1) res1 += S.AR[r1 >= i ? t1 + i : tri_i + r1] * delta;
-        }
-        tri_i += i + 1;
+        res0 = fmaf(acol0, delta, res0);
+        res1 = fmaf(acol1, delta, res1);
+        acol0 = an0; acol1 = an1;
+        tri_i = tri_n;
       }
     }
     iter++;
