@@ -659,11 +659,11 @@ __device__ __noinline__ void make_constraint(const ModelS& M, EnvS& S, int lane)
           const V3 p = cl + cross(ca, ld3(&S.c_pos[3 * c]) - com);
           jn = sg * dot(ld3(fr), p); j1 = sg * dot(ld3(fr + 3), p); j2 = sg * dot(ld3(fr + 6), p);
         }
-        const float mu = S.c_mu[c];
-        S.u.Y[a * YS + d] = jn + mu * j1;
-        S.u.Y[(a + 1) * YS + d] = jn - mu * j1;
-        S.u.Y[(a + 2) * YS + d] = jn + mu * j2;
-        S.u.Y[(a + 3) * YS + d] = jn - mu * j2;
+        // base rows of the contact frame; half_solve_rows() solves these three together and then
+        // expands them to the four pyramid edges  n +- mu t1, n +- mu t2
+        S.u.Y[a * YS + d] = jn;
+        S.u.Y[(a + 1) * YS + d] = j1;
+        S.u.Y[(a + 2) * YS + d] = j2;
       }
     }
   }
@@ -773,57 +773,65 @@ __device__ void mul_L_sqrtD(const ModelS& M, EnvS& S, int lane, const float* x, 
 }
 
 // ------------------------------------------------------------------------------------------
-// Half solve  Y_r <- D^-1/2 L^-T Y_r.  S.rowmask[r] holds the ancestor-closed dof support of
-// row r (chains of the bodies in contact / of the limited joint), which the elimination keeps.
-// Two schedules with identical arithmetic per entry:
-//  * few rows  -> one row at a time in registers (lane = dof), visiting only the dofs of the
-//    row's support, deepest first (one broadcast shuffle + one FFMA per dof);
-//  * many rows -> all rows at once (lane = row), serial over dofs with warp-uniform bounds; the
-//    <= 12 ancestor updates of one dof are independent, so loads are batched ahead of the FMAs.
+// Half solve  Y_r <- D^-1/2 L^-T J_r'  (lane = dof, rows in registers).  S.rowmask[r] holds the
+// ancestor-closed dof support of row r (chains of the bodies in contact / of the limited joint);
+// only those dofs are visited, deepest first: one broadcast shuffle + one FFMA per dof and row.
+// A pyramidal contact arrives as its three frame rows (n, t1, t2), which share one support: they
+// are eliminated together (factor entries and index work shared) and then expanded to the four
+// edge rows  n +- mu t1,  n +- mu t2  (the elimination is linear).
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void half_solve_rows(const ModelS& M, EnvS& S, int lane, int nrows) {
-  if (nrows <= 12) {
-    const float dlo = lane < M.nv ? S.dsq[lane] : 0.f, dhi = lane + 32 < M.nv ? S.dsq[lane + 32] : 0.f;
-    for (int r = 0; r < nrows; r++) {
-      float* y = &S.u.Y[r * YS];
-      float lo = lane < M.nv ? y[lane] : 0.f, hi = lane + 32 < M.nv ? y[lane + 32] : 0.f;
-      unsigned long long sup = S.rowmask[r];
-      while (sup) {
-        const int i = 63 - __clzll((long long)sup);
-        sup &= ~(1ull << i);
-        if (M.dof_nanc[i] == 0) continue;
-        const float* Lrow = &S.qLD[M.dof_Madr[i] + 1];
-        const unsigned rk = M.anc_rank[i][lane];
-        const float Lv = rk != 255u ? Lrow[rk] : 0.f;
-        float Lh = 0.f;
-        if (i > 32 && lane + 32 < M.nv) { const unsigned rh = M.anc_rank[i][lane + 32]; if (rh != 255u) Lh = Lrow[rh]; }
-        const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
-        lo = fmaf(-Lv, xi, lo);
-        hi = fmaf(-Lh, xi, hi);
-      }
-      if (lane < M.nv) y[lane] = lo * dlo;
-      if (lane + 32 < M.nv) y[lane + 32] = hi * dhi;
+  const bool has_lo = lane < M.nv, has_hi = lane + 32 < M.nv;
+  const float dlo = has_lo ? S.dsq[lane] : 0.f, dhi = has_hi ? S.dsq[lane + 32] : 0.f;
+  int r = 0;
+  while (r < nrows) {
+    const int src = S.e_src[r];
+    const bool pyr = src >= 0 && S.c_dim[src >> 2] == 3;
+    float* y = &S.u.Y[r * YS];
+    float a_lo = has_lo ? y[lane] : 0.f, a_hi = has_hi ? y[lane + 32] : 0.f;
+    float b_lo = 0.f, b_hi = 0.f, c_lo = 0.f, c_hi = 0.f;
+    if (pyr) {
+      if (has_lo) { b_lo = y[YS + lane]; c_lo = y[2 * YS + lane]; }
+      if (has_hi) { b_hi = y[YS + lane + 32]; c_hi = y[2 * YS + lane + 32]; }
     }
-    __syncwarp();
-    return;
-  }
-  for (int base = 0; base < nrows; base += 32) {
-    const int r = base + lane;
-    const bool act = r < nrows;
-    float* y = &S.u.Y[(act ? r : 0) * YS];
-    for (int i = M.nv - 1; i >= 0; i--) {
-      const float yi = act ? y[i] : 0.f;
-      if (!__any_sync(DMB_FULL, yi != 0.f)) continue;
-      const int c = M.dof_nanc[i], adr = M.dof_Madr[i] + 1;
-      if (act && yi != 0.f) {
-        float tmp[MAXANC];
-#pragma unroll
-        for (int k = 0; k < MAXANC; k++) if (k < c) tmp[k] = y[M.dof_anc[i][k]];
-#pragma unroll
-        for (int k = 0; k < MAXANC; k++) if (k < c) y[M.dof_anc[i][k]] = tmp[k] - S.qLD[adr + k] * yi;
+    unsigned long long sup = S.rowmask[r];
+    while (sup) {
+      const int i = 63 - __clzll((long long)sup);
+      sup &= ~(1ull << i);
+      if (M.dof_nanc[i] == 0) continue;
+      const float* Lrow = &S.qLD[M.dof_Madr[i] + 1];
+      const unsigned rk = M.anc_rank[i][lane];
+      const float Lv = rk != 255u ? Lrow[rk] : 0.f;
+      float Lh = 0.f;
+      if (i > 32 && has_hi) { const unsigned rh = M.anc_rank[i][lane + 32]; if (rh != 255u) Lh = Lrow[rh]; }
+      const int sl = i & 31;
+      if (pyr) {
+        const float xa = __shfl_sync(DMB_FULL, i >= 32 ? a_hi : a_lo, sl);
+        const float xb = __shfl_sync(DMB_FULL, i >= 32 ? b_hi : b_lo, sl);
+        const float xc = __shfl_sync(DMB_FULL, i >= 32 ? c_hi : c_lo, sl);
+        a_lo = fmaf(-Lv, xa, a_lo); b_lo = fmaf(-Lv, xb, b_lo); c_lo = fmaf(-Lv, xc, c_lo);
+        a_hi = fmaf(-Lh, xa, a_hi); b_hi = fmaf(-Lh, xb, b_hi); c_hi = fmaf(-Lh, xc, c_hi);
+      } else {
+        const float xa = __shfl_sync(DMB_FULL, i >= 32 ? a_hi : a_lo, sl);
+        a_lo = fmaf(-Lv, xa, a_lo);
+        a_hi = fmaf(-Lh, xa, a_hi);
       }
     }
-    if (act) for (int i = 0; i < M.nv; i++) y[i] *= S.dsq[i];
+    a_lo *= dlo; a_hi *= dhi;
+    if (pyr) {
+      const float mu = S.c_mu[src >> 2];
+      b_lo *= mu * dlo; b_hi *= mu * dhi; c_lo *= mu * dlo; c_hi *= mu * dhi;
+      if (has_lo) { y[lane] = a_lo + b_lo; y[YS + lane] = a_lo - b_lo; y[2 * YS + lane] = a_lo + c_lo; y[3 * YS + lane] = a_lo - c_lo; }
+      if (has_hi) {
+        y[lane + 32] = a_hi + b_hi; y[YS + lane + 32] = a_hi - b_hi;
+        y[2 * YS + lane + 32] = a_hi + c_hi; y[3 * YS + lane + 32] = a_hi - c_hi;
+      }
+      r += 4;
+    } else {
+      if (has_lo) y[lane] = a_lo;
+      if (has_hi) y[lane + 32] = a_hi;
+      r += 1;
+    }
   }
   __syncwarp();
 }
