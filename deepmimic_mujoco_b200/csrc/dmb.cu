@@ -590,6 +590,7 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
     S.dof_nanc[d] = (int8_t)c;
     for (int a = 0; a < NVC; a++) S.anc_rank[d][a] = 255;
     for (int k = 0; k < c; k++) S.anc_rank[d][S.dof_anc[d][k]] = (uint8_t)k;
+    for (int k = 0; k < c; k++) S.anc_rowbase[d][k] = (int16_t)m->dof_Madr[S.dof_anc[d][k]];
     S.dof_Madr[d] = (int16_t)m->dof_Madr[d];
     S.dof_armature[d] = (float)m->dof_armature[d]; S.dof_damping[d] = (float)m->dof_damping[d];
     S.dof_invw[d] = (float)m->dof_invweight0[d];
@@ -641,6 +642,10 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
   S.nclip = mc->nclip; S.nframe_total = mc->nframe_total;
   S.ngroups = 1;
   S.arrive_k = 0;
+  S.cost_mode = 0;
+  S.patience = 0;
+  if (const char* pt = getenv("DMB_PATIENCE")) S.patience = atoi(pt);
+  if (const char* cm = getenv("DMB_COST_MODE")) S.cost_mode = atoi(cm);
   if (const char* ak = getenv("DMB_ARRIVE_K")) S.arrive_k = atoi(ak);
   S.sync_mask = 0x01;  // one barrier per RK stage (sweep on B200: best of 0x7f..0x01)
   if (const char* sm = getenv("DMB_SYNC_MASK")) S.sync_mask = (int)strtol(sm, nullptr, 0);

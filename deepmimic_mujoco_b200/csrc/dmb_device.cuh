@@ -172,27 +172,36 @@ __device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, floa
     if (dbg_qM) dbg_qM[e] = s;
   }
   __syncwarp();
-  // sparse L'DL (mj_factorM): for k = nv-1..0 eliminate dof k from all its ancestors
+  // sparse L'DL (mj_factorM): for k = nv-1..0 eliminate dof k from all its ancestors.  Each lane
+  // keeps the (p, q) decode of its <= 3 update slots in registers; anc_rowbase[k][p] is the packed
+  // address of the row of k's p-th ancestor (one table load instead of a dependent pair); rows are
+  // left unscaled during the elimination and divided by their pivot in one parallel pass at the end.
+  int tp[3], tq[3];
+#pragma unroll
+  for (int u = 0; u < 3; u++) { const int t = lane + 32 * u; tp[u] = t < 78 ? M.tri_p[t] : 0; tq[u] = t < 78 ? M.tri_q[t] : 0; }
   for (int k = M.nv - 1; k >= 0; k--) {
     const int c = M.dof_nanc[k];
     if (c == 0) continue;
     const int adrk = M.dof_Madr[k];
+    const float* rowk = &S.qLD[adrk + 1];
     const float inv = __frcp_rn(S.qLD[adrk]);
     const int npair = c * (c + 1) / 2;
-    for (int t = lane; t < npair; t += 32) {
-      const int p = M.tri_p[t], q = M.tri_q[t];  // p <= q
-      const int i = M.dof_anc[k][p];
-      S.qLD[M.dof_Madr[i] + (q - p)] -= S.qLD[adrk + 1 + p] * S.qLD[adrk + 1 + q] * inv;
+#pragma unroll
+    for (int u = 0; u < 3; u++) {
+      if (lane + 32 * u < npair) {
+        const int p = tp[u], q = tq[u];  // p <= q
+        float* dst = &S.qLD[M.anc_rowbase[k][p] + (q - p)];
+        *dst -= rowk[p] * rowk[q] * inv;
+      }
     }
     __syncwarp();
-    if (lane < c) S.qLD[adrk + 1 + lane] *= inv;
-    __syncwarp();
   }
-  for (int d = lane; d < M.nv; d += 32) {
-    const float dd = S.qLD[M.dof_Madr[d]];
-    S.dinv[d] = __frcp_rn(dd);
-    S.dsq[d] = rsqrtf(dd);
+  // L entries = row / pivot; D^-1/2 for the half solves
+  for (int e = lane; e < M.nM; e += 32) {
+    const int i = M.M_i[e];
+    if (M.M_j[e] != i) S.qLD[e] *= __frcp_rn(S.qLD[M.dof_Madr[i]]);
   }
+  for (int d = lane; d < M.nv; d += 32) S.dsq[d] = rsqrtf(S.qLD[M.dof_Madr[d]]);
   __syncwarp();
 }
 
@@ -973,7 +982,7 @@ __device__ __noinline__ void solve_constraints(const ModelS& M, EnvS& S, int lan
     if (a1) S.e_f[r1] = f1;
     __syncwarp();
   }
-  if (lane == 0) { S.iter = iter; S.cost += nefc * iter; }
+  if (lane == 0) { S.iter = iter; S.cost += M.cost_mode == 1 ? nefc * 16 : (M.cost_mode == 2 ? nefc * (16 + iter) : nefc * iter); }
   // t = y_s + sum_r Y_r f_r  (lane = dof), then qacc = L^-1 D^-1/2 t in registers
   float tlo = lane < M.nv ? S.ys[lane] : 0.f, thi = lane + 32 < M.nv ? S.ys[lane + 32] : 0.f;
   for (int r = 0; r < nefc; r++) {
@@ -1015,11 +1024,21 @@ __device__ __forceinline__ void arrival_barrier(int* cnt, int W, int K, int lane
   }
   __syncwarp();
 }
+// Stage barrier with a patience limit: wait for all W warps, but at most `patience` cycles -- warps
+// stay together when their work is similar and stop waiting for a straggler that is far behind.
+__device__ __forceinline__ void patient_barrier(int* cnt, int W, int patience, int lane) {
+  if (lane == 0) {
+    atomicAdd(cnt, 1);
+    const long long t0 = clock64();
+    while (*(volatile int*)cnt < W && clock64() - t0 < (long long)patience) __nanosleep(32);
+  }
+  __syncwarp();
+}
 
 template <bool LOCKSTEP>
 __device__ __noinline__ float forward_eval(const ModelS& M, EnvS& S, int lane, float* dbgrow, bool active, int bar_id,
                                          int bar_n, int* arrive) {
-#define DMB_PHASE_SYNC(bit) do { if (LOCKSTEP && (M.sync_mask & (bit))) { if (M.arrive_k > 0) arrival_barrier(arrive, bar_n >> 5, M.arrive_k, lane); else group_barrier(bar_id, bar_n); } } while (0)
+#define DMB_PHASE_SYNC(bit) do { if (LOCKSTEP && (M.sync_mask & (bit))) { if (M.arrive_k > 0) arrival_barrier(arrive, bar_n >> 5, M.arrive_k, lane); else if (M.patience > 0) patient_barrier(arrive, bar_n >> 5, M.patience, lane); else group_barrier(bar_id, bar_n); } } while (0)
   DMB_PHASE_SYNC(1);
   if (active) {
     kinematics(M, S, lane);

@@ -33,7 +33,7 @@ struct ModelS {
   int nq, nv, nu, nbody, njnt, ngeom, npair, nM;
   int iterations, max_con, max_efc, maxdepth;
   int nclip, nframe_total, nee, sync_mask;  // sync_mask: which lockstep phase barriers are active
-  int ngroups, arrive_k, pad_g1, pad_g2;    // arrive_k > 0: stage barrier releases warps in arrival-order groups of k      // lockstep groups per CTA (each with its own named barrier)
+  int ngroups, arrive_k, cost_mode, patience;  // patience > 0: stage barrier gives up after that many cycles    // arrive_k > 0: stage barrier releases warps in arrival-order groups of k      // lockstep groups per CTA (each with its own named barrier)
   float timestep, tolerance, pgs_scale, margin;
   float gravity[3], inv_total_mass;
   float imp_k, imp_b;        // reference spring constants after refsafe (mj_makeImpedance)
@@ -49,6 +49,7 @@ struct ModelS {
   // dofs
   int8_t dof_bodyid[NVC], dof_kind[NVC], dof_axisk[NVC], dof_nanc[NVC], dof_anc[NVC][MAXANC], dof_act[NVC];
   int16_t dof_Madr[NVC];
+  int16_t anc_rowbase[NVC][MAXANC];     // dof_Madr of the p-th ancestor of each dof
   unsigned long long dof_velmask[NVC];  // dofs summed into the velocity seen by cdof_dot (mj_comVel)
   unsigned long long dof_ancmask[NVC];  // strict ancestors of each dof
   uint8_t anc_rank[NVC][NVC];           // anc_rank[d][a] = k if a is the k-th ancestor of d (nearest first), else 255
@@ -103,7 +104,7 @@ struct EnvS {
   float vec0[NQC], vec1[NQC], ys[NQC];  // qfrc_smooth / scratch / y_s = D^-1/2 L^-T qfrc_smooth
   float com[4];
   float cdof[NVC * 6], cvel[NB * 6];
-  float qLD[NMX], dinv[NVC], dsq[NVC];
+  float qLD[NMX], dsq[NVC];
   // contacts
   float c_dist[MAXC], c_pos[MAXC * 3], c_frame[MAXC * 9], c_mu[MAXC];
   int c_g1[MAXC], c_g2[MAXC], c_dim[MAXC], c_adr[MAXC];
