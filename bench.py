@@ -60,11 +60,26 @@ def measured_peak_hbm():
 
 
 def host_cores():
-    """Cores this process may actually run on (cgroup/affinity aware)."""
+    """Cores this process may actually use: CPU affinity, capped by the cgroup CPU quota when one is set
+    (oversubscribing a quota-limited container only adds context switches to the CPU arm)."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:            # cgroup v2: "<quota|max> <period>"
+            q, per = f.read().split()
+        if q != "max":
+            n = max(1, min(n, int(-(-int(q) // int(per)))))
+    except Exception:
+        try:                                                  # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = max(1, min(n, -(-q // per)))
+        except Exception:
+            pass
+    return n
 
 
 class ClockSampler(threading.Thread):
