@@ -122,6 +122,7 @@ class Oracle:
         self.d.arr("qvel")[: self.nv] = qvel
         self.d.arr("ctrl")[: self.nu] = 0.0 if ctrl is None else ctrl
         self.d.arr("qacc_warmstart")[: self.nv] = 0.0 if warm is None else warm
+        self.d.flags = 0   # overflow / non-finite flags accumulate until the next set_state
 
     def forward(self):
         self.L.dmo_forward(C.byref(self.m), C.byref(self.d))

@@ -311,3 +311,71 @@ def test_config3_spinkick_16384_and_config5_mixed():
     assert alive.any()
     assert ((env.sim.idx_init[alive] + 8) % lens[alive] == env.sim.idx_curr[alive]).all()
     env.close()
+
+
+def test_capacity_overflow_matches_oracle(ctx):
+    """A humanoid lying on the floor produces more contacts / rows than the per-env capacities
+    (max_con 16, max_efc 40): the CUDA path must drop exactly the contacts the oracle drops and raise
+    the same flags."""
+    sim, o, mt, po = ctx
+    rng = np.random.default_rng(21)
+    q = np.tile(mt.qpos0, (N, 1)); v = np.zeros((N, mt.nv))
+    for i in range(N):
+        ang = np.pi / 2 + rng.uniform(-0.2, 0.2)
+        q[i, 3:7] = [np.cos(ang / 2), 0, np.sin(ang / 2), 0]      # pitched onto its back / front
+        q[i, 2] = rng.uniform(0.08, 0.14)
+        q[i, 7:] = rng.uniform(-0.15, 0.15, mt.nq - 7)
+    q, v = common.f32(q), common.f32(v)
+    ctrl = np.zeros((N, mt.nu))
+    sim.set_state(q, v)
+    g = sim.forward_debug(torch.tensor(ctrl, dtype=torch.float32))
+    flags = sim.flags.cpu().numpy()
+    nover = 0
+    for i in range(N):
+        d = oracle_forward(o, mt, q[i], v[i], ctrl[i], np.zeros(mt.nv))
+        assert d.ncon == g["ncon"][i] and d.nefc == g["nefc"][i], (i, d.ncon, g["ncon"][i], d.nefc, g["nefc"][i])
+        assert (d.flags & 3) == (flags[i] & 3), (i, d.flags, flags[i])
+        assert d.ncon <= 16 and d.nefc <= 40
+        nover += int((d.flags & 3) != 0)
+        if d.ncon:
+            oc = np.array([[c.dist, c.geom1, c.geom2, c.dim] for c in d.contact[:d.ncon]])
+            gc = g["contact"][i][: d.ncon][:, [0, 13, 14, 15]]
+            assert np.abs(oc - gc).max() < 2e-5
+    assert nover > 0, "test state should exceed the capacities at least once"
+
+
+def test_nonfinite_state_guard():
+    from deepmimic_mujoco_b200.sim import BatchedSim
+    mt = common.tables()
+    sim = BatchedSim(8, motions=("walk",), seed=0)
+    q = np.tile(mt.qpos0, (8, 1)); v = np.zeros((8, mt.nv))
+    v[3, 10] = 1e12                      # |qvel| >= 1e10 is MuJoCo's mj_checkVel "bad state"
+    q[5, 1] = np.nan
+    sim.set_state(q, v)
+    obs, rew, done = sim.step(torch.zeros(8, 28, device=sim.device))
+    done = done.cpu().numpy(); flags = sim.flags.cpu().numpy(); rew = rew.cpu().numpy()
+    assert done[3] == 1 and done[5] == 1 and (flags[3] & 4) and (flags[5] & 4) and rew[3] == 0 and rew[5] == 0
+    assert done[[0, 1, 2, 4, 6, 7]].sum() == 0 and (flags[[0, 1, 2, 4, 6, 7]] & 4).sum() == 0
+    gq, gv, _ = sim.get_state()
+    assert np.isfinite(gq).all() and np.isfinite(gv).all()
+    assert np.abs(gq[3] - np.float32(mt.qpos0)).max() == 0 and np.abs(gv[3]).max() == 0   # parked at the reference pose
+    assert torch.isfinite(obs).all()
+    sim.close()
+
+
+def test_odd_batch_sizes():
+    """N not a multiple of the envs per CTA / smaller than one CTA; results independent of N and of the schedule."""
+    from deepmimic_mujoco_b200.sim import BatchedSim
+    mt = common.tables()
+    rng = np.random.default_rng(5)
+    q, v = common.standing_states(rng, 37)
+    act = common.f32(rng.uniform(-0.5, 0.5, (37, 28)))
+    outs = []
+    for n in (37, 5, 1):
+        sim = BatchedSim(n, motions=("walk",), seed=0)
+        sim.set_state(q[:n], v[:n])
+        sim.step(torch.tensor(act[:n], dtype=torch.float32, device=sim.device))
+        outs.append(sim.get_state()[:2])
+        sim.close()
+    for n, (gq, gv) in zip((5, 1), outs[1:]):
+        assert np.array_equal(gq, outs[0][0][:n]) and np.array_equal(gv, outs[0][1][:n])
