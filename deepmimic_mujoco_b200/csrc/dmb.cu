@@ -363,7 +363,12 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
     }
     if (bad) rew = 0.f;
     // termination (dp_env_v3.py:134-139) on the CoM height of the last stage evaluation
-    const bool done = bad || zc < M.z_min || zc > M.z_max;
+    bool done = bad || zc < M.z_min || zc > M.z_max;
+    if (M.term_mode == 1 && !bad) {  // DeepMimic fall-contact rule on the contacts of the last RK4 stage
+      bool fall = false;
+      if (lane < S.ncon) fall = M.geom_type[S.c_g1[lane]] == DMB_GEOM_PLANE && ((M.fall_body_mask >> M.geom_bodyid[S.c_g2[lane]]) & 1u);
+      done = done || __any_sync(DMB_FULL, fall);
+    }
     const int flags = S.flags | (bad ? 4 : 0);
     int ep_len = st.ep_len[env] + 1;
     float ep_ret = st.ep_ret[env] + rew;
@@ -633,6 +638,7 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
   S.nee = m->nee;
   for (int e = 0; e < m->nee; e++) { S.ee_body[e] = m->ee_body[e]; for (int k = 0; k < 3; k++) S.ee_pos[e][k] = (float)m->ee_pos[e][k]; }
   S.ctrl_mode = c->ctrl_mode; S.reward_mode = c->reward_mode; S.reset_mode = c->reset_mode; S.auto_reset = c->auto_reset;
+  S.term_mode = c->term_mode; S.fall_body_mask = c->fall_body_mask;
   S.z_min = (float)c->z_min; S.z_max = (float)c->z_max; S.reset_noise = (float)c->reset_noise; S.pd_dt = (float)m->timestep;
   S.w_pose = (float)c->w_pose; S.w_vel = (float)c->w_vel; S.w_ee = (float)c->w_end_eff; S.w_root = (float)c->w_root; S.w_com = (float)c->w_com;
   S.s_pose = (float)c->s_pose; S.s_vel = (float)c->s_vel; S.s_ee = (float)c->s_end_eff; S.s_root = (float)c->s_root; S.s_com = (float)c->s_com;

@@ -92,6 +92,9 @@ typedef struct dmb_config {
                           4: 5-term DeepMimic (code.md:979-1146) */
   int32_t reset_mode;  /* 0: mocap RSI (dp_env_v3.py:148-156); 1: init pose + U(-.01,.01) (158-164) */
   int32_t auto_reset;  /* 1: done envs are re-initialised inside step (vec_env semantics) */
+  int32_t term_mode;   /* 0: CoM height only (dp_env_v3.py:134-139); 1: + DeepMimic fall-contact rule
+                          (--fall_contact_bodies, src/args/train_humanoid3d_walk_args.txt:20) */
+  uint32_t fall_body_mask; /* bit b set: a floor contact of body b ends the episode (all but the ankles) */
   double z_min, z_max; /* CoM-height termination band (dp_env_v3.py:134-139): 0.7, 2.0 */
   double reset_noise;  /* 0.01 */
   double w_pose, w_vel, w_end_eff, w_root, w_com;          /* dp_env_v3.py:42-46 */

@@ -1129,6 +1129,12 @@ int dmo_env_step(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_
   }
   if (bad) rew = 0;
   int done = bad || zc < cfg->z_min || zc > cfg->z_max;
+  if (cfg->term_mode == 1) { /* fall contact: a listed body touches the floor (contacts of the last RK4 stage) */
+    for (int ci = 0; ci < d->ncon; ci++) {
+      const dmo_contact_t* c = &d->contact[ci];
+      if (m->geom_type[c->geom1] == DMB_GEOM_PLANE && ((cfg->fall_body_mask >> m->geom_bodyid[c->geom2]) & 1u)) done = 1;
+    }
+  }
   e->ep_len++; e->ep_ret += rew;
   *reward = rew;
   if (done && cfg->auto_reset) dmo_env_reset(m, cfg, mc, e, cfg->reset_mode);

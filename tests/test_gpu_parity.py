@@ -146,11 +146,12 @@ def test_step_airborne_self_contacts(ctx):
     compare_step(ctx, q, v, common.f32(rng.uniform(-0.5, 0.5, (N, 28))), vtol=3e-4)
 
 
-def _env_pair(po, reward_mode, ctrl_mode, motions=("walk",), n=32, seed=5, auto_reset=1, reset_mode=0):
+def _env_pair(po, reward_mode, ctrl_mode, motions=("walk",), n=32, seed=5, auto_reset=1, reset_mode=0, term_mode=0):
     from deepmimic_mujoco_b200.model_blob import default_config
     from deepmimic_mujoco_b200.refaux import compute_ref_aux
     from deepmimic_mujoco_b200.sim import BatchedSim, load_motions, make_mocap_struct
-    cfg = default_config(reward_mode=reward_mode, ctrl_mode=ctrl_mode, auto_reset=auto_reset, reset_mode=reset_mode)
+    cfg = default_config(reward_mode=reward_mode, ctrl_mode=ctrl_mode, auto_reset=auto_reset, reset_mode=reset_mode,
+                         term_mode=term_mode)
     aux = compute_ref_aux(motions) if reward_mode == 4 else None
     clip_ids = torch.arange(n, dtype=torch.int32) % len(motions)
     sim = BatchedSim(n, motions=motions, seed=seed, config=cfg, ref_aux=aux, clip_ids=clip_ids)
@@ -158,14 +159,14 @@ def _env_pair(po, reward_mode, ctrl_mode, motions=("walk",), n=32, seed=5, auto_
     return sim, cfg, mcs, keep, clip_ids
 
 
-@pytest.mark.parametrize("reward_mode,ctrl_mode", [(0, 0), (1, 0), (4, 0), (4, 1), (1, 2)])
-def test_env_step_rewards_pd_and_reset(ctx, reward_mode, ctrl_mode):
+@pytest.mark.parametrize("reward_mode,ctrl_mode,term_mode", [(0, 0, 0), (1, 0, 0), (4, 0, 0), (4, 1, 0), (1, 2, 0), (4, 0, 1)])
+def test_env_step_rewards_pd_and_reset(ctx, reward_mode, ctrl_mode, term_mode):
     """Full env step (PD -> RK4 -> reward -> done -> auto reset) for a few consecutive steps vs the
     oracle env; RSI frame indices must be bit-identical (same Philox stream)."""
     _, _, mt, po = ctx
     n = 32
     motions = ("walk", "dance_b", "spinkick")
-    sim, cfg, mcs, keep, clip_ids = _env_pair(po, reward_mode, ctrl_mode, motions, n)
+    sim, cfg, mcs, keep, clip_ids = _env_pair(po, reward_mode, ctrl_mode, motions, n, term_mode=term_mode)
     L = po.lib()
     m = common.model()
     envs = [po.DmoEnv() for _ in range(n)]
@@ -179,7 +180,8 @@ def test_env_step_rewards_pd_and_reset(ctx, reward_mode, ctrl_mode):
         assert np.abs(np.ctypeslib.as_array(e.d.qpos)[: mt.nq] - gq[i]).max() == 0.0
     rng = np.random.default_rng(9)
     obs_o = np.zeros(56); rew_o = C.c_double()
-    for t in range(6):
+    ndone = 0
+    for t in range(6 if term_mode == 0 else 14):
         scale = 1.0 if ctrl_mode == 0 else 1.0
         act = common.f32(rng.uniform(-0.5, 0.5, (n, 28)) * scale)
         # identical inputs for both: copy the GPU state (fp32) into the oracle envs each step
@@ -196,8 +198,11 @@ def test_env_step_rewards_pd_and_reset(ctx, reward_mode, ctrl_mode):
             zc = e.d.com[2] if not od else None
             assert abs(rew_o.value - rew[i]) < 2e-5, (t, i, rew_o.value, rew[i])
             assert bool(od) == bool(done[i]), (t, i)
+            ndone += int(od)
             assert e.idx_curr == int(sim.idx_curr[i]) and e.idx_init == int(sim.idx_init[i])
             assert np.abs(obs_o - obs[i]).max() < 2e-4 * max(1.0, np.abs(obs_o).max()), (t, i)
+    if term_mode == 1:
+        assert ndone > 0   # spinkick / dance frames put hands or knees on the floor quickly
     sim.close()
 
 
