@@ -360,6 +360,39 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
     } else if (M.reward_mode == 4) {
       if (!bad) rew = reward_imitate(M, S, P, lane, M.clip_start[clip] + idx_curr);
       idx_curr = (idx_curr + 1) % M.clip_len[clip];
+    } else if (M.reward_mode == 2 || M.reward_mode == 3) {
+      // v2 / v1 rewards (dp_env_v2.py:116-183, dp_env_v1.py:82-152): frame advances first; the
+      // control cost is on the raw action
+      idx_curr = (idx_curr + 1) % M.clip_len[clip];
+      const float* rq = P.mocap_cfg + (size_t)(M.clip_start[clip] + idx_curr) * M.nq;
+      const float* rv = P.mocap_vel + (size_t)(M.clip_start[clip] + idx_curr) * M.nv;
+      float acs = 0.f;
+      if (lane < M.nu) { const float a = action[(size_t)env * M.nu + lane]; acs = a * a; }
+      acs = warp_sum(acs);
+      if (M.reward_mode == 2) {
+        float e = 0.f;
+        for (int i = 3 + lane; i < M.nq; i += 32) e += fabsf(S.qpos[i] - rq[i]);
+        rew = expf(-M.s_err * M.s_pose * warp_sum(e)) - 0.1f * acs;
+      } else {
+        float pe = 0.f;
+        if (lane == 1) {
+          Q4 q0; q0.w = S.qpos[3]; q0.x = S.qpos[4]; q0.y = S.qpos[5]; q0.z = S.qpos[6];
+          Q4 q1; q1.w = rq[3]; q1.x = rq[4]; q1.y = rq[5]; q1.z = rq[6];
+          pe = M.dof_weight[3] * quat_diff_theta(qnormalize(q0), qnormalize(q1));
+        } else if (lane >= 2 && lane < M.nbody) {
+          const int da = M.body_dofadr[lane], nd = M.body_dofnum[lane];
+          if (nd == 3) pe = M.dof_weight[da] * quat_diff_theta(quat_from_xyz(S.qpos[da + 1], S.qpos[da + 2], S.qpos[da + 3]),
+                                                               quat_from_xyz(rq[da + 1], rq[da + 2], rq[da + 3]));
+          else if (nd == 1) pe = M.dof_weight[da] * fabsf(S.qpos[da + 1] - rq[da + 1]);
+        }
+        const float pose = warp_sum(pe) * M.joint_weight_sum;
+        float ve = 0.f;
+        for (int d = lane; d < M.nv; d += 32) if (d >= 3) ve += fabsf(S.qvel[d] - rv[d]);
+        const float vel = warp_sum(ve);
+        const float root = fabsf(S.qpos[0] - rq[0]) + fabsf(S.qpos[1] - rq[1]) + fabsf(S.qpos[2] - rq[2]);
+        rew = M.w_pose * expf(-M.s_err * M.s_pose * pose) + M.w_vel * expf(-M.s_err * M.s_vel * vel) +
+              M.w_root * expf(-M.s_err * M.s_root * root) - 0.1f * acs;
+      }
     }
     if (bad) rew = 0.f;
     // termination (dp_env_v3.py:134-139) on the CoM height of the last stage evaluation
@@ -638,12 +671,13 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
   S.nee = m->nee;
   for (int e = 0; e < m->nee; e++) { S.ee_body[e] = m->ee_body[e]; for (int k = 0; k < 3; k++) S.ee_pos[e][k] = (float)m->ee_pos[e][k]; }
   S.ctrl_mode = c->ctrl_mode; S.reward_mode = c->reward_mode; S.reset_mode = c->reset_mode; S.auto_reset = c->auto_reset;
+  S.joint_weight_sum = (float)c->joint_weight_sum;
   S.term_mode = c->term_mode; S.fall_body_mask = c->fall_body_mask;
   S.z_min = (float)c->z_min; S.z_max = (float)c->z_max; S.reset_noise = (float)c->reset_noise; S.pd_dt = (float)m->timestep;
   S.w_pose = (float)c->w_pose; S.w_vel = (float)c->w_vel; S.w_ee = (float)c->w_end_eff; S.w_root = (float)c->w_root; S.w_com = (float)c->w_com;
   S.s_pose = (float)c->s_pose; S.s_vel = (float)c->s_vel; S.s_ee = (float)c->s_end_eff; S.s_root = (float)c->s_root; S.s_com = (float)c->s_com;
   S.s_err = (float)c->s_err;
-  if (c->reward_mode != 0 && c->reward_mode != 1 && c->reward_mode != 4) { why = "reward_mode must be 0, 1 or 4"; return DMB_ERR_ARG; }
+  if (c->reward_mode < 0 || c->reward_mode > 4) { why = "reward_mode must be 0..4"; return DMB_ERR_ARG; }
   if (c->ctrl_mode < 0 || c->ctrl_mode > 2) { why = "ctrl_mode must be 0, 1 or 2"; return DMB_ERR_ARG; }
   S.nclip = mc->nclip; S.nframe_total = mc->nframe_total;
   S.ngroups = 1;

@@ -68,6 +68,7 @@ struct ModelS {
   int ctrl_mode, reward_mode, reset_mode, auto_reset;
   int term_mode; unsigned fall_body_mask; int pad_t0, pad_t1;
   float z_min, z_max, reset_noise, pd_dt;
+  float joint_weight_sum, pad_w0, pad_w1, pad_w2;
   float w_pose, w_vel, w_ee, w_root, w_com, s_pose, s_vel, s_ee, s_root, s_com, s_err, pad_g;
   // reference pose
   float qpos0[NQC];

@@ -66,7 +66,7 @@ class DmbConfig(C.Structure):
     _fields_ = [
         ("ctrl_mode", i32), ("reward_mode", i32), ("reset_mode", i32), ("auto_reset", i32),
         ("term_mode", i32), ("fall_body_mask", C.c_uint32),
-        ("z_min", f64), ("z_max", f64), ("reset_noise", f64),
+        ("z_min", f64), ("z_max", f64), ("reset_noise", f64), ("joint_weight_sum", f64),
         ("w_pose", f64), ("w_vel", f64), ("w_end_eff", f64), ("w_root", f64), ("w_com", f64),
         ("s_pose", f64), ("s_vel", f64), ("s_end_eff", f64), ("s_root", f64), ("s_com", f64), ("s_err", f64),
     ]
@@ -138,6 +138,7 @@ def default_config(**kw) -> DmbConfig:
     # DeepMimic walk args: every body except the two ankles (bodies 10 and 13 of dp_env_v3.xml) is a fall contact
     c.fall_body_mask = sum(1 << b for b in range(1, 14) if b not in (10, 13))
     c.z_min, c.z_max, c.reset_noise = 0.7, 2.0, 0.01
+    c.joint_weight_sum = float(sum(JOINT_WEIGHT.values()))
     c.w_pose, c.w_vel, c.w_end_eff, c.w_root, c.w_com = 0.5, 0.05, 0.15, 0.2, 0.1
     c.s_pose, c.s_vel, c.s_end_eff, c.s_root, c.s_com, c.s_err = 2.0, 0.1, 40.0, 5.0, 10.0, 1.0
     for k, v in kw.items():

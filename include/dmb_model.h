@@ -89,6 +89,8 @@ typedef struct dmb_config {
   int32_t ctrl_mode;   /* 0: action is motor ctrl (dp_env_v3.py:112); 1: PD "reference intent"
                           (mujoco_interface.py:97-107); 2: plain PD  kp*(a-q) - kd*qvel */
   int32_t reward_mode; /* 0: 1.0 (dp_env_v3.py:117); 1: exp(-L1) (dp_env_v3.py:89-104);
+                          2: v2 pose reward - 0.1|a|^2 (dp_env_v2.py:116-183); 3: v1 3-term reward
+                          - 0.1|a|^2 (dp_env_v1.py:82-152, mujoco_interface.py:169-210);
                           4: 5-term DeepMimic (code.md:979-1146) */
   int32_t reset_mode;  /* 0: mocap RSI (dp_env_v3.py:148-156); 1: init pose + U(-.01,.01) (158-164) */
   int32_t auto_reset;  /* 1: done envs are re-initialised inside step (vec_env semantics) */
@@ -97,6 +99,7 @@ typedef struct dmb_config {
   uint32_t fall_body_mask; /* bit b set: a floor contact of body b ends the episode (all but the ankles) */
   double z_min, z_max; /* CoM-height termination band (dp_env_v3.py:134-139): 0.7, 2.0 */
   double reset_noise;  /* 0.01 */
+  double joint_weight_sum; /* sum of the raw DeepMimic joint weights (mocap_util.py:26-29): 4.8 */
   double w_pose, w_vel, w_end_eff, w_root, w_com;          /* dp_env_v3.py:42-46 */
   double s_pose, s_vel, s_end_eff, s_root, s_com, s_err;   /* dp_env_v3.py:48-53 */
 } dmb_config_t;

@@ -1126,6 +1126,35 @@ int dmo_env_step(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_
   } else if (cfg->reward_mode == 4) {
     rew = reward_imitate(m, cfg, mc, e);
     e->idx_curr = (e->idx_curr + 1) % mc->clip_len[e->clip];
+  } else if (cfg->reward_mode == 2 || cfg->reward_mode == 3) {
+    /* v2 / v1 rewards: the frame counter advances before the reward is evaluated
+     * (dp_env_v2.py:174-183, dp_env_v1.py:143-152); control cost on the raw action */
+    e->idx_curr = (e->idx_curr + 1) % mc->clip_len[e->clip];
+    size_t f = (size_t)(mc->clip_start[e->clip] + e->idx_curr);
+    double rq[DMB_MAX_Q], rv[DMB_MAX_DOF], acs = 0;
+    for (int i = 0; i < m->nq; i++) rq[i] = (double)(float)mc->data_config[f*m->nq + i];
+    for (int i = 0; i < m->nv; i++) rv[i] = (double)(float)mc->data_vel[f*m->nv + i];
+    for (int u = 0; u < m->nu; u++) acs += action[u]*action[u];
+    if (cfg->reward_mode == 2) { /* exp(-scale_err*scale_pose*|qpos[3:] - ref[3:]|_1) */
+      double err = 0;
+      for (int i = 3; i < m->nq; i++) err += fabs(d->qpos[i] - rq[i]);
+      rew = exp(-cfg->s_err*cfg->s_pose*err) - 0.1*acs;
+    } else { /* v1: weighted joint angles (root included), L1 velocity, L1 root position */
+      double pose = 0, vel = 0, root = 0;
+      double q0[4] = {d->qpos[3], d->qpos[4], d->qpos[5], d->qpos[6]}, q1[4] = {rq[3], rq[4], rq[5], rq[6]};
+      normalize4(q0); normalize4(q1);
+      pose += m->dof_weight[3]*cfg->joint_weight_sum*quat_diff_theta(q0, q1);
+      for (int b = 2; b < m->nbody; b++) {
+        int da = m->body_dofadr[b], nd = m->body_dofnum[b];
+        double w = m->dof_weight[da]*cfg->joint_weight_sum;
+        if (nd == 3) { double a[4], c[4]; quat_from_xyz(a, d->qpos + da + 1); quat_from_xyz(c, rq + da + 1); pose += w*quat_diff_theta(a, c); }
+        else if (nd == 1) pose += w*fabs(d->qpos[da + 1] - rq[da + 1]);
+      }
+      for (int i = 3; i < m->nv; i++) vel += fabs(d->qvel[i] - rv[i]);
+      for (int i = 0; i < 3; i++) root += fabs(d->qpos[i] - rq[i]);
+      rew = cfg->w_pose*exp(-cfg->s_err*cfg->s_pose*pose) + cfg->w_vel*exp(-cfg->s_err*cfg->s_vel*vel) +
+            cfg->w_root*exp(-cfg->s_err*cfg->s_root*root) - 0.1*acs;
+    }
   }
   if (bad) rew = 0;
   int done = bad || zc < cfg->z_min || zc > cfg->z_max;

@@ -159,7 +159,7 @@ def _env_pair(po, reward_mode, ctrl_mode, motions=("walk",), n=32, seed=5, auto_
     return sim, cfg, mcs, keep, clip_ids
 
 
-@pytest.mark.parametrize("reward_mode,ctrl_mode,term_mode", [(0, 0, 0), (1, 0, 0), (4, 0, 0), (4, 1, 0), (1, 2, 0), (4, 0, 1)])
+@pytest.mark.parametrize("reward_mode,ctrl_mode,term_mode", [(0, 0, 0), (1, 0, 0), (2, 0, 0), (3, 0, 0), (4, 0, 0), (4, 1, 0), (1, 2, 0), (4, 0, 1)])
 def test_env_step_rewards_pd_and_reset(ctx, reward_mode, ctrl_mode, term_mode):
     """Full env step (PD -> RK4 -> reward -> done -> auto reset) for a few consecutive steps vs the
     oracle env; RSI frame indices must be bit-identical (same Philox stream)."""
