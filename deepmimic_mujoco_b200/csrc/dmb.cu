@@ -859,3 +859,5 @@ int dmb_launch_info(dmb_handle_t h, int32_t* grid, int32_t* block, int32_t* smem
 }
 
 }  // extern "C"
+
+#include "dmb_policy.cuh"

@@ -37,7 +37,7 @@ class DmbError(RuntimeError):
 def build_library(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/dmb.cu for sm_100a into the in-tree libdmb200.so (nvcc cross-compiles without a GPU)."""
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
-    srcs += [os.path.join(_PKG, "..", "include", f) for f in ("dmb.h", "dmb_model.h")]
+    srcs += [os.path.join(_PKG, "..", "include", f) for f in ("dmb.h", "dmb_model.h", "dmb_policy.h")]
     if not force and os.path.exists(LIB_PATH) and all(
             os.path.getmtime(s) <= os.path.getmtime(LIB_PATH) for s in srcs if os.path.exists(s)):
         return LIB_PATH
@@ -50,6 +50,7 @@ _lib: Optional[C.CDLL] = None
 
 EXPORTS = ("dmb_version", "dmb_sizeof_model", "dmb_sizeof_config", "dmb_sizeof_mocap", "dmb_sizeof_tile", "dmb_create", "dmb_destroy", "dmb_reset", "dmb_step", "dmb_get_obs", "dmb_forward_debug",
            "dmb_debug_stride", "dmb_debug_offset", "dmb_launch_info", "dmb_last_error")
+POLICY_EXPORTS = ("dmb_policy_act",)   # include/dmb_policy.h
 
 
 def load() -> C.CDLL:

@@ -1,0 +1,69 @@
+"""Device-resident rollout segments + GAE (SURVEY.md section 8(f) rank 1/2 entry points).
+
+Batched restatement of /root/reference/src/trpo.py:27-80 ``traj_segment_generator`` (a horizon of T steps
+per env instead of one env, history kept in CUDA tensors instead of numpy arrays, auto-reset inside the
+env step instead of the reset()/reset_model_init() pair) and of trpo.py:83-94 ``add_vtarg_and_adv``.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from .env import DPVecEnv
+from .policy import MlpPolicy
+
+
+def add_vtarg_and_adv(seg: Dict[str, torch.Tensor], gamma: float, lam: float) -> None:
+    """GAE(lambda) over [T, N] tensors; seg['new'][t] = 1 if step t starts a new episode (trpo.py:83-94)."""
+    rew, vpred, new = seg["rew"], seg["vpred"], seg["new"]
+    T = rew.shape[0]
+    nextv = torch.cat([vpred[1:], seg["nextvpred"][None]], dim=0)
+    nextnew = torch.cat([new[1:], torch.zeros_like(new[:1])], dim=0)
+    adv = torch.empty_like(rew)
+    last = torch.zeros_like(rew[0])
+    for t in reversed(range(T)):
+        nonterminal = 1.0 - nextnew[t]
+        delta = rew[t] + gamma * nextv[t] * nonterminal - vpred[t]
+        last = delta + gamma * lam * nonterminal * last
+        adv[t] = last
+    seg["adv"] = adv
+    seg["tdlamret"] = adv + vpred
+
+
+class SegmentGenerator:
+    """Yields {"ob","ac","rew","vpred","new","nextvpred","ep_rets","ep_lens"} with leading dims [T, N]."""
+
+    def __init__(self, pi: MlpPolicy, env: DPVecEnv, horizon: int, stochastic: bool = True):
+        self.pi, self.env, self.T, self.stochastic = pi, env, horizon, stochastic
+        N, d = env.num_envs, env.sim.device
+        self.ob = torch.zeros(horizon, N, env.sim.obs_dim, device=d)
+        self.ac = torch.zeros(horizon, N, env.sim.nu, device=d)
+        self.rew = torch.zeros(horizon, N, device=d)
+        self.vpred = torch.zeros(horizon, N, device=d)
+        self.new = torch.zeros(horizon, N, device=d)
+        self.cur_ob = env.reset().clone()
+        self.cur_new = torch.ones(N, device=d)      # trpo.py:31 `new = True`
+
+    def __iter__(self):
+        return self
+
+    def __next__(self) -> Dict[str, torch.Tensor]:
+        ep_rets, ep_lens = [], []
+        for t in range(self.T):
+            self.ob[t].copy_(self.cur_ob)
+            self.new[t].copy_(self.cur_new)
+            self.pi.act(self.stochastic, self.cur_ob, out_ac=self.ac[t], out_vpred=self.vpred[t])
+            obs, rew, done, info = self.env.step(self.ac[t])
+            self.rew[t].copy_(rew)
+            self.cur_ob.copy_(obs)
+            self.cur_new.copy_(done.float())
+            d = done.bool()
+            ep_rets.append(info["episode_return"][d].clone())
+            ep_lens.append(info["episode_length"][d].clone())
+        nextvpred = torch.empty(self.env.num_envs, device=self.ob.device)
+        tmp_ac = torch.empty(self.env.num_envs, self.env.sim.nu, device=self.ob.device)
+        self.pi.act(self.stochastic, self.cur_ob, out_ac=tmp_ac, out_vpred=nextvpred)
+        nextvpred = nextvpred * (1.0 - self.cur_new)   # trpo.py:56
+        return {"ob": self.ob, "ac": self.ac, "rew": self.rew, "vpred": self.vpred, "new": self.new,
+                "nextvpred": nextvpred, "ep_rets": torch.cat(ep_rets), "ep_lens": torch.cat(ep_lens)}
