@@ -460,6 +460,23 @@ __device__ int raw_capsule_capsule(RawCon* c, float margin, V3 pos1, const float
 __device__ int raw_box_box(RawCon* c, float margin, V3 pos1, const float* mat1, V3 s1, V3 pos2, const float* mat2,
                            V3 s2) {
   int n = 0;
+  // exact early-out on the 6 face axes (feet are almost always inside each other's bounding sphere)
+  for (int pass = 0; pass < 2; pass++) {
+    const V3 pa = pass == 0 ? pos1 : pos2, pb = pass == 0 ? pos2 : pos1;
+    const float* ma = pass == 0 ? mat1 : mat2;
+    const float* mb = pass == 0 ? mat2 : mat1;
+    const V3 sa = pass == 0 ? s1 : s2, sb = pass == 0 ? s2 : s1;
+    const V3 dc = pb - pa;
+    const float sak[3] = {sa.x, sa.y, sa.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const V3 ax = v3(ma[k], ma[3 + k], ma[6 + k]);
+      const float r = sb.x * fabsf(ax.x * mb[0] + ax.y * mb[3] + ax.z * mb[6]) +
+                      sb.y * fabsf(ax.x * mb[1] + ax.y * mb[4] + ax.z * mb[7]) +
+                      sb.z * fabsf(ax.x * mb[2] + ax.y * mb[5] + ax.z * mb[8]);
+      if (fabsf(dot(dc, ax)) - sak[k] - r > margin) return 0;
+    }
+  }
   for (int pass = 0; pass < 2 && n < 4; pass++) {
     const V3 vp = pass == 0 ? pos2 : pos1;
     const float* vm = pass == 0 ? mat2 : mat1;

@@ -199,11 +199,19 @@ class DPEnv(_EnvBase):
     def _get_obs(self):
         return self._sim.get_obs()[0].double().cpu().numpy()
 
+    def _forward(self, ctrl: torch.Tensor):
+        """gym ``MujocoEnv.set_state`` ends with ``sim.forward()``: one mj_forward that leaves
+        qacc_warmstart = qacc for the next step (the batched auto-reset path starts from 0 instead)."""
+        self._sim.forward_debug(ctrl)
+
     def set_state(self, qpos, qvel):
         self._sim.set_state(np.asarray(qpos)[None], np.asarray(qvel)[None])
+        self._forward(self._act)                                  # data.ctrl still holds the last action
 
     def reset(self):
         ob = self._sim.reset(mode=0)[0].double().cpu().numpy()   # reset_model(): mocap RSI
+        self._act.zero_()                                         # sim.reset() clears data.ctrl
+        self._forward(self._act)
         self._needs_reset = False
         return ob
 

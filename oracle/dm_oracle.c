@@ -470,6 +470,19 @@ static int raw_capsule_capsule(rawcon_t* c, double margin, const double* pos1, c
 static int raw_box_box(rawcon_t* c, double margin, const double* pos1, const double* mat1, const double* size1,
                        const double* pos2, const double* mat2, const double* size2) {
   int n = 0;
+  /* exact early-out: if the boxes are separated by more than the margin along a face axis of either
+   * box, no vertex of one can be within the margin of the other */
+  for (int pass = 0; pass < 2; pass++) {
+    const double *pa = pass == 0 ? pos1 : pos2, *ma = pass == 0 ? mat1 : mat2, *sa = pass == 0 ? size1 : size2;
+    const double *pb = pass == 0 ? pos2 : pos1, *mb = pass == 0 ? mat2 : mat1, *sb = pass == 0 ? size2 : size1;
+    double dc[3] = {pb[0] - pa[0], pb[1] - pa[1], pb[2] - pa[2]};
+    for (int k = 0; k < 3; k++) {
+      double ax[3] = {ma[k], ma[3 + k], ma[6 + k]};
+      double r = 0;
+      for (int j = 0; j < 3; j++) r += sb[j]*fabs(ax[0]*mb[j] + ax[1]*mb[3 + j] + ax[2]*mb[6 + j]);
+      if (fabs(dot3(dc, ax)) - sa[k] - r > margin) return 0;
+    }
+  }
   for (int pass = 0; pass < 2 && n < 4; pass++) {
     const double* vp = pass == 0 ? pos2 : pos1;   /* owner of the vertices */
     const double* vm = pass == 0 ? mat2 : mat1;
