@@ -919,15 +919,19 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
     // cost decrease  -(0.5 delta^2 AR_ii + delta res_i)  is summed once per sweep
     float dm0 = 0.f, rm0 = 0.f, dm1 = 0.f, rm1 = 0.f;
     // branch-free row updates; the AR column of row i+1 is loaded while row i is in flight, so the
-    // serial chain per row is FFMA -> FMNMX -> FADD -> SHFL -> FFMA
-    int tri_i = 0;
-    float acol0 = a0 ? S.AR[t0] : 0.f;                       // column 0: AR[r0][0]
-    float acol1 = (HI && a1) ? S.AR[t1] : 0.f;
+    // serial chain per row is FFMA -> FMNMX -> FADD -> SHFL -> FFMA.  Column i of the packed
+    // triangle for lane-row r is AR[tri(r) + i] (i <= r) or AR[tri(i) + r] (i > r): the index moves
+    // by 1 while i < r and by i + 1 afterwards.  Loads are unpredicated (indices past the last row
+    // stay inside the tile; lanes without a row never own an update).
+    int idx0 = t0, idx1 = t1;
+    float acol0 = S.AR[idx0];
+    float acol1 = HI ? S.AR[a1 ? idx1 : 0] : 0.f;
+#pragma unroll 2
     for (int i = 0; i < nlo; i++) {
-      const int in = i + 1;                                   // next column (clamped reads stay in range)
-      const int tri_n = tri_i + in;
-      const float an0 = (a0 && in < nefc) ? S.AR[r0 >= in ? t0 + in : tri_n + r0] : 0.f;
-      const float an1 = (HI && a1 && in < nefc) ? S.AR[r1 >= in ? t1 + in : tri_n + r1] : 0.f;
+      idx0 += (i < r0) ? 1 : i + 1;
+      const float an0 = S.AR[idx0];
+      float an1 = 0.f;
+      if (HI) { idx1 += (i < r1) ? 1 : i + 1; an1 = S.AR[a1 ? idx1 : 0]; }
       const float fnew = fmaxf(0.f, f0 - res0 * inv0);
       const float mine = fnew - f0;
       const float delta = __shfl_sync(DMB_FULL, mine, i);
@@ -935,14 +939,13 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
       res0 = fmaf(acol0, delta, res0);
       if (HI) res1 = fmaf(acol1, delta, res1);
       acol0 = an0; acol1 = an1;
-      tri_i = tri_n;
     }
     if (HI) {
       for (int i = 32; i < nefc; i++) {
-        const int in = i + 1;
-        const int tri_n = tri_i + in;
-        const float an0 = (a0 && in < nefc) ? S.AR[tri_n + r0] : 0.f;   // in > 32 > r0
-        const float an1 = (a1 && in < nefc) ? S.AR[r1 >= in ? t1 + in : tri_n + r1] : 0.f;
+        idx0 += i + 1;                                          // i >= 32 > r0
+        idx1 += (i < r1) ? 1 : i + 1;
+        const float an0 = S.AR[idx0 < NTRI ? idx0 : 0];
+        const float an1 = S.AR[(a1 && idx1 < NTRI) ? idx1 : 0];
         const float fnew = fmaxf(0.f, f1 - res1 * inv1);
         const float mine = fnew - f1;
         const float delta = __shfl_sync(DMB_FULL, mine, i - 32);
@@ -950,7 +953,6 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
         res0 = fmaf(acol0, delta, res0);
         res1 = fmaf(acol1, delta, res1);
         acol0 = an0; acol1 = an1;
-        tri_i = tri_n;
       }
     }
     iter++;
