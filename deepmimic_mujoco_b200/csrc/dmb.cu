@@ -433,8 +433,13 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
 // Counting sort of the envs by the constraint work of their previous step (256 buckets,
 // heaviest first) + reset of the scheduler counter.  One CTA; order inside a bucket is arbitrary
 // (envs are independent, so results do not depend on the schedule).
-__global__ void k_order(const int* __restrict__ cost, int* __restrict__ order, int* counter, int N) {
+__global__ void k_order(const int* __restrict__ cost, int* __restrict__ order, int* counter, int N, int identity) {
   __shared__ int hist[256], cursor[256];
+  if (identity) {  // DMB_NO_SORT=1: schedule in index order (experiments)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) order[i] = i;
+    if (threadIdx.x == 0) *counter = 0;
+    return;
+  }
   if (threadIdx.x < 256) hist[threadIdx.x] = 0;
   __syncthreads();
   for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&hist[min(255, max(0, cost[i]))], 1);
@@ -541,6 +546,7 @@ struct dmb_handle_s {
   int grid = 0, block = 0, smem = 0, envs_per_cta = 0;
   int nu = 0, obs_dim = 0;
   int lockstep = 1;
+  int no_sort = 0;
   std::string err;
 };
 
@@ -772,6 +778,7 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
     if (W > wreg) W = wreg;
   }
   if (const char* lenv = getenv("DMB_LOCKSTEP")) h->lockstep = atoi(lenv) != 0;
+  if (const char* ns = getenv("DMB_NO_SORT")) h->no_sort = atoi(ns) != 0;
   if (const char* wenv = getenv("DMB_ENVS_PER_CTA")) { int w = atoi(wenv); if (w >= 1 && w < W) W = w; }
   if (W < 1) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, "not enough shared memory for one env tile"); }
   {  // lockstep groups: DMB_GROUPS (default 1); must divide the warps of a CTA
@@ -821,7 +828,7 @@ int dmb_step(dmb_handle_t h, const dmb_state_t* st, const float* action, const d
   if (!h) return DMB_ERR_ARG;
   if (!state_ok(st) || !action || !out || !out->obs || !out->reward || !out->done) return fail(h, DMB_ERR_ARG, "dmb_step: bad argument");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  k_order<<<1, 1024, 0, (cudaStream_t)stream>>>(h->d_cost, h->d_order, h->d_counter, h->num_envs);
+  k_order<<<1, 1024, 0, (cudaStream_t)stream>>>(h->d_cost, h->d_order, h->d_counter, h->num_envs, h->no_sort);
   if (h->lockstep) k_step<true><<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
   else k_step<false><<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
   CUDA_TRY(h, cudaGetLastError());

@@ -1001,7 +1001,13 @@ __device__ __noinline__ void solve_constraints(const ModelS& M, EnvS& S, int lan
     if (a1) S.e_f[r1] = f1;
     __syncwarp();
   }
-  if (lane == 0) { S.iter = iter; S.cost += M.cost_mode == 1 ? nefc * 16 : (M.cost_mode == 2 ? nefc * (16 + iter) : nefc * iter); }
+  if (lane == 0) {
+    S.iter = iter;
+    // scheduler key (see k_order): modes 0-2 accumulate over the RK stages, 3-4 keep the last stage only
+    if (M.cost_mode == 3) S.cost = 4 * nefc * iter;
+    else if (M.cost_mode == 4) S.cost = 4 * nefc * (8 + iter);
+    else S.cost += M.cost_mode == 1 ? nefc * 16 : (M.cost_mode == 2 ? nefc * (16 + iter) : nefc * iter);
+  }
   // t = y_s + sum_r Y_r f_r  (lane = dof), then qacc = L^-1 D^-1/2 t in registers
   float tlo = lane < M.nv ? S.ys[lane] : 0.f, thi = lane + 32 < M.nv ? S.ys[lane + 32] : 0.f;
   for (int r = 0; r < nefc; r++) {
