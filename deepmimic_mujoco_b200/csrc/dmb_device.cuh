@@ -964,6 +964,43 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
   return iter;
 }
 
+// nefc <= 32 (every env of the benchmark rollout): this lane's column of AR (= its row, AR is
+// symmetric) is held in 32 registers, loaded once per solve; a sweep is then a fully unrolled chain of
+// row updates with no shared-memory access and no index arithmetic.  The increment is computed as
+// max(-f, -res/AR_ii) (= max(0, f - res/AR_ii) - f without the extra dependent subtraction), so the
+// serial chain per row is FMUL -> FMNMX -> SHFL -> FFMA.
+#ifndef DMB_PGS_REG
+#define DMB_PGS_REG 1
+#endif
+__device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, EnvS& S, int lane, int nefc, float& f0, float& res0) {
+  const int r0 = lane, t0 = tri(r0);
+  const bool a0 = r0 < nefc;
+  float acol[32];
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    const int idx = i <= r0 ? t0 + i : tri(i) + r0;
+    acol[i] = (a0 && i < nefc) ? S.AR[idx] : 0.f;
+  }
+  const float d0 = a0 ? S.AR[t0 + r0] : 1.f;
+  const float ninv0 = -1.0f / d0;
+  int iter = 0;
+  while (iter < M.iterations) {
+    float dm0 = 0.f, rm0 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+      if (i >= nefc) break;
+      const float mine = fmaxf(-f0, res0 * ninv0);
+      const float delta = __shfl_sync(DMB_FULL, mine, i);
+      if (lane == i) { dm0 = mine; rm0 = res0; f0 += mine; }
+      res0 = fmaf(acol[i], delta, res0);
+    }
+    iter++;
+    const float imp = warp_sum(-(dm0 * (0.5f * dm0 * d0 + rm0))) * M.pgs_scale;
+    if (imp < M.tolerance) break;
+  }
+  return iter;
+}
+
 // ------------------------------------------------------------------------------------------
 // mj_fwdConstraint: warmstart + PGS on the dual, then qacc = L^-1 D^-1/2 (y_s + Y' f).
 // ------------------------------------------------------------------------------------------
@@ -995,8 +1032,13 @@ __device__ __noinline__ void solve_constraints(const ModelS& M, EnvS& S, int lan
     float cost = f0 * 0.5f * (res0 + b0) + f1 * 0.5f * (res1 + b1);
     cost = warp_sum(cost);
     if (cost > 0.f) { f0 = 0.f; f1 = 0.f; res0 = b0; res1 = b1; }
+#if DMB_PGS_REG
+    iter = nefc > 32 ? pgs_sweeps<true>(M, S, lane, nefc, f0, f1, res0, res1)
+                     : pgs_sweeps_reg(M, S, lane, nefc, f0, res0);
+#else
     iter = nefc > 32 ? pgs_sweeps<true>(M, S, lane, nefc, f0, f1, res0, res1)
                      : pgs_sweeps<false>(M, S, lane, nefc, f0, f1, res0, res1);
+#endif
     if (a0) S.e_f[r0] = f0;
     if (a1) S.e_f[r1] = f1;
     __syncwarp();

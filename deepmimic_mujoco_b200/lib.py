@@ -10,7 +10,8 @@ from typing import Optional
 from .model_blob import DmbConfig, DmbMocap, DmbModel
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libdmb200.so")
+# DMB_LIB selects another in-tree build of the same sources (A/B kernel variants for measurements)
+LIB_PATH = os.environ.get("DMB_LIB") or os.path.join(_PKG, "libdmb200.so")
 CSRC = os.path.join(_PKG, "csrc")
 QSTRIDE = 36
 VSTRIDE = 36
