@@ -63,6 +63,184 @@ __device__ __forceinline__ void write_obs(const ModelS& M, const EnvS& S, float*
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// kinematic features of the pose in (S.qpos, S.qvel), shared by the imitation reward and the
+// DeepMimic state
+// ---------------------------------------------------------------------------------------
+// fresh kinematics + CoM frame + per-dof spatial velocity terms cdof[d] * qvel[d] (in buf6)
+__device__ __noinline__ void kin_vel_prep(const ModelS& M, EnvS& S, int lane) {
+  kinematics(M, S, lane);
+  com_pos(M, S, lane);
+  for (int d = lane; d < M.nv; d += 32) {
+    const float qv = S.qvel[d];
+#pragma unroll
+    for (int k = 0; k < 6; k++) S.u.a.buf6[6 * d + k] = S.cdof[6 * d + k] * qv;
+  }
+  __syncwarp();
+}
+// spatial velocity [omega; v at the c-frame origin] of body b: sum over its dof chain
+__device__ __forceinline__ void body_cvel(const ModelS& M, const EnvS& S, int b, float* v) {
+#pragma unroll
+  for (int k = 0; k < 6; k++) v[k] = 0.f;
+  unsigned long long mk = M.body_dofmask[b];
+  while (mk) {
+    const int d = __ffsll((long long)mk) - 1;
+    mk &= mk - 1;
+#pragma unroll
+    for (int k = 0; k < 6; k++) v[k] += S.u.a.buf6[6 * d + k];
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// time-based mocap phase with interpolation (phase_mode 1); fp32 restatement of
+// oracle/dm_oracle.c quat_slerp / euler_rxyz_from_quat / dmo_mocap_sample
+// ---------------------------------------------------------------------------------------
+// transformations.quaternion_slerp (shortest path).  The angle comes from the chord |q1 - q0| =
+// 2 sin(theta/2), which keeps its relative accuracy in fp32 where acos(dot) does not; below
+// 0.01 rad the sine weights equal the linear ones to 2e-8 rad.
+__device__ __forceinline__ Q4 quat_slerp(Q4 q0, Q4 q1, float f) {
+  q0 = qnormalize(q0); q1 = qnormalize(q1);
+  const float d = q0.w * q1.w + q0.x * q1.x + q0.y * q1.y + q0.z * q1.z;
+  if (d < 0.f) { q1.w = -q1.w; q1.x = -q1.x; q1.y = -q1.y; q1.z = -q1.z; }
+  const float dw = q1.w - q0.w, dx = q1.x - q0.x, dy = q1.y - q0.y, dz = q1.z - q0.z;
+  const float c2 = dw * dw + dx * dx + dy * dy + dz * dz;
+  float w0 = 1.f - f, w1 = f;
+  if (c2 >= 1e-4f) {
+    const float th = 2.f * asinf(fminf(1.f, 0.5f * sqrtf(c2)));
+    const float isin = 1.f / sinf(th);
+    w0 = sinf((1.f - f) * th) * isin;
+    w1 = sinf(f * th) * isin;
+  }
+  Q4 r;
+  r.w = w0 * q0.w + w1 * q1.w; r.x = w0 * q0.x + w1 * q1.x; r.y = w0 * q0.y + w1 * q1.y; r.z = w0 * q0.z + w1 * q1.z;
+  return qnormalize(r);
+}
+// transformations.euler_from_quaternion(q, 'rxyz'): angles of R = Rx(a) Ry(b) Rz(c)
+__device__ __forceinline__ void euler_rxyz_from_quat(Q4 q, float& a, float& b, float& c) {
+  q = qnormalize(q);
+  const float s = 1.41421356237f;
+  const float w = q.w * s, x = q.x * s, y = q.y * s, z = q.z * s;
+  const float R00 = 1.f - y * y - z * z, R01 = x * y - z * w, R02 = x * z + y * w;
+  const float R10 = x * y + z * w, R11 = 1.f - x * x - z * z, R12 = y * z - x * w, R22 = 1.f - x * x - y * y;
+  const float cy = sqrtf(R22 * R22 + R12 * R12);
+  if (cy > 4.8e-7f) { a = atan2f(-R12, R22); b = atan2f(R02, cy); c = atan2f(-R01, R00); }
+  else { a = 0.f; b = atan2f(R02, cy); c = atan2f(R10, R11); }
+}
+// quaternion of a hinge triple, R = Rx(a) Ry(b) Rz(c)
+__device__ __forceinline__ Q4 quat_from_xyz(float a, float b, float c) {
+  float sa, ca, sb, cb, sc, cc;
+  sincosf(0.5f * a, &sa, &ca); sincosf(0.5f * b, &sb, &cb); sincosf(0.5f * c, &sc, &cc);
+  Q4 qx; qx.w = ca; qx.x = sa; qx.y = 0.f; qx.z = 0.f;
+  Q4 qy; qy.w = cb; qy.x = 0.f; qy.y = sb; qy.z = 0.f;
+  Q4 qz; qz.w = cc; qz.x = 0.f; qz.y = 0.f; qz.z = sc;
+  return qmul(qmul(qx, qy), qz);
+}
+// frame coordinate u -> cycle, frame interval k, fraction alpha, phase in [0,1); same double
+// arithmetic as the oracle's phase_split (an F-frame clip has F-1 intervals per cycle)
+__device__ __forceinline__ void phase_split(int F, double u, int& cycle, int& k, float& alpha, float& phase) {
+  cycle = 0; k = 0; alpha = 0.f; phase = 0.f;
+  if (F < 2) return;
+  const double c = floor(u / (double)(F - 1));
+  const double uu = u - c * (double)(F - 1);
+  int kk = (int)uu;
+  kk = kk > F - 2 ? F - 2 : (kk < 0 ? 0 : kk);
+  cycle = (int)c; k = kk; alpha = (float)(uu - (double)kk); phase = (float)(uu / (double)(F - 1));
+}
+__device__ __forceinline__ double frame_coord(const ModelS& M, int clip, int idx_init, int steps) {
+  return __dadd_rn((double)idx_init, __dmul_rn((double)steps, M.clip_rate[clip]));
+}
+// interpolated reference pose at frame coordinate u into rq[nq] / rv[nv] (shared memory):
+// linear for the root position (+ cycle * last frame's root xy: root-offset accumulation of
+// MocapDM.play, mocap_v2.py:168-182), 1-DoF joints and velocities (lane = coordinate); slerp for the
+// root quaternion and the hinge triples (lane = body).  Returns the frame interval k.
+__device__ __noinline__ int mocap_sample(const ModelS& M, const DevPtrs& P, int clip, double u, int lane, float* rq,
+                                         float* rv) {
+  const int F = M.clip_len[clip], start = M.clip_start[clip];
+  int cycle, k;
+  float a, ph;
+  phase_split(F, u, cycle, k, a, ph);
+  const int k1 = F < 2 ? k : k + 1;
+  const float* c0 = P.mocap_cfg + (size_t)(start + k) * M.nq;
+  const float* c1 = P.mocap_cfg + (size_t)(start + k1) * M.nq;
+  const float* cl = P.mocap_cfg + (size_t)(start + F - 1) * M.nq;
+  const float* v0 = P.mocap_vel + (size_t)(start + k) * M.nv;
+  const float* v1 = P.mocap_vel + (size_t)(start + k1) * M.nv;
+  for (int i = lane; i < M.nq; i += 32) { const float x0 = c0[i]; rq[i] = fmaf(a, c1[i] - x0, x0); }
+  for (int i = lane; i < M.nv; i += 32) { const float x0 = v0[i]; rv[i] = fmaf(a, v1[i] - x0, x0); }
+  __syncwarp();
+  if (lane == 1) {
+    rq[0] += (float)cycle * cl[0];
+    rq[1] += (float)cycle * cl[1];
+    Q4 q0; q0.w = c0[3]; q0.x = c0[4]; q0.y = c0[5]; q0.z = c0[6];
+    Q4 q1; q1.w = c1[3]; q1.x = c1[4]; q1.y = c1[5]; q1.z = c1[6];
+    const Q4 q = quat_slerp(q0, q1, a);
+    rq[3] = q.w; rq[4] = q.x; rq[5] = q.y; rq[6] = q.z;
+  } else if (lane >= 2 && lane < M.nbody && M.body_dofnum[lane] == 3) {
+    const int qa = M.body_dofadr[lane] + 1;
+    const Q4 q = quat_slerp(quat_from_xyz(c0[qa], c0[qa + 1], c0[qa + 2]), quat_from_xyz(c1[qa], c1[qa + 1], c1[qa + 2]), a);
+    euler_rxyz_from_quat(q, rq[qa], rq[qa + 1], rq[qa + 2]);
+  }
+  __syncwarp();
+  return k;
+}
+// phase in [0, 1) reported by the DeepMimic state
+__device__ __forceinline__ float phase_of(const ModelS& M, int clip, int idx_init, int idx_curr, int ep_len) {
+  const int F = M.clip_len[clip];
+  if (M.phase_mode == 1) {
+    int cycle, k;
+    float a, ph;
+    phase_split(F, frame_coord(M, clip, idx_init, ep_len), cycle, k, a, ph);
+    return ph;
+  }
+  return (float)idx_curr / (float)F;
+}
+
+// DeepMimic state (obs_mode 1; cCtController::BuildStatePose / BuildStateVel, code.md:287-504, and
+// record_state, mujoco_env.py:91-124): [phase, root height, npart x (pos 3, quat 4), npart x
+// (lin vel 3, ang vel 3)] in the root heading frame, lane = body part.  The row is staged in the
+// (dead) Delassus tile and written out coalesced.
+__device__ __noinline__ void write_obs_dm(const ModelS& M, EnvS& S, float phase, float* obs, float* rec, int env, int lane) {
+  kin_vel_prep(M, S, lane);
+  float* buf = S.AR;
+  const float* R = &S.u.a.xmat[9];
+  const float heading = atan2f(R[3], R[0]);
+  float sh, ch, shh, chh;
+  sincosf(heading, &sh, &ch);
+  sincosf(0.5f * heading, &shh, &chh);
+  if (lane == 0) { buf[0] = phase; buf[1] = S.u.a.xpos[5]; }
+  if (lane < M.npart) {
+    const int g = M.part_geom[lane], b = M.geom_bodyid[g];
+    const V3 gp = ld3(&S.u.a.xpos[3 * b]) + mat_vec(&S.u.a.xmat[9 * b], ld3(M.geom_pos[g]));
+    const V3 rel = gp - ld3(&S.u.a.xpos[3]);
+    float* o = buf + 2 + 7 * lane;
+    o[0] = ch * rel.x + sh * rel.y; o[1] = -sh * rel.x + ch * rel.y; o[2] = rel.z;
+    Q4 qh; qh.w = chh; qh.x = 0.f; qh.y = 0.f; qh.z = -shh;
+    Q4 qb; qb.w = S.u.a.xquat[4 * b]; qb.x = S.u.a.xquat[4 * b + 1]; qb.y = S.u.a.xquat[4 * b + 2]; qb.z = S.u.a.xquat[4 * b + 3];
+    Q4 q = qmul(qh, qb);
+    const float sg = q.w < 0.f ? -1.f : 1.f;
+    o[3] = sg * q.w; o[4] = sg * q.x; o[5] = sg * q.y; o[6] = sg * q.z;
+    float v[6];
+    body_cvel(M, S, b, v);
+    const V3 vl = v3(v[3], v[4], v[5]) + cross(v3(v[0], v[1], v[2]), gp - ld3(S.com));
+    float* ov = buf + 2 + 7 * M.npart + 6 * lane;
+    ov[0] = ch * vl.x + sh * vl.y; ov[1] = -sh * vl.x + ch * vl.y; ov[2] = vl.z;
+    ov[3] = ch * v[0] + sh * v[1]; ov[4] = -sh * v[0] + ch * v[1]; ov[5] = v[2];
+  }
+  __syncwarp();
+  const int od = M.obs_dim;
+  for (int o = lane; o < od; o += 32) {
+    const float v = buf[o];
+    if (obs) obs[(size_t)env * od + o] = v;
+    if (rec) rec[(size_t)env * (od + 2) + o] = v;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void emit_obs(const ModelS& M, EnvS& S, int clip, int idx_init, int idx_curr, int ep_len,
+                                         float* obs, float* rec, int env, int lane) {
+  if (M.obs_mode == 1) write_obs_dm(M, S, phase_of(M, clip, idx_init, idx_curr, ep_len), obs, rec, env, lane);
+  else write_obs(M, S, obs, rec, env, lane);
+}
+
 // action -> per-dof actuator force (mj_fwdActuation with the ctrl clamp; optional PD)
 __device__ __forceinline__ void set_ctrl(const ModelS& M, EnvS& S, const float* action, int env, int lane) {
   for (int d = lane; d < M.nv; d += 32) S.ctrlf[d] = 0.f;
@@ -149,8 +327,8 @@ __device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bo
 }
 
 // reference-state initialisation (dp_env_v3.py:67-71,148-164); Philox keyed by (seed, env id)
-__device__ void reset_env(const ModelS& M, EnvS& S, const DevPtrs& P, const dmb_state_t& st, int env, int lane,
-                          unsigned long long seed, unsigned first_env_id, int mode) {
+__device__ int reset_env(const ModelS& M, EnvS& S, const DevPtrs& P, const dmb_state_t& st, int env, int lane,
+                         unsigned long long seed, unsigned first_env_id, int mode) {
   const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
   const unsigned eid = first_env_id + (unsigned)env;
   const unsigned rc = st.reset_count[env];
@@ -176,59 +354,34 @@ __device__ void reset_env(const ModelS& M, EnvS& S, const DevPtrs& P, const dmb_
     st.ep_len[env] = 0; st.ep_ret[env] = 0.f;
   }
   __syncwarp();
+  return idx;
 }
 
-// quaternion of a hinge triple, R = Rx(a) Ry(b) Rz(c)
-__device__ __forceinline__ Q4 quat_from_xyz(float a, float b, float c) {
-  float sa, ca, sb, cb, sc, cc;
-  sincosf(0.5f * a, &sa, &ca); sincosf(0.5f * b, &sb, &cb); sincosf(0.5f * c, &sc, &cc);
-  Q4 qx; qx.w = ca; qx.x = sa; qx.y = 0.f; qx.z = 0.f;
-  Q4 qy; qy.w = cb; qy.x = 0.f; qy.y = sb; qy.z = 0.f;
-  Q4 qz; qz.w = cc; qz.x = 0.f; qz.y = 0.f; qz.z = sc;
-  return qmul(qmul(qx, qy), qz);
-}
 __device__ __forceinline__ float quat_diff_theta(Q4 a, Q4 b) {
   Q4 ac; ac.w = a.w; ac.x = -a.x; ac.y = -a.y; ac.z = -a.z;
   const Q4 qd = qmul(ac, b);
   return 2.f * atan2f(sqrtf(qd.x * qd.x + qd.y * qd.y + qd.z * qd.z), fabsf(qd.w));
 }
 
-// 5-term DeepMimic imitation reward (code.md:979-1146 adapted to the hinge model; weights and
-// scales from dp_env_v3.py:42-53).  Needs fresh kinematics at the post-step state; the
-// reference pose's end-effector / CoM-velocity features are tabulated per frame (ref_aux).
-__device__ float reward_imitate(const ModelS& M, EnvS& S, const DevPtrs& P, int lane, int frame) {
-  const float* rq = P.mocap_cfg + (size_t)frame * M.nq;
-  const float* rv = P.mocap_vel + (size_t)frame * M.nv;
-  const float* aux = P.ref_aux + (size_t)frame * DMB_REF_AUX;
-  kinematics(M, S, lane);
-  com_pos(M, S, lane);
-  for (int d = lane; d < M.nv; d += 32) {
-    const float qv = S.qvel[d];
-#pragma unroll
-    for (int k = 0; k < 6; k++) S.u.a.buf6[6 * d + k] = S.cdof[6 * d + k] * qv;
-  }
-  __syncwarp();
+// end-effector points in the root heading frame (lane = end effector) and whole-body CoM velocity
+// (all lanes) of the pose in (S.qpos, S.qvel); runs fresh kinematics
+struct PoseFeat { float ex, ey, ez, vx, vy, vz; };
+__device__ __noinline__ PoseFeat pose_features(const ModelS& M, EnvS& S, int lane) {
+  kin_vel_prep(M, S, lane);
+  PoseFeat out;
   // CoM velocity: sum_b m_b (v_lin + w x (xipos_b - com)) / M
   float px = 0.f, py = 0.f, pz = 0.f;
   if (lane >= 1 && lane < M.nbody) {
     const int b = lane;
-    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    unsigned long long mk = M.body_dofmask[b];
-    while (mk) {
-      const int d = __ffsll((long long)mk) - 1;
-      mk &= mk - 1;
-#pragma unroll
-      for (int k = 0; k < 6; k++) v[k] += S.u.a.buf6[6 * d + k];
-    }
+    float v[6];
+    body_cvel(M, S, b, v);
     const V3 r = ld3(&S.u.a.xipos[3 * b]) - ld3(S.com);
     const V3 vb = v3(v[3], v[4], v[5]) + cross(v3(v[0], v[1], v[2]), r);
     const float ms = M.body_mass[b];
     px = ms * vb.x; py = ms * vb.y; pz = ms * vb.z;
   }
-  const float vcx = warp_sum(px) * M.inv_total_mass, vcy = warp_sum(py) * M.inv_total_mass,
-              vcz = warp_sum(pz) * M.inv_total_mass;
-  // end effectors in the root heading frame (lane = end effector)
-  float ee = 0.f;
+  out.vx = warp_sum(px) * M.inv_total_mass; out.vy = warp_sum(py) * M.inv_total_mass; out.vz = warp_sum(pz) * M.inv_total_mass;
+  out.ex = out.ey = out.ez = 0.f;
   if (lane < M.nee) {
     const float* R = &S.u.a.xmat[9];
     const float heading = atan2f(R[3], R[0]);
@@ -237,8 +390,18 @@ __device__ float reward_imitate(const ModelS& M, EnvS& S, const DevPtrs& P, int 
     const int b = M.ee_body[lane];
     const V3 w = ld3(&S.u.a.xpos[3 * b]) + mat_vec(&S.u.a.xmat[9 * b], ld3(M.ee_pos[lane]));
     const float rx = w.x - S.u.a.xpos[3], ry = w.y - S.u.a.xpos[4];
-    const float e0 = ch * rx + sh * ry - aux[3 * lane], e1 = -sh * rx + ch * ry - aux[3 * lane + 1],
-                e2 = w.z - aux[3 * lane + 2];
+    out.ex = ch * rx + sh * ry; out.ey = -sh * rx + ch * ry; out.ez = w.z;
+  }
+  return out;
+}
+
+// 5-term DeepMimic imitation reward (code.md:979-1146 adapted to the hinge model; weights and
+// scales from dp_env_v3.py:42-53) against the reference pose rq / rv with features `ref`.
+__device__ float reward_imitate(const ModelS& M, EnvS& S, int lane, const float* rq, const float* rv, PoseFeat ref) {
+  const PoseFeat cur = pose_features(M, S, lane);
+  float ee = 0.f;
+  if (lane < M.nee) {
+    const float e0 = cur.ex - ref.ex, e1 = cur.ey - ref.ey, e2 = cur.ez - ref.ez;
     ee = e0 * e0 + e1 * e1 + e2 * e2;
   }
   ee = warp_sum(ee);
@@ -273,7 +436,7 @@ __device__ float reward_imitate(const ModelS& M, EnvS& S, const DevPtrs& P, int 
     rp += a * a; rvv += b * b; rw += c * c;
   }
   const float root_err = rp + 0.1f * th_root * th_root + 0.01f * rvv + 0.001f * rw;
-  const float cx = aux[12] - vcx, cy = aux[13] - vcy, cz = aux[14] - vcz;
+  const float cx = ref.vx - cur.vx, cy = ref.vy - cur.vy, cz = ref.vz - cur.vz;
   const float com_err = 0.1f * (cx * cx + cy * cy + cz * cz);
   return M.w_pose * expf(-M.s_err * M.s_pose * pose_err) + M.w_vel * expf(-M.s_err * M.s_vel * vel_err) +
          M.w_ee * expf(-M.s_err * M.s_ee * ee) + M.w_root * expf(-M.s_err * M.s_root * root_err) +
@@ -308,7 +471,7 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
   stage_model(&M, P.model);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
   EnvS& S = tiles[warp];
-  const int od = (M.nq - 7) + (M.nv - 6);
+  const int od = M.obs_dim;
   __shared__ int s_base[8];
   __shared__ int s_arrive[4];
   // lockstep groups: the CTA's warps are split into M.ngroups groups, each with its own named
@@ -345,55 +508,92 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
     const float zc = rk4_step<LOCKSTEP>(M, S, lane, have && !bad, bar_id, bar_n, s_arrive);
     if (!have) continue;
     if (!bad) bad = state_bad(M, S, lane);
-    // reward (dp_env_v3.py:117 / 89-104)
+    // reward (dp_env_v3.py:117 / 89-104).  Reference pose: phase_mode 0 = table row of the integer frame
+    // counter; phase_mode 1 = interpolated at the post-step mocap time into S.x_q0 / S.x_dv (dead here)
     float rew = 1.0f;
-    int idx_curr = st.idx_curr[env];
+    int idx_curr = st.idx_curr[env], idx_init = st.idx_init[env];
     const int clip = st.clip[env];
-    if (M.reward_mode == 1) {
-      const int len = M.clip_len[clip], start = M.clip_start[clip];
-      float e = 0.f;
-      for (int j = lane; j < M.nq - 7; j += 32)
-        e += fabsf(S.qpos[7 + j] - P.mocap_cfg[(size_t)(start + idx_curr) * M.nq + 7 + j]);
-      e = warp_sum(e);
-      rew = expf(-e);
-      idx_curr = (idx_curr + 1) % len;
-    } else if (M.reward_mode == 4) {
-      if (!bad) rew = reward_imitate(M, S, P, lane, M.clip_start[clip] + idx_curr);
-      idx_curr = (idx_curr + 1) % M.clip_len[clip];
-    } else if (M.reward_mode == 2 || M.reward_mode == 3) {
-      // v2 / v1 rewards (dp_env_v2.py:116-183, dp_env_v1.py:82-152): frame advances first; the
-      // control cost is on the raw action
-      idx_curr = (idx_curr + 1) % M.clip_len[clip];
-      const float* rq = P.mocap_cfg + (size_t)(M.clip_start[clip] + idx_curr) * M.nq;
-      const float* rv = P.mocap_vel + (size_t)(M.clip_start[clip] + idx_curr) * M.nv;
-      float acs = 0.f;
-      if (lane < M.nu) { const float a = action[(size_t)env * M.nu + lane]; acs = a * a; }
-      acs = warp_sum(acs);
-      if (M.reward_mode == 2) {
-        float e = 0.f;
-        for (int i = 3 + lane; i < M.nq; i += 32) e += fabsf(S.qpos[i] - rq[i]);
-        rew = expf(-M.s_err * M.s_pose * warp_sum(e)) - 0.1f * acs;
+    const int len = M.clip_len[clip], start = M.clip_start[clip];
+    int ep_len = st.ep_len[env] + 1;
+    const int rmode = M.reward_mode;
+    if (rmode != 0 && !bad) {
+      const float* rq;
+      const float* rv;
+      int frame = idx_curr;                                   // modes 1, 4: reward first, then advance
+      if (rmode == 2 || rmode == 3) frame = (idx_curr + 1) % len;  // v2 / v1: the frame advances first
+      int k_ref = 0;
+      if (M.phase_mode == 1) {
+        k_ref = mocap_sample(M, P, clip, frame_coord(M, clip, idx_init, ep_len), lane, S.x_q0, S.x_dv);
+        rq = S.x_q0; rv = S.x_dv;
       } else {
-        float pe = 0.f;
-        if (lane == 1) {
-          Q4 q0; q0.w = S.qpos[3]; q0.x = S.qpos[4]; q0.y = S.qpos[5]; q0.z = S.qpos[6];
-          Q4 q1; q1.w = rq[3]; q1.x = rq[4]; q1.y = rq[5]; q1.z = rq[6];
-          pe = M.dof_weight[3] * quat_diff_theta(qnormalize(q0), qnormalize(q1));
-        } else if (lane >= 2 && lane < M.nbody) {
-          const int da = M.body_dofadr[lane], nd = M.body_dofnum[lane];
-          if (nd == 3) pe = M.dof_weight[da] * quat_diff_theta(quat_from_xyz(S.qpos[da + 1], S.qpos[da + 2], S.qpos[da + 3]),
-                                                               quat_from_xyz(rq[da + 1], rq[da + 2], rq[da + 3]));
-          else if (nd == 1) pe = M.dof_weight[da] * fabsf(S.qpos[da + 1] - rq[da + 1]);
-        }
-        const float pose = warp_sum(pe) * M.joint_weight_sum;
-        float ve = 0.f;
-        for (int d = lane; d < M.nv; d += 32) if (d >= 3) ve += fabsf(S.qvel[d] - rv[d]);
-        const float vel = warp_sum(ve);
-        const float root = fabsf(S.qpos[0] - rq[0]) + fabsf(S.qpos[1] - rq[1]) + fabsf(S.qpos[2] - rq[2]);
-        rew = M.w_pose * expf(-M.s_err * M.s_pose * pose) + M.w_vel * expf(-M.s_err * M.s_vel * vel) +
-              M.w_root * expf(-M.s_err * M.s_root * root) - 0.1f * acs;
+        rq = P.mocap_cfg + (size_t)(start + frame) * M.nq;
+        rv = P.mocap_vel + (size_t)(start + frame) * M.nv;
       }
+      if (rmode == 1) {
+        float e = 0.f;
+        for (int j = lane; j < M.nq - 7; j += 32) e += fabsf(S.qpos[7 + j] - rq[7 + j]);
+        rew = expf(-warp_sum(e));
+      } else if (rmode == 4) {
+        PoseFeat ref;
+        if (M.phase_mode == 1) {
+          // features of the interpolated reference pose: swap it into the tile, run the kinematics, swap back
+          const int i1 = lane + 32;
+          const float q0 = S.qpos[lane], q1 = i1 < M.nq ? S.qpos[i1] : 0.f;
+          const float v0 = S.qvel[lane], v1 = i1 < M.nv ? S.qvel[i1] : 0.f;
+          __syncwarp();
+          S.qpos[lane] = rq[lane]; if (i1 < M.nq) S.qpos[i1] = rq[i1];
+          S.qvel[lane] = rv[lane]; if (i1 < M.nv) S.qvel[i1] = rv[i1];
+          __syncwarp();
+          ref = pose_features(M, S, lane);
+          __syncwarp();
+          S.qpos[lane] = q0; if (i1 < M.nq) S.qpos[i1] = q1;
+          S.qvel[lane] = v0; if (i1 < M.nv) S.qvel[i1] = v1;
+          __syncwarp();
+        } else {
+          const float* aux = P.ref_aux + (size_t)(start + frame) * DMB_REF_AUX;
+          ref.ex = ref.ey = ref.ez = 0.f;
+          if (lane < M.nee) { ref.ex = aux[3 * lane]; ref.ey = aux[3 * lane + 1]; ref.ez = aux[3 * lane + 2]; }
+          ref.vx = aux[12]; ref.vy = aux[13]; ref.vz = aux[14];
+        }
+        rew = reward_imitate(M, S, lane, rq, rv, ref);
+      } else {
+        // v2 / v1 rewards (dp_env_v2.py:116-183, dp_env_v1.py:82-152); the control cost is on the raw action
+        float acs = 0.f;
+        if (lane < M.nu) { const float a = action[(size_t)env * M.nu + lane]; acs = a * a; }
+        acs = warp_sum(acs);
+        if (rmode == 2) {
+          float e = 0.f;
+          for (int i = 3 + lane; i < M.nq; i += 32) e += fabsf(S.qpos[i] - rq[i]);
+          rew = expf(-M.s_err * M.s_pose * warp_sum(e)) - 0.1f * acs;
+        } else {
+          float pe = 0.f;
+          if (lane == 1) {
+            Q4 q0; q0.w = S.qpos[3]; q0.x = S.qpos[4]; q0.y = S.qpos[5]; q0.z = S.qpos[6];
+            Q4 q1; q1.w = rq[3]; q1.x = rq[4]; q1.y = rq[5]; q1.z = rq[6];
+            pe = M.dof_weight[3] * quat_diff_theta(qnormalize(q0), qnormalize(q1));
+          } else if (lane >= 2 && lane < M.nbody) {
+            const int da = M.body_dofadr[lane], nd = M.body_dofnum[lane];
+            if (nd == 3) pe = M.dof_weight[da] * quat_diff_theta(quat_from_xyz(S.qpos[da + 1], S.qpos[da + 2], S.qpos[da + 3]),
+                                                                 quat_from_xyz(rq[da + 1], rq[da + 2], rq[da + 3]));
+            else if (nd == 1) pe = M.dof_weight[da] * fabsf(S.qpos[da + 1] - rq[da + 1]);
+          }
+          const float pose = warp_sum(pe) * M.joint_weight_sum;
+          float ve = 0.f;
+          for (int d = lane; d < M.nv; d += 32) if (d >= 3) ve += fabsf(S.qvel[d] - rv[d]);
+          const float vel = warp_sum(ve);
+          const float root = fabsf(S.qpos[0] - rq[0]) + fabsf(S.qpos[1] - rq[1]) + fabsf(S.qpos[2] - rq[2]);
+          rew = M.w_pose * expf(-M.s_err * M.s_pose * pose) + M.w_vel * expf(-M.s_err * M.s_vel * vel) +
+                M.w_root * expf(-M.s_err * M.s_root * root) - 0.1f * acs;
+        }
+      }
+      (void)k_ref;
     }
+    // frame counter: phase_mode 0 advances by one per step whenever a mocap reward is configured (also for a
+    // non-finite state); phase_mode 1 reports the frame interval of the post-step reference time
+    if (M.phase_mode == 1) {
+      int cyc; float al, ph;
+      phase_split(len, frame_coord(M, clip, idx_init, ep_len), cyc, idx_curr, al, ph);
+    } else if (rmode != 0) idx_curr = (idx_curr + 1) % len;
     if (bad) rew = 0.f;
     // termination (dp_env_v3.py:134-139) on the CoM height of the last stage evaluation
     bool done = bad || zc < M.z_min || zc > M.z_max;
@@ -403,7 +603,6 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
       done = done || __any_sync(DMB_FULL, fall);
     }
     const int flags = S.flags | (bad ? 4 : 0);
-    int ep_len = st.ep_len[env] + 1;
     float ep_ret = st.ep_ret[env] + rew;
     if (lane == 0) {
       out.reward[env] = rew;
@@ -418,13 +617,15 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
       st.ep_ret[env] = ep_ret;
     }
     __syncwarp();
-    if (done && M.auto_reset) reset_env(M, S, P, st, env, lane, seed, first_env_id, M.reset_mode);
-    else if (bad) {  // keep a finite state in HBM
+    if (done && M.auto_reset) {
+      idx_init = idx_curr = reset_env(M, S, P, st, env, lane, seed, first_env_id, M.reset_mode);
+      ep_len = 0;
+    } else if (bad) {  // keep a finite state in HBM
       for (int i = lane; i < M.nq; i += 32) S.qpos[i] = M.qpos0[i];
       for (int i = lane; i < M.nv; i += 32) { S.qvel[i] = 0.f; S.warm[i] = 0.f; }
       __syncwarp();
     }
-    write_obs(M, S, out.obs, out.rec, env, lane);
+    emit_obs(M, S, clip, idx_init, idx_curr, ep_len, out.obs, out.rec, env, lane);
     store_state(M, S, st, env, lane);
     __syncwarp();
   }
@@ -463,9 +664,9 @@ __global__ void k_reset(DevPtrs P, dmb_state_t st, const unsigned char* __restri
   EnvS& S = tiles[warp];
   for (int env = blockIdx.x * W + warp; env < N; env += gridDim.x * W) {
     if (mask && !mask[env]) continue;
-    reset_env(M, S, P, st, env, lane, seed, first_env_id, mode < 0 ? M.reset_mode : mode);
+    const int idx = reset_env(M, S, P, st, env, lane, seed, first_env_id, mode < 0 ? M.reset_mode : mode);
     if (lane == 0) st.flags[env] = 0;
-    write_obs(M, S, obs, nullptr, env, lane);
+    if (obs) emit_obs(M, S, st.clip[env], idx, idx, 0, obs, nullptr, env, lane);
     store_state(M, S, st, env, lane);
     __syncwarp();
   }
@@ -479,6 +680,49 @@ __global__ void k_obs(DevPtrs P, dmb_state_t st, float* obs, int N) {
     const size_t env = i / od;
     const int o = (int)(i % od);
     obs[i] = o < np ? st.qpos[env * DMB_QSTRIDE + 7 + o] : st.qvel[env * DMB_VSTRIDE + 6 + o - np];
+  }
+}
+
+// DeepMimic state of the stored state (obs_mode 1): one warp per env, needs the tile for the kinematics
+__global__ void k_obs_dm(DevPtrs P, dmb_state_t st, float* obs, int N) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ModelS& M = *reinterpret_cast<ModelS*>(smem);
+  EnvS* tiles = reinterpret_cast<EnvS*>(smem + MODEL_BYTES);
+  stage_model(&M, P.model);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  EnvS& S = tiles[warp];
+  for (int env = blockIdx.x * W + warp; env < N; env += gridDim.x * W) {
+    load_state(M, S, st, env, lane);
+    emit_obs(M, S, st.clip[env], st.idx_init[env], st.idx_curr[env], st.ep_len[env], obs, nullptr, env, lane);
+    __syncwarp();
+  }
+}
+
+// Interpolated reference poses for arbitrary (clip, frame coordinate) pairs: one warp per sample
+// (dmb_mocap_sample; the kinematic playback of MocapDM.play, mocap_v2.py:151-182, without a simulator)
+constexpr int SAMPLE_WARPS = 8;
+__global__ void k_mocap_sample(DevPtrs P, const int* __restrict__ clip, const double* __restrict__ u, int n, float* qpos,
+                               float* qvel, float* phase) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  ModelS& M = *reinterpret_cast<ModelS*>(smem);
+  float* scratch = reinterpret_cast<float*>(smem + MODEL_BYTES);
+  stage_model(&M, P.model);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* rq = scratch + warp * 2 * NQC;
+  float* rv = rq + NQC;
+  for (int i = blockIdx.x * SAMPLE_WARPS + warp; i < n; i += gridDim.x * SAMPLE_WARPS) {
+    int c = clip ? clip[i] : 0;
+    c = c < 0 ? 0 : (c >= M.nclip ? M.nclip - 1 : c);
+    const double ui = u[i];
+    mocap_sample(M, P, c, ui, lane, rq, rv);
+    for (int k = lane; k < DMB_QSTRIDE; k += 32) qpos[(size_t)i * DMB_QSTRIDE + k] = k < M.nq ? rq[k] : 0.f;
+    for (int k = lane; k < DMB_VSTRIDE; k += 32) qvel[(size_t)i * DMB_VSTRIDE + k] = k < M.nv ? rv[k] : 0.f;
+    if (phase && lane == 0) {
+      int cyc, kk; float al, ph;
+      phase_split(M.clip_len[c], ui, cyc, kk, al, ph);
+      phase[i] = ph;
+    }
+    __syncwarp();
   }
 }
 
@@ -679,6 +923,17 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
   S.ctrl_mode = c->ctrl_mode; S.reward_mode = c->reward_mode; S.reset_mode = c->reset_mode; S.auto_reset = c->auto_reset;
   S.joint_weight_sum = (float)c->joint_weight_sum;
   S.term_mode = c->term_mode; S.fall_body_mask = c->fall_body_mask;
+  S.phase_mode = c->phase_mode; S.obs_mode = c->obs_mode;
+  if (c->phase_mode < 0 || c->phase_mode > 1) { why = "phase_mode must be 0 or 1"; return DMB_ERR_ARG; }
+  if (c->obs_mode < 0 || c->obs_mode > 1) { why = "obs_mode must be 0 or 1"; return DMB_ERR_ARG; }
+  if (m->npart < 0 || m->npart > DMB_MAX_PART) { why = "npart out of range"; return DMB_ERR_MODEL; }
+  S.npart = m->npart;
+  for (int p = 0; p < m->npart; p++) {
+    if (m->part_geom[p] < 0 || m->part_geom[p] >= m->ngeom) { why = "part_geom out of range"; return DMB_ERR_MODEL; }
+    S.part_geom[p] = (int8_t)m->part_geom[p];
+  }
+  if (c->obs_mode == 1 && m->npart < 1) { why = "obs_mode 1 needs the body-part table (npart >= 1)"; return DMB_ERR_MODEL; }
+  S.obs_dim = c->obs_mode == 1 ? 2 + 13 * m->npart : (m->nq - 7) + (m->nv - 6);
   S.z_min = (float)c->z_min; S.z_max = (float)c->z_max; S.reset_noise = (float)c->reset_noise; S.pd_dt = (float)m->timestep;
   S.w_pose = (float)c->w_pose; S.w_vel = (float)c->w_vel; S.w_ee = (float)c->w_end_eff; S.w_root = (float)c->w_root; S.w_com = (float)c->w_com;
   S.s_pose = (float)c->s_pose; S.s_vel = (float)c->s_vel; S.s_ee = (float)c->s_end_eff; S.s_root = (float)c->s_root; S.s_com = (float)c->s_com;
@@ -696,7 +951,14 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
   S.sync_mask = 0x01;  // one barrier per RK stage (sweep on B200: best of 0x7f..0x01)
   if (const char* sm = getenv("DMB_SYNC_MASK")) S.sync_mask = (int)strtol(sm, nullptr, 0);
   if (mc->nclip < 1 || mc->nclip > DMB_MAX_CLIP) { why = "need 1..16 motion clips"; return DMB_ERR_ARG; }
-  for (int k = 0; k < mc->nclip; k++) { S.clip_start[k] = mc->clip_start[k]; S.clip_len[k] = mc->clip_len[k]; }
+  for (int k = 0; k < mc->nclip; k++) {
+    S.clip_start[k] = mc->clip_start[k]; S.clip_len[k] = mc->clip_len[k];
+    if (mc->clip_len[k] < 1 || mc->clip_start[k] < 0 || mc->clip_start[k] + mc->clip_len[k] > mc->nframe_total) {
+      why = "clip_start / clip_len outside the mocap tables"; return DMB_ERR_ARG;
+    }
+    S.clip_rate[k] = mc->clip_dt[k] > 0 ? m->timestep / mc->clip_dt[k] : 0.0;
+    if (c->phase_mode == 1 && !(mc->clip_dt[k] > 0)) { why = "phase_mode 1 needs clip_dt > 0"; return DMB_ERR_ARG; }
+  }
   return DMB_OK;
 }
 
@@ -739,7 +1001,7 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
   int rc = build_model(model, config, mocap, h->hmodel, why);
   if (rc != DMB_OK) { delete h; return fail(nullptr, rc, "dmb_create: " + why); }
   h->device = cuda_device; h->num_envs = num_envs; h->seed = seed; h->first_env_id = first_env_id;
-  h->nu = model->nu; h->obs_dim = (model->nq - 7) + (model->nv - 6);
+  h->nu = model->nu; h->obs_dim = h->hmodel.obs_dim;
   cudaError_t e = cudaSetDevice(cuda_device);
   if (e != cudaSuccess) { delete h; return fail(nullptr, DMB_ERR_CUDA, cudaGetErrorString(e)); }
   const size_t F = (size_t)mocap->nframe_total;
@@ -793,7 +1055,7 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
   h->smem = (int)(MODEL_BYTES + (size_t)W * sizeof(EnvS));
   int need = (num_envs + W - 1) / W;
   h->grid = need < prop.multiProcessorCount ? need : prop.multiProcessorCount;
-  for (auto fn : {(const void*)k_step<false>, (const void*)k_step<true>, (const void*)k_reset, (const void*)k_forward_debug}) {
+  for (auto fn : {(const void*)k_step<false>, (const void*)k_step<true>, (const void*)k_reset, (const void*)k_forward_debug, (const void*)k_obs_dm}) {
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
     if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
   }
@@ -839,10 +1101,14 @@ int dmb_get_obs(dmb_handle_t h, const dmb_state_t* st, float* obs, void* stream)
   if (!h) return DMB_ERR_ARG;
   if (!state_ok(st) || !obs) return fail(h, DMB_ERR_ARG, "dmb_get_obs: bad argument");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  const size_t total = (size_t)h->num_envs * h->obs_dim;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 4096) blocks = 4096;
-  k_obs<<<blocks, 256, 0, (cudaStream_t)stream>>>(devptrs(h), *st, obs, h->num_envs);
+  if (h->hmodel.obs_mode == 1) {
+    k_obs_dm<<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, obs, h->num_envs);
+  } else {
+    const size_t total = (size_t)h->num_envs * h->obs_dim;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 4096) blocks = 4096;
+    k_obs<<<blocks, 256, 0, (cudaStream_t)stream>>>(devptrs(h), *st, obs, h->num_envs);
+  }
   CUDA_TRY(h, cudaGetLastError());
   return DMB_OK;
 }
@@ -855,6 +1121,22 @@ int dmb_forward_debug(dmb_handle_t h, const dmb_state_t* st, const float* ctrl, 
   CUDA_TRY(h, cudaGetLastError());
   return DMB_OK;
 }
+
+int dmb_mocap_sample(dmb_handle_t h, const int32_t* clip, const double* frame_coord, int32_t n, float* qpos, float* qvel,
+                     float* phase, void* stream) {
+  if (!h) return DMB_ERR_ARG;
+  if (!frame_coord || !qpos || !qvel || n < 0) return fail(h, DMB_ERR_ARG, "dmb_mocap_sample: bad argument");
+  if (n == 0) return DMB_OK;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  int blocks = (n + SAMPLE_WARPS - 1) / SAMPLE_WARPS;
+  if (blocks > 1184) blocks = 1184;
+  const size_t smem = MODEL_BYTES + (size_t)SAMPLE_WARPS * 2 * NQC * sizeof(float);
+  k_mocap_sample<<<blocks, SAMPLE_WARPS * 32, smem, (cudaStream_t)stream>>>(devptrs(h), clip, frame_coord, n, qpos, qvel, phase);
+  CUDA_TRY(h, cudaGetLastError());
+  return DMB_OK;
+}
+
+int32_t dmb_obs_dim(dmb_handle_t h) { return h ? h->obs_dim : DMB_ERR_ARG; }
 
 int dmb_launch_info(dmb_handle_t h, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* envs_per_cta) {
   if (!h) return DMB_ERR_ARG;

@@ -66,7 +66,10 @@ struct ModelS {
   int8_t act_dofadr[NU];
   // env config
   int ctrl_mode, reward_mode, reset_mode, auto_reset;
-  int term_mode; unsigned fall_body_mask; int pad_t0, pad_t1;
+  int term_mode; unsigned fall_body_mask; int phase_mode, obs_mode;
+  int npart, obs_dim, pad_t0, pad_t1;
+  int8_t part_geom[DMB_MAX_PART];
+  double clip_rate[DMB_MAX_CLIP];  // env steps -> mocap frames: timestep / clip_dt (phase_mode 1)
   float z_min, z_max, reset_noise, pd_dt;
   float joint_weight_sum, pad_w0, pad_w1, pad_w2;
   float w_pose, w_vel, w_ee, w_root, w_com, s_pose, s_vel, s_ee, s_root, s_com, s_err, pad_g;

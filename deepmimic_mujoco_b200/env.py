@@ -70,9 +70,12 @@ class DPVecEnv:
 
     def __init__(self, num_envs: int, motions: Sequence[str] = ("walk",), device=None, seed: int = 0,
                  first_env_id: int = 0, reward_mode: int = 0, ctrl_mode: int = 0, reset_mode: int = 0,
-                 auto_reset: bool = True, clip_ids: Optional[torch.Tensor] = None, **cfg_kw):
+                 auto_reset: bool = True, clip_ids: Optional[torch.Tensor] = None, phase_mode: int = 0,
+                 obs_mode: int = 0, **cfg_kw):
+        """phase_mode 1: time-based mocap phase with lerp/slerp interpolation (instead of one frame per step);
+        obs_mode 1: the 197-d DeepMimic state instead of qpos[7:] || qvel[6:]."""
         cfg = default_config(reward_mode=reward_mode, ctrl_mode=ctrl_mode, reset_mode=reset_mode,
-                             auto_reset=int(auto_reset), **cfg_kw)
+                             auto_reset=int(auto_reset), phase_mode=phase_mode, obs_mode=obs_mode, **cfg_kw)
         ref_aux = None
         if reward_mode == 4:
             from .refaux import compute_ref_aux
@@ -132,11 +135,12 @@ class DPEnv(_EnvBase):
     spec = None
 
     def __init__(self, motion: Optional[str] = None, device=None, seed: int = 0, reward_mode: int = 0,
-                 ctrl_mode: int = 0, frame_skip: int = 6):
+                 ctrl_mode: int = 0, frame_skip: int = 6, phase_mode: int = 0, obs_mode: int = 0):
         from .mocap import load_clip
         from .sim import motion_path
         self.motion = motion or Config.motion
-        cfg = default_config(reward_mode=reward_mode, ctrl_mode=ctrl_mode, reset_mode=0, auto_reset=0)
+        cfg = default_config(reward_mode=reward_mode, ctrl_mode=ctrl_mode, reset_mode=0, auto_reset=0,
+                             phase_mode=phase_mode, obs_mode=obs_mode)
         ref_aux = None
         if reward_mode == 4:
             from .refaux import compute_ref_aux

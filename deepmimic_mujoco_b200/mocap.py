@@ -119,6 +119,75 @@ def calc_rot_vel(seg0, seg1, dura):
     return (quat_angle(qd) / dura)[..., None] * quat_axis(qd)
 
 
+def quat_from_euler_rxyz(e):
+    """Quaternion (w,x,y,z) of the hinge triple R = Rx(a) Ry(b) Rz(c); inverse of euler_rxyz_from_quat and
+    equal to transformations.quaternion_from_euler(a, b, c, 'rxyz') (transformations.py:1100-1154)."""
+    e = np.asarray(e, dtype=np.float64)
+    h = 0.5 * e
+    z, o = np.zeros_like(h[..., 0]), np.ones_like(h[..., 0])
+    qx = np.stack([np.cos(h[..., 0]), np.sin(h[..., 0]), z, z], axis=-1)
+    qy = np.stack([np.cos(h[..., 1]), z, np.sin(h[..., 1]), z], axis=-1)
+    qz = np.stack([np.cos(h[..., 2]), z, z, np.sin(h[..., 2])], axis=-1)
+    del o
+    return qmul(qmul(qx, qy), qz)
+
+
+_EPS = np.finfo(float).eps * 4.0
+
+
+def quat_slerp(q0, q1, fraction):
+    """transformations.quaternion_slerp(q0, q1, fraction, spin=0, shortestpath=True)
+    (transformations.py:1270-1308), restated for one pair of quaternions (any component order)."""
+    q0 = np.array(q0, dtype=np.float64); q1 = np.array(q1, dtype=np.float64)
+    q0 /= np.linalg.norm(q0); q1 /= np.linalg.norm(q1)
+    if fraction == 0.0:
+        return q0
+    if fraction == 1.0:
+        return q1
+    d = float(np.dot(q0, q1))
+    if abs(abs(d) - 1.0) < _EPS:
+        return q0
+    if d < 0.0:
+        d, q1 = -d, -q1
+    angle = np.arccos(d)
+    if abs(angle) < _EPS:
+        return q0
+    isin = 1.0 / np.sin(angle)
+    return q0 * (np.sin((1.0 - fraction) * angle) * isin) + q1 * (np.sin(fraction * angle) * isin)
+
+
+def sample_tables(data_config, data_vel, u, body_dofs=None):
+    """Time-based mocap lookup with interpolation (BASELINE north_star
+    "mocap-frame interpolation"): reference pose at the fractional frame coordinate ``u = t / clip_dt``.
+
+    One cycle of an F-frame clip spans F-1 frame intervals (the last frame closes the loop); past the
+    end the clip wraps and the root x/y are shifted by the last frame's root x/y once per completed
+    cycle -- the root-offset accumulation of MocapDM.play (mocap_v2.py:168-182).  Inside an interval:
+    root position, 1-DoF joints and all velocities are interpolated linearly; the root quaternion and
+    the 3-DoF joints (hinge triples <-> quaternions) by quaternion_slerp, back to 'rxyz' Euler angles.
+    Returns (qpos[35], qvel[34], cycle, k, alpha)."""
+    cfg, vel = np.asarray(data_config, dtype=np.float64), np.asarray(data_vel, dtype=np.float64)
+    F = cfg.shape[0]
+    if F < 2:
+        return cfg[0].copy(), vel[0].copy(), 0, 0, 0.0
+    cycle = int(np.floor(u / (F - 1)))
+    uu = u - cycle * (F - 1)
+    k = min(int(uu), F - 2)
+    a = uu - k
+    c0, c1 = cfg[k], cfg[k + 1]
+    q = c0 + a * (c1 - c0)
+    q[0:2] += cycle * cfg[F - 1, 0:2]
+    q[3:7] = quat_slerp(c0[3:7], c1[3:7], a)
+    off = 7
+    for jn in BODY_JOINTS:
+        if DOF_DEF[jn] == 3:
+            qs = quat_slerp(quat_from_euler_rxyz(c0[off:off + 3]), quat_from_euler_rxyz(c1[off:off + 3]), a)
+            q[off:off + 3] = euler_rxyz_from_quat(qs)
+        off += DOF_DEF[jn]
+    v = vel[k] + a * (vel[k + 1] - vel[k])
+    return q, v, cycle, k, a
+
+
 # ---------------------------------------------------------------------------------------------
 @dataclasses.dataclass
 class Clip:
@@ -132,6 +201,11 @@ class Clip:
 
     def __len__(self):
         return self.data_config.shape[0]
+
+    def sample(self, t: float):
+        """Interpolated reference (qpos, qvel) at mocap time ``t`` seconds (see sample_tables)."""
+        q, v, _, _, _ = sample_tables(self.data_config, np.nan_to_num(self.data_vel), t / self.dt)
+        return q, v
 
 
 def compile_frames(frames: np.ndarray, name: str = "clip", loop: str = "wrap") -> Clip:

@@ -12,8 +12,8 @@ import numpy as np
 
 from .mjcf import ModelTables
 
-MAX_BODY, MAX_JNT, MAX_DOF, MAX_Q, MAX_GEOM, MAX_PAIR, MAX_U, MAX_M, MAX_CLIP, MAX_EE = (
-    16, 32, 40, 40, 16, 128, 32, 320, 16, 4)
+MAX_BODY, MAX_JNT, MAX_DOF, MAX_Q, MAX_GEOM, MAX_PAIR, MAX_U, MAX_M, MAX_CLIP, MAX_EE, MAX_PART = (
+    16, 32, 40, 40, 16, 128, 32, 320, 16, 4, 16)
 REF_AUX = 24
 
 i32, f64 = C.c_int32, C.c_double
@@ -29,6 +29,13 @@ JOINT_WEIGHT = {"root": 1, "chest": 0.5, "neck": 0.3, "right_hip": 0.5, "right_k
 # joint origins, wrists = wrist geom centres on the elbow bodies (dp_env_v3.xml:51,65)
 END_EFFECTORS = (("right_ankle", (0.0, 0.0, 0.0)), ("right_elbow", (0.0, 0.0, -0.258947)),
                  ("left_ankle", (0.0, 0.0, 0.0)), ("left_elbow", (0.0, 0.0, -0.258947)))
+
+
+# DeepMimic body parts in the order of src/data/characters/humanoid3d.txt: (owning body, index of the
+# part's geom among that body's geoms) -- the wrists are the second geoms of the elbow bodies
+DM_PARTS = (("root", 0), ("chest", 0), ("neck", 0), ("right_hip", 0), ("right_knee", 0), ("right_ankle", 0),
+            ("right_shoulder", 0), ("right_elbow", 0), ("right_elbow", 1), ("left_hip", 0), ("left_knee", 0),
+            ("left_ankle", 0), ("left_shoulder", 0), ("left_elbow", 0), ("left_elbow", 1))
 
 
 class DmbModel(C.Structure):
@@ -59,13 +66,14 @@ class DmbModel(C.Structure):
         ("dof_weight", f64 * MAX_DOF),
         ("ee_body", i32 * MAX_EE), ("nee", i32), ("pad1", i32 * 3),
         ("ee_pos", (f64 * 3) * MAX_EE),
+        ("npart", i32), ("pad2", i32), ("part_geom", i32 * MAX_PART),
     ]
 
 
 class DmbConfig(C.Structure):
     _fields_ = [
         ("ctrl_mode", i32), ("reward_mode", i32), ("reset_mode", i32), ("auto_reset", i32),
-        ("term_mode", i32), ("fall_body_mask", C.c_uint32),
+        ("term_mode", i32), ("fall_body_mask", C.c_uint32), ("phase_mode", i32), ("obs_mode", i32),
         ("z_min", f64), ("z_max", f64), ("reset_noise", f64), ("joint_weight_sum", f64),
         ("w_pose", f64), ("w_vel", f64), ("w_end_eff", f64), ("w_root", f64), ("w_com", f64),
         ("s_pose", f64), ("s_vel", f64), ("s_end_eff", f64), ("s_root", f64), ("s_com", f64), ("s_err", f64),
@@ -127,6 +135,16 @@ def pack_model(mt: ModelTables, max_con: int = 16, max_efc: int = 40) -> DmbMode
                 m.ee_pos[nee][k] = off[k]
             nee += 1
     m.nee = nee
+    # DeepMimic body parts (humanoid3d.txt order) -> geom ids: the k-th geom of the named body
+    npart = 0
+    for body, k in DM_PARTS:
+        if body in mt.body_names:
+            b = mt.body_names.index(body)
+            gs = [g for g in range(mt.ngeom) if mt.geom_bodyid[g] == b]
+            if k < len(gs):
+                m.part_geom[npart] = gs[k]
+                npart += 1
+    m.npart = npart
     return m
 
 
@@ -135,6 +153,7 @@ def default_config(**kw) -> DmbConfig:
     c = DmbConfig()
     c.ctrl_mode, c.reward_mode, c.reset_mode, c.auto_reset = 0, 0, 0, 0
     c.term_mode = 0
+    c.phase_mode, c.obs_mode = 0, 0
     # DeepMimic walk args: every body except the two ankles (bodies 10 and 13 of dp_env_v3.xml) is a fall contact
     c.fall_body_mask = sum(1 << b for b in range(1, 14) if b not in (10, 13))
     c.z_min, c.z_max, c.reset_noise = 0.7, 2.0, 0.01

@@ -69,12 +69,12 @@ class BatchedSim:
         self.mocap: MocapTables = load_motions(list(motions))
         self._mc_struct, self._mc_keep = make_mocap_struct(self.mocap, ref_aux)
         self.nq, self.nv, self.nu = self.tables.nq, self.tables.nv, self.tables.nu
-        self.obs_dim = (self.nq - 7) + (self.nv - 6)
         self.handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self.L.dmb_create(C.byref(self.model), C.byref(self.config), C.byref(self._mc_struct), self.N,
                                          self.device.index, C.c_uint64(seed), C.c_uint32(first_env_id),
                                          C.byref(self.handle)), None, "dmb_create")
+        self.obs_dim = int(self.L.dmb_obs_dim(self.handle))   # 56, or 197 for the DeepMimic state (obs_mode 1)
         d, N = self.device, self.N
         f32, i32 = torch.float32, torch.int32
         self.qpos = torch.zeros(N, _lib.QSTRIDE, dtype=f32, device=d)
@@ -149,6 +149,26 @@ class BatchedSim:
             _lib.check(self.L.dmb_get_obs(self.handle, C.byref(self._st), C.c_void_p(self.obs.data_ptr()),
                                           self._stream()), self.handle, "dmb_get_obs")
         return self.obs
+
+    def mocap_sample(self, t, clip_ids: Optional[torch.Tensor] = None):
+        """Interpolated reference poses at mocap times ``t`` [n] seconds (phase_mode 1 arithmetic: lerp / slerp
+        between frames, loop wrap with root-offset accumulation).  Returns (qpos [n,nq], qvel [n,nv], phase [n])
+        CUDA float32 tensors; ``clip_ids`` [n] int (default: clip 0)."""
+        t = torch.as_tensor(t, dtype=torch.float64).reshape(-1)
+        n = t.numel()
+        clip = (torch.zeros(n, dtype=torch.int64) if clip_ids is None else torch.as_tensor(clip_ids).reshape(-1).cpu().long())
+        dt = torch.as_tensor(np.asarray(self.mocap.clip_dt), dtype=torch.float64)[clip]
+        u = (t.cpu() / dt).to(self.device).contiguous()                 # frame coordinate t / clip_dt, float64
+        clip_d = clip.to(self.device, torch.int32).contiguous()
+        qpos = torch.empty(n, _lib.QSTRIDE, dtype=torch.float32, device=self.device)
+        qvel = torch.empty(n, _lib.VSTRIDE, dtype=torch.float32, device=self.device)
+        phase = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.dmb_mocap_sample(self.handle, C.c_void_p(clip_d.data_ptr()), C.c_void_p(u.data_ptr()), n,
+                                               C.c_void_p(qpos.data_ptr()), C.c_void_p(qvel.data_ptr()),
+                                               C.c_void_p(phase.data_ptr()), self._stream()), self.handle,
+                       "dmb_mocap_sample")
+        return qpos[:, : self.nq], qvel[:, : self.nv], phase
 
     def set_state(self, qpos, qvel, warm=None, idx_curr=None):
         """Overwrite state from arrays [N,nq] / [N,nv] (numpy or torch, any float dtype)."""

@@ -16,7 +16,8 @@
  *    unless the name ends in _host; the library owns only the opaque handle (constant
  *    tables, launch configuration);
  *  - env-major rows, fp32: qpos[N][DMB_QSTRIDE], qvel[N][DMB_VSTRIDE], warm[N][DMB_VSTRIDE]
- *    (strides padded to 16 B multiples), action[N][nu], obs[N][nq-7 + nv-6];
+ *    (strides padded to 16 B multiples), action[N][nu], obs[N][obs_dim] (obs_dim = nq-7 + nv-6 = 56, or
+ *    2 + 13*npart = 197 for the DeepMimic state, config.obs_mode 1);
  *  - all work is enqueued on the caller's CUDA stream (pass torch.cuda.current_stream()
  *    .cuda_stream, or NULL for the legacy default stream); calls are asynchronous w.r.t.
  *    the host except create/destroy;
@@ -34,7 +35,7 @@
 extern "C" {
 #endif
 
-#define DMB_VERSION 1
+#define DMB_VERSION 2
 #define DMB_QSTRIDE 36 /* floats per qpos row (nq = 35 padded) */
 #define DMB_VSTRIDE 36 /* floats per qvel / warmstart row (nv = 34 padded) */
 
@@ -98,8 +99,17 @@ int dmb_reset(dmb_handle_t h, const dmb_state_t* st, const uint8_t* mask, int32_
  * done (+ in-kernel auto reset when config.auto_reset).  dp_env_v3.py:106-132. */
 int dmb_step(dmb_handle_t h, const dmb_state_t* st, const float* action, const dmb_step_out_t* out, void* stream);
 
-/* Observation of the current state (dp_env_v3.py:62-65). */
+/* Observation of the current state: obs_mode 0 = qpos[7:] || qvel[6:] (dp_env_v3.py:62-65);
+ * obs_mode 1 = DeepMimic state (code.md:287-504, mujoco_env.py:91-124).  obs is [N][dmb_obs_dim()]. */
 int dmb_get_obs(dmb_handle_t h, const dmb_state_t* st, float* obs, void* stream);
+int32_t dmb_obs_dim(dmb_handle_t h);
+
+/* Interpolated mocap reference poses (phase_mode 1 arithmetic; replaces the kinematic playback of
+ * MocapDM.play, mocap_v2.py:151-182, and transformations.quaternion_slerp, transformations.py:1270-1308):
+ * for i < n, the pose of clip[i] (NULL = clip 0) at frame coordinate frame_coord[i] = t / clip_dt (device
+ * float64) -> qpos[n][DMB_QSTRIDE], qvel[n][DMB_VSTRIDE], phase[n] in [0,1) (may be NULL). */
+int dmb_mocap_sample(dmb_handle_t h, const int32_t* clip, const double* frame_coord, int32_t n, float* qpos, float* qvel,
+                     float* phase, void* stream);
 
 /* Stage-level debug: run ONE forward evaluation (mj_forward) at the current state with the
  * given ctrl[N][nu] and dump stage outputs into dbg[N][dmb_debug_stride()] (layout in

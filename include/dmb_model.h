@@ -26,6 +26,7 @@ extern "C" {
 #define DMB_MAX_M 320
 #define DMB_MAX_CLIP 16
 #define DMB_MAX_EE 4
+#define DMB_MAX_PART 16
 
 /* geom / joint type ids (MuJoCo's numbering) */
 #define DMB_GEOM_PLANE 0
@@ -82,6 +83,11 @@ typedef struct dmb_model {
   int32_t ee_body[DMB_MAX_EE];    /* end-effector points: body id + local offset */
   int32_t nee, pad1[3];
   double ee_pos[DMB_MAX_EE][3];
+  /* DeepMimic body parts for the 197-d state (obs_mode 1): geom id of each part, in the part order of
+   * src/data/characters/humanoid3d.txt (root, chest, neck, r_hip, r_knee, r_ankle, r_shoulder, r_elbow,
+   * r_wrist, l_hip, ..., l_wrist); a part's position is its geom centre, its rotation the owning body's */
+  int32_t npart, pad2;
+  int32_t part_geom[DMB_MAX_PART];
 } dmb_model_t;
 
 /* Environment-level configuration (reward / control / termination / reset modes). */
@@ -97,6 +103,13 @@ typedef struct dmb_config {
   int32_t term_mode;   /* 0: CoM height only (dp_env_v3.py:134-139); 1: + DeepMimic fall-contact rule
                           (--fall_contact_bodies, src/args/train_humanoid3d_walk_args.txt:20) */
   uint32_t fall_body_mask; /* bit b set: a floor contact of body b ends the episode (all but the ankles) */
+  int32_t phase_mode;  /* 0: integer frame stepping, one frame per env step (dp_env_v3.py:101-102);
+                          1: time-based phase, reference pose interpolated between frames (lerp / slerp,
+                          transformations.py:1270-1308) with loop wrap + root-offset accumulation
+                          (mocap_v2.py:168-182); reference time = idx_init*clip_dt + steps*timestep */
+  int32_t obs_mode;    /* 0: qpos[7:] || qvel[6:] (dp_env_v3.py:62-65);
+                          1: DeepMimic state (code.md:287-504, mujoco_env.py:91-124): phase, root height,
+                          npart x (pos 3 + quat 4), npart x (lin vel 3 + ang vel 3) in the root heading frame */
   double z_min, z_max; /* CoM-height termination band (dp_env_v3.py:134-139): 0.7, 2.0 */
   double reset_noise;  /* 0.01 */
   double joint_weight_sum; /* sum of the raw DeepMimic joint weights (mocap_util.py:26-29): 4.8 */

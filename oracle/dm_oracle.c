@@ -1052,13 +1052,112 @@ void dmo_ref_aux(const dmb_model_t* m, const double* qpos, const double* qvel, d
   for (int i = 0; i < 4; i++) aux[15 + i] = qpos[3 + i];
 }
 
-static double reward_imitate(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, dmo_env_t* e) {
-  dmo_data_t* d = &e->d;
-  size_t f = (size_t)(mc->clip_start[e->clip] + e->idx_curr);
-  double rq[DMB_MAX_Q], rv[DMB_MAX_DOF], aux[DMB_REF_AUX];
+/* ------------------------------------------------------------------------------------
+ * Time-based mocap phase with interpolation (spec pinned against the
+ * reference's own routines in tests/golden/make_interp_golden.py).
+ * ------------------------------------------------------------------------------------ */
+/* transformations.quaternion_slerp(q0, q1, fraction, spin=0, shortestpath=True)
+ * (/root/reference/src/transformations.py:1270-1308) */
+static void quat_slerp(double* out, const double* qa, const double* qb, double f) {
+  const double EPS = 2.220446049250313e-16*4.0;
+  double q0[4], q1[4];
+  memcpy(q0, qa, sizeof(q0)); memcpy(q1, qb, sizeof(q1));
+  normalize4(q0); normalize4(q1);
+  if (f == 0.0) { memcpy(out, q0, sizeof(q0)); return; }
+  if (f == 1.0) { memcpy(out, q1, sizeof(q1)); return; }
+  double d = q0[0]*q1[0] + q0[1]*q1[1] + q0[2]*q1[2] + q0[3]*q1[3];
+  if (fabs(fabs(d) - 1.0) < EPS) { memcpy(out, q0, sizeof(q0)); return; }
+  if (d < 0.0) { d = -d; for (int i = 0; i < 4; i++) q1[i] = -q1[i]; }
+  double angle = acos(d);
+  if (fabs(angle) < EPS) { memcpy(out, q0, sizeof(q0)); return; }
+  double isin = 1.0/sin(angle);
+  double w0 = sin((1.0 - f)*angle)*isin, w1 = sin(f*angle)*isin;
+  for (int i = 0; i < 4; i++) out[i] = q0[i]*w0 + q1[i]*w1;
+}
+/* transformations.euler_from_quaternion([x,y,z,w], 'rxyz') (transformations.py:1031-1097,1174-1193)
+ * for a (w,x,y,z) quaternion: R = Rx(a) Ry(b) Rz(c) */
+static void euler_rxyz_from_quat(double* e, const double* q) {
+  const double EPS = 2.220446049250313e-16*4.0;
+  double n = q[0]*q[0] + q[1]*q[1] + q[2]*q[2] + q[3]*q[3];
+  if (n < EPS) { e[0] = e[1] = e[2] = 0; return; }
+  double s = sqrt(2.0/n);
+  double w = q[0]*s, x = q[1]*s, y = q[2]*s, z = q[3]*s;
+  double R00 = 1.0 - y*y - z*z, R01 = x*y - z*w, R02 = x*z + y*w;
+  double R10 = x*y + z*w, R11 = 1.0 - x*x - z*z, R12 = y*z - x*w, R22 = 1.0 - x*x - y*y;
+  double cy = sqrt(R22*R22 + R12*R12);
+  if (cy > EPS) { e[0] = atan2(-R12, R22); e[1] = atan2(R02, cy); e[2] = atan2(-R01, R00); }
+  else { e[0] = 0; e[1] = atan2(R02, cy); e[2] = atan2(R10, R11); }
+}
+/* frame coordinate u -> (cycle, k, alpha, phase) for an F-frame clip: one cycle = F-1 intervals */
+static void phase_split(int F, double u, int* cycle, int* k, double* alpha, double* phase) {
+  if (F < 2) { *cycle = 0; *k = 0; *alpha = 0; *phase = 0; return; }
+  double c = floor(u/(double)(F - 1));
+  double uu = u - c*(double)(F - 1);
+  int kk = (int)uu;
+  if (kk > F - 2) kk = F - 2;
+  if (kk < 0) kk = 0;
+  *cycle = (int)c; *k = kk; *alpha = uu - (double)kk; *phase = uu/(double)(F - 1);
+}
+
+/* interpolated reference pose at frame coordinate u = t / clip_dt (mocap.py sample_tables); table
+ * entries are rounded to fp32 first, as the CUDA path stores them */
+void dmo_mocap_sample(const dmb_model_t* m, const dmb_mocap_t* mc, int clip, double u, double* qpos, double* qvel,
+                      double* phase) {
+  int F = mc->clip_len[clip], start = mc->clip_start[clip], cycle, k;
+  double a, ph;
+  phase_split(F, u, &cycle, &k, &a, &ph);
+  int k1 = F < 2 ? k : k + 1;
+  const double* c0 = mc->data_config + (size_t)(start + k)*m->nq;
+  const double* c1 = mc->data_config + (size_t)(start + k1)*m->nq;
+  const double* cl = mc->data_config + (size_t)(start + F - 1)*m->nq;
+  const double* v0 = mc->data_vel + (size_t)(start + k)*m->nv;
+  const double* v1 = mc->data_vel + (size_t)(start + k1)*m->nv;
+  double r0[DMB_MAX_Q], r1[DMB_MAX_Q];
+  for (int i = 0; i < m->nq; i++) { r0[i] = (double)(float)c0[i]; r1[i] = (double)(float)c1[i]; }
+  for (int i = 0; i < m->nq; i++) qpos[i] = r0[i] + a*(r1[i] - r0[i]);
+  qpos[0] += (double)cycle*(double)(float)cl[0];
+  qpos[1] += (double)cycle*(double)(float)cl[1];
+  quat_slerp(qpos + 3, r0 + 3, r1 + 3, a);
+  for (int b = 2; b < m->nbody; b++) {
+    if (m->body_dofnum[b] != 3) continue;
+    int qa = m->body_dofadr[b] + 1;
+    double q0[4], q1[4], qs[4];
+    quat_from_xyz(q0, r0 + qa); quat_from_xyz(q1, r1 + qa);
+    quat_slerp(qs, q0, q1, a);
+    euler_rxyz_from_quat(qpos + qa, qs);
+  }
+  for (int i = 0; i < m->nv; i++) {
+    double x0 = (double)(float)v0[i], x1 = (double)(float)v1[i];
+    qvel[i] = x0 + a*(x1 - x0);
+  }
+  if (phase) *phase = ph;
+}
+
+/* frame coordinate of env e `extra` env steps after its current step count (phase_mode 1) */
+static double env_frame_coord(const dmb_model_t* m, const dmb_mocap_t* mc, const dmo_env_t* e, int extra) {
+  double rate = m->timestep/mc->clip_dt[e->clip];
+  return (double)e->idx_init + (double)(e->ep_len + extra)*rate;
+}
+
+/* reference pose for the reward: phase_mode 0 = table row `frame` of the clip (tables rounded to fp32
+ * as the CUDA path stores them); phase_mode 1 = interpolated at frame coordinate u, with the
+ * end-effector / CoM-velocity features recomputed by forward kinematics of the interpolated pose */
+static void get_reference(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, const dmo_env_t* e,
+                          int frame, double u, double* rq, double* rv, double* aux) {
+  if (cfg->phase_mode == 1) {
+    dmo_mocap_sample(m, mc, e->clip, u, rq, rv, NULL);
+    if (aux) dmo_ref_aux(m, rq, rv, aux);
+    return;
+  }
+  size_t f = (size_t)(mc->clip_start[e->clip] + frame);
   for (int i = 0; i < m->nq; i++) rq[i] = (double)(float)mc->data_config[f*m->nq + i];
   for (int i = 0; i < m->nv; i++) rv[i] = (double)(float)mc->data_vel[f*m->nv + i];
-  for (int i = 0; i < DMB_REF_AUX; i++) aux[i] = (double)(float)mc->ref_aux[f*DMB_REF_AUX + i];
+  if (aux) for (int i = 0; i < DMB_REF_AUX; i++) aux[i] = (double)(float)mc->ref_aux[f*DMB_REF_AUX + i];
+}
+
+static double reward_imitate(const dmb_model_t* m, const dmb_config_t* cfg, dmo_env_t* e, const double* rq,
+                             const double* rv, const double* aux) {
+  dmo_data_t* d = &e->d;
   /* fresh kinematics at the post-step state */
   dmo_kinematics(m, d); com_pos(m, d); com_vel(m, d);
   double ee[3*DMB_MAX_EE], vcom[3];
@@ -1110,6 +1209,44 @@ static double reward_imitate(const dmb_model_t* m, const dmb_config_t* cfg, cons
          cfg->w_root*e->reward_terms[3] + cfg->w_com*e->reward_terms[4];
 }
 
+/* DeepMimic state (obs_mode 1): cCtController::BuildStatePose / BuildStateVel quoted in
+ * /root/reference/code.md:287-504 and the MuJoCo prototype /root/reference/src/mujoco/mujoco_env.py:91-124
+ * (record_state), on the hinge model: [phase, root height, npart x (pos 3, quat 4), npart x (lin vel 3,
+ * ang vel 3)], positions relative to the root and everything rotated into the root heading frame
+ * (BuildOriginTrans); quaternions (w,x,y,z) with w >= 0; z-up component order.  Recomputes the
+ * kinematics of the CURRENT state (post-reset for auto-reset envs). */
+int dmo_env_obs_dm(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, dmo_env_t* e, double* obs) {
+  dmo_data_t* d = &e->d;
+  dmo_kinematics(m, d); com_pos(m, d); com_vel(m, d);
+  const int np = m->npart, len = mc->clip_len[e->clip];
+  double phase;
+  if (cfg->phase_mode == 1) { int cyc, k; double al; phase_split(len, env_frame_coord(m, mc, e, 0), &cyc, &k, &al, &phase); }
+  else phase = (double)e->idx_curr/(double)len;
+  const double* R = d->xmat[1];
+  double heading = atan2(R[3], R[0]), ch = cos(heading), sh = sin(heading);
+  double qhi[4] = {cos(0.5*heading), 0, 0, -sin(0.5*heading)}; /* inverse heading rotation */
+  obs[0] = phase;
+  obs[1] = d->xpos[1][2];
+  for (int p = 0; p < np; p++) {
+    int g = m->part_geom[p], b = m->geom_bodyid[g];
+    double rel[3] = {d->geom_xpos[g][0] - d->xpos[1][0], d->geom_xpos[g][1] - d->xpos[1][1], d->geom_xpos[g][2] - d->xpos[1][2]};
+    double* o = obs + 2 + 7*p;
+    o[0] = ch*rel[0] + sh*rel[1]; o[1] = -sh*rel[0] + ch*rel[1]; o[2] = rel[2];
+    double q[4];
+    mul_quat(q, qhi, d->xquat[b]);
+    double sg = q[0] < 0 ? -1.0 : 1.0;
+    for (int i = 0; i < 4; i++) o[3 + i] = sg*q[i];
+    /* velocity of the part centre: cvel = [omega; v at the c-frame origin (subtree CoM)] */
+    double r[3] = {d->geom_xpos[g][0] - d->com[0], d->geom_xpos[g][1] - d->com[1], d->geom_xpos[g][2] - d->com[2]}, t[3];
+    cross3(t, d->cvel[b], r);
+    double v[3] = {d->cvel[b][3] + t[0], d->cvel[b][4] + t[1], d->cvel[b][5] + t[2]};
+    double* ov = obs + 2 + 7*np + 6*p;
+    ov[0] = ch*v[0] + sh*v[1]; ov[1] = -sh*v[0] + ch*v[1]; ov[2] = v[2];
+    ov[3] = ch*d->cvel[b][0] + sh*d->cvel[b][1]; ov[4] = -sh*d->cvel[b][0] + ch*d->cvel[b][1]; ov[5] = d->cvel[b][2];
+  }
+  return 2 + 13*np;
+}
+
 int dmo_env_step(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, dmo_env_t* e,
                  const double* action, double* obs, double* reward) {
   dmo_data_t* d = &e->d;
@@ -1130,23 +1267,26 @@ int dmo_env_step(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_
   int bad = (d->flags & 4) != 0;
   double zc = d->com[2]; /* stale CoM of the last RK4 stage, as mjData.xipos is after mj_step */
   double rew = 1.0;
+  const int len = mc->clip_len[e->clip];
+  /* phase_mode 1: the reference is sampled at the post-step time for every reward mode */
+  const double u_ref = cfg->phase_mode == 1 ? env_frame_coord(m, mc, e, 1) : 0.0;
+  double rq[DMB_MAX_Q], rv[DMB_MAX_DOF], aux[DMB_REF_AUX];
   if (cfg->reward_mode == 1) {
-    size_t f = (size_t)(mc->clip_start[e->clip] + e->idx_curr);
+    get_reference(m, cfg, mc, e, e->idx_curr, u_ref, rq, rv, NULL);
     double err = 0;
-    for (int j = 0; j < m->nq - 7; j++) err += fabs(d->qpos[7 + j] - (double)(float)mc->data_config[f*m->nq + 7 + j]);
+    for (int j = 0; j < m->nq - 7; j++) err += fabs(d->qpos[7 + j] - rq[7 + j]);
     rew = exp(-err);
-    e->idx_curr = (e->idx_curr + 1) % mc->clip_len[e->clip];
+    e->idx_curr = (e->idx_curr + 1) % len;
   } else if (cfg->reward_mode == 4) {
-    rew = reward_imitate(m, cfg, mc, e);
-    e->idx_curr = (e->idx_curr + 1) % mc->clip_len[e->clip];
+    get_reference(m, cfg, mc, e, e->idx_curr, u_ref, rq, rv, aux);
+    rew = reward_imitate(m, cfg, e, rq, rv, aux);
+    e->idx_curr = (e->idx_curr + 1) % len;
   } else if (cfg->reward_mode == 2 || cfg->reward_mode == 3) {
     /* v2 / v1 rewards: the frame counter advances before the reward is evaluated
      * (dp_env_v2.py:174-183, dp_env_v1.py:143-152); control cost on the raw action */
-    e->idx_curr = (e->idx_curr + 1) % mc->clip_len[e->clip];
-    size_t f = (size_t)(mc->clip_start[e->clip] + e->idx_curr);
-    double rq[DMB_MAX_Q], rv[DMB_MAX_DOF], acs = 0;
-    for (int i = 0; i < m->nq; i++) rq[i] = (double)(float)mc->data_config[f*m->nq + i];
-    for (int i = 0; i < m->nv; i++) rv[i] = (double)(float)mc->data_vel[f*m->nv + i];
+    e->idx_curr = (e->idx_curr + 1) % len;
+    get_reference(m, cfg, mc, e, e->idx_curr, u_ref, rq, rv, NULL);
+    double acs = 0;
     for (int u = 0; u < m->nu; u++) acs += action[u]*action[u];
     if (cfg->reward_mode == 2) { /* exp(-scale_err*scale_pose*|qpos[3:] - ref[3:]|_1) */
       double err = 0;
@@ -1169,6 +1309,11 @@ int dmo_env_step(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_
             cfg->w_root*exp(-cfg->s_err*cfg->s_root*root) - 0.1*acs;
     }
   }
+  if (cfg->phase_mode == 1) { /* idx_curr reports the frame interval of the reference time */
+    int cyc, k; double al, ph;
+    phase_split(len, u_ref, &cyc, &k, &al, &ph);
+    e->idx_curr = k;
+  }
   if (bad) rew = 0;
   int done = bad || zc < cfg->z_min || zc > cfg->z_max;
   if (cfg->term_mode == 1) { /* fall contact: a listed body touches the floor (contacts of the last RK4 stage) */
@@ -1181,14 +1326,14 @@ int dmo_env_step(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_
   *reward = rew;
   if (done && cfg->auto_reset) dmo_env_reset(m, cfg, mc, e, cfg->reset_mode);
   else if (bad) { memcpy(d->qpos, m->qpos0, sizeof(double)*m->nq); memset(d->qvel, 0, sizeof(d->qvel)); memset(d->qacc_warmstart, 0, sizeof(d->qacc_warmstart)); }
-  if (obs) dmo_env_obs(m, e, obs);
+  if (obs) { if (cfg->obs_mode == 1) dmo_env_obs_dm(m, cfg, mc, e, obs); else dmo_env_obs(m, e, obs); }
   return done;
 }
 
 /* CPU baseline loop: random actions a ~ U(-0.5, 0.5)^nu (action_space.sample()), reset on done */
 long dmo_rollout(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, dmo_env_t* e,
                  long nsteps, uint64_t action_seed) {
-  double action[DMB_MAX_U], obs[2*DMB_MAX_DOF], rew;
+  double action[DMB_MAX_U], obs[2 + 13*DMB_MAX_PART + 2*DMB_MAX_DOF], rew;
   uint32_t r[4];
   dmb_config_t c = *cfg;
   c.auto_reset = 1;

@@ -95,6 +95,11 @@ void dmo_env_set_state(const dmb_model_t* m, dmo_env_t* e, const double* qpos, c
 int dmo_env_step(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, dmo_env_t* e,
                  const double* action, double* obs, double* reward);
 void dmo_env_obs(const dmb_model_t* m, const dmo_env_t* e, double* obs);
+/* DeepMimic 197-d state of the current state (obs_mode 1); returns its length 2 + 13*npart */
+int dmo_env_obs_dm(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, dmo_env_t* e, double* obs);
+/* interpolated reference pose at frame coordinate u = t / clip_dt (phase_mode 1) */
+void dmo_mocap_sample(const dmb_model_t* m, const dmb_mocap_t* mc, int clip, double u, double* qpos, double* qvel,
+                      double* phase);
 /* reference-pose extras for one mocap frame (fills DMB_REF_AUX doubles) */
 void dmo_ref_aux(const dmb_model_t* m, const double* qpos, const double* qvel, double* aux);
 /* counter-based RNG shared bit-for-bit with the CUDA kernels */

@@ -95,6 +95,10 @@ def lib():
         L.dmo_env_step.argtypes = [mp, cp, mcp, ep, C.POINTER(f64), C.POINTER(f64), C.POINTER(f64)]
         L.dmo_env_step.restype = C.c_int
         L.dmo_env_obs.argtypes = [mp, ep, C.POINTER(f64)]
+        L.dmo_env_obs_dm.argtypes = [mp, cp, mcp, ep, C.POINTER(f64)]
+        L.dmo_env_obs_dm.restype = C.c_int
+        L.dmo_mocap_sample.argtypes = [mp, mcp, C.c_int, C.c_double, C.POINTER(f64), C.POINTER(f64), C.POINTER(f64)]
+        L.dmo_mocap_sample.restype = None
         L.dmo_ref_aux.argtypes = [mp, C.POINTER(f64), C.POINTER(f64), C.POINTER(f64)]
         L.dmo_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.dmo_rollout.argtypes = [mp, cp, mcp, ep, C.c_long, C.c_uint64]

@@ -21,7 +21,7 @@ def test_library_exports_header_symbols():
     assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.dmb_version() == 1
+    assert L.dmb_version() == 2
     phdr = open(os.path.join(common.ROOT, "include", "dmb_policy.h")).read()
     assert set(re.findall(r"\b(dmb_policy_[a-z_0-9]+)\s*\(", phdr)) == set(lib.POLICY_EXPORTS)
     for name in lib.POLICY_EXPORTS:

@@ -146,12 +146,13 @@ def test_step_airborne_self_contacts(ctx):
     compare_step(ctx, q, v, common.f32(rng.uniform(-0.5, 0.5, (N, 28))), vtol=3e-4)
 
 
-def _env_pair(po, reward_mode, ctrl_mode, motions=("walk",), n=32, seed=5, auto_reset=1, reset_mode=0, term_mode=0):
+def _env_pair(po, reward_mode, ctrl_mode, motions=("walk",), n=32, seed=5, auto_reset=1, reset_mode=0, term_mode=0,
+              phase_mode=0, obs_mode=0):
     from deepmimic_mujoco_b200.model_blob import default_config
     from deepmimic_mujoco_b200.refaux import compute_ref_aux
     from deepmimic_mujoco_b200.sim import BatchedSim, load_motions, make_mocap_struct
     cfg = default_config(reward_mode=reward_mode, ctrl_mode=ctrl_mode, auto_reset=auto_reset, reset_mode=reset_mode,
-                         term_mode=term_mode)
+                         term_mode=term_mode, phase_mode=phase_mode, obs_mode=obs_mode)
     aux = compute_ref_aux(motions) if reward_mode == 4 else None
     clip_ids = torch.arange(n, dtype=torch.int32) % len(motions)
     sim = BatchedSim(n, motions=motions, seed=seed, config=cfg, ref_aux=aux, clip_ids=clip_ids)
@@ -159,27 +160,39 @@ def _env_pair(po, reward_mode, ctrl_mode, motions=("walk",), n=32, seed=5, auto_
     return sim, cfg, mcs, keep, clip_ids
 
 
-@pytest.mark.parametrize("reward_mode,ctrl_mode,term_mode", [(0, 0, 0), (1, 0, 0), (2, 0, 0), (3, 0, 0), (4, 0, 0), (4, 1, 0), (1, 2, 0), (4, 0, 1)])
-def test_env_step_rewards_pd_and_reset(ctx, reward_mode, ctrl_mode, term_mode):
+@pytest.mark.parametrize("reward_mode,ctrl_mode,term_mode,phase_mode,obs_mode",
+                         [(0, 0, 0, 0, 0), (1, 0, 0, 0, 0), (2, 0, 0, 0, 0), (3, 0, 0, 0, 0), (4, 0, 0, 0, 0), (4, 1, 0, 0, 0),
+                          (1, 2, 0, 0, 0), (4, 0, 1, 0, 0),
+                          # time-based phase with lerp/slerp interpolation; DeepMimic 197-d state
+                          (4, 0, 0, 1, 0), (1, 0, 0, 1, 0), (2, 0, 0, 1, 0), (3, 0, 1, 1, 1), (4, 0, 0, 0, 1), (0, 0, 1, 1, 1)])
+def test_env_step_rewards_pd_and_reset(ctx, reward_mode, ctrl_mode, term_mode, phase_mode, obs_mode):
     """Full env step (PD -> RK4 -> reward -> done -> auto reset) for a few consecutive steps vs the
     oracle env; RSI frame indices must be bit-identical (same Philox stream)."""
     _, _, mt, po = ctx
     n = 32
     motions = ("walk", "dance_b", "spinkick")
-    sim, cfg, mcs, keep, clip_ids = _env_pair(po, reward_mode, ctrl_mode, motions, n, term_mode=term_mode)
+    sim, cfg, mcs, keep, clip_ids = _env_pair(po, reward_mode, ctrl_mode, motions, n, term_mode=term_mode,
+                                              phase_mode=phase_mode, obs_mode=obs_mode)
+    odim = 197 if obs_mode == 1 else 56
+    assert sim.obs_dim == odim and tuple(sim.obs.shape) == (n, odim) and tuple(sim.rec.shape) == (n, odim + 2)
     L = po.lib()
     m = common.model()
     envs = [po.DmoEnv() for _ in range(n)]
     for i, e in enumerate(envs):
         L.dmo_env_init(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), 5, i, int(clip_ids[i]))
         L.dmo_env_reset(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), 0)
-    sim.reset()
+    obs_r = sim.reset().double().cpu().numpy()
     gq, gv, _ = sim.get_state()
+    obs_o = np.zeros(256); rew_o = C.c_double()
     for i, e in enumerate(envs):
         assert e.idx_init == int(sim.idx_init[i]) and e.idx_curr == int(sim.idx_curr[i])
         assert np.abs(np.ctypeslib.as_array(e.d.qpos)[: mt.nq] - gq[i]).max() == 0.0
+        if obs_mode == 1:   # post-reset observation, and dmb_get_obs of the stored state
+            L.dmo_env_obs_dm(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), po.dptr(obs_o))
+            assert np.abs(obs_o[:odim] - obs_r[i]).max() < 5e-5 * max(1.0, np.abs(obs_o[:odim]).max()), i
+    if obs_mode == 1:
+        assert np.abs(sim.get_obs().double().cpu().numpy() - obs_r).max() < 1e-6
     rng = np.random.default_rng(9)
-    obs_o = np.zeros(56); rew_o = C.c_double()
     ndone = 0
     for t in range(6 if term_mode == 0 else 14):
         scale = 1.0 if ctrl_mode == 0 else 1.0
@@ -200,7 +213,11 @@ def test_env_step_rewards_pd_and_reset(ctx, reward_mode, ctrl_mode, term_mode):
             assert bool(od) == bool(done[i]), (t, i)
             ndone += int(od)
             assert e.idx_curr == int(sim.idx_curr[i]) and e.idx_init == int(sim.idx_init[i])
-            assert np.abs(obs_o - obs[i]).max() < 2e-4 * max(1.0, np.abs(obs_o).max()), (t, i)
+            assert np.abs(obs_o[:odim] - obs[i]).max() < 2e-4 * max(1.0, np.abs(obs_o[:odim]).max()), (t, i)
+            if obs_mode == 1:
+                assert abs(obs_o[0] - obs[i][0]) < 1e-6   # phase
+        rec = sim.rec.double().cpu().numpy()
+        assert np.array_equal(rec[:, :odim], obs) and np.array_equal(rec[:, odim], rew) and np.array_equal(rec[:, odim + 1], done.astype(float))
     if term_mode == 1:
         assert ndone > 0   # spinkick / dance frames put hands or knees on the floor quickly
     sim.close()
@@ -384,3 +401,47 @@ def test_odd_batch_sizes():
         sim.close()
     for n, (gq, gv) in zip((5, 1), outs[1:]):
         assert np.array_equal(gq, outs[0][0][:n]) and np.array_equal(gv, outs[0][1][:n])
+
+
+@pytest.mark.parametrize("name", ["walk", "spinkick", "dance_b", "run", "backflip"])
+def test_mocap_sample_kernel(name):
+    """dmb_mocap_sample (in-kernel lerp / slerp, fp32) vs the oracle and vs the golden vectors computed with the
+    reference's transformations.quaternion_slerp / euler_from_quaternion (tests/golden/make_interp_golden.py)."""
+    import os
+    import oracle.pyoracle as po
+    from deepmimic_mujoco_b200.sim import BatchedSim, load_motions, make_mocap_struct
+    g = np.load(os.path.join(common.GOLDEN, "mocap_interp.npz"))
+    sim = BatchedSim(4, motions=("walk", name), seed=1)
+    mcs, keep = make_mocap_struct(load_motions(["walk", name]))
+    m = common.model()
+    us, gq, gv = g[name + "_u"], g[name + "_qpos"], g[name + "_qvel"]
+    dt = float(sim.mocap.clip_dt[1])
+    q, v, ph = sim.mocap_sample(us * dt, clip_ids=torch.ones(len(us), dtype=torch.int32))
+    q, v, ph = q.double().cpu().numpy(), v.double().cpu().numpy(), ph.double().cpu().numpy()
+    L = po.lib()
+    oq, ov, oph = np.zeros(40), np.zeros(40), C.c_double()
+    for i, u in enumerate(us):
+        L.dmo_mocap_sample(C.byref(m), C.byref(mcs), 1, float(us[i] * dt / dt), po.dptr(oq), po.dptr(ov), C.byref(oph))
+        # Euler angles near +-pi may differ by 2 pi between fp32 and fp64: compare on the circle
+        dq = q[i] - oq[:35]; dq[7:] = (dq[7:] + np.pi) % (2 * np.pi) - np.pi
+        assert np.abs(dq).max() < 2e-5, (i, u, np.abs(dq).max())
+        assert np.abs(v[i] - ov[:34]).max() < 1e-5 * max(1.0, np.abs(ov[:34]).max())
+        assert abs(ph[i] - oph.value) < 1e-6
+        dg = q[i] - gq[i]; dg[7:] = (dg[7:] + np.pi) % (2 * np.pi) - np.pi
+        assert np.abs(dg).max() < 2e-5 and np.abs(v[i] - gv[i]).max() < 1e-5 * max(1.0, np.abs(gv[i]).max())
+    sim.close()
+
+
+def test_gym_surface_dm_state_and_phase():
+    from deepmimic_mujoco_b200.env import DPEnv
+    env = DPEnv(motion="walk", seed=3, reward_mode=4, phase_mode=1, obs_mode=1)
+    assert env.observation_space.shape == (197,)
+    ob = env.reset()
+    assert ob.shape == (197,) and np.isfinite(ob).all()
+    k0 = env.idx_init
+    rate = env._sim.tables.timestep / env.mocap_dt
+    for t in range(5):
+        ob, r, done, _ = env.step(env.action_space.sample())
+        assert ob.shape == (197,) and 0.0 < r <= 1.0
+        assert env.idx_curr == min(int((k0 + (t + 1) * rate) % 38), 37)
+    env.close()
