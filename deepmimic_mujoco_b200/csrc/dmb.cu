@@ -880,6 +880,18 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
     for (int k = 0; k < c; k++) S.anc_rank[d][S.dof_anc[d][k]] = (uint8_t)k;
     for (int k = 0; k < c; k++) S.anc_rowbase[d][k] = (int16_t)m->dof_Madr[S.dof_anc[d][k]];
     S.dof_Madr[d] = (int16_t)m->dof_Madr[d];
+    S.dof_Lend[d] = (int16_t)(m->dof_Madr[d] + c);
+    for (int k = 0; k < c; k++) S.dof_ancr[d][k] = (uint8_t)S.dof_anc[d][c - 1 - k];
+    if (c > S.maxanc) S.maxanc = c;
+    {  // descendants must be the contiguous id range d+1 .. d+ndesc (depth-first numbering, as MuJoCo compiles it)
+      int nd = 0;
+      for (int e = d + 1; e < m->nv; e++) {
+        bool desc = false;
+        for (int a = m->dof_parentid[e]; a >= 0; a = m->dof_parentid[a]) if (a == d) { desc = true; break; }
+        if (desc) { if (e != d + 1 + nd) { why = "dofs are not numbered depth first"; return DMB_ERR_MODEL; } nd++; }
+      }
+      S.dof_ndesc[d] = (int8_t)nd;
+    }
     S.dof_armature[d] = (float)m->dof_armature[d]; S.dof_damping[d] = (float)m->dof_damping[d];
     S.dof_invw[d] = (float)m->dof_invweight0[d];
     S.dof_act[d] = -1; S.dof_gear[d] = 1.f; S.dof_ctrl_lo[d] = 0.f; S.dof_ctrl_hi[d] = 0.f;

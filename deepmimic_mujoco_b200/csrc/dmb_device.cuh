@@ -138,6 +138,20 @@ __device__ __noinline__ void com_pos(const ModelS& M, EnvS& S, int lane) {
   __syncwarp();
 }
 
+#ifndef DMB_FAST_RCP
+#define DMB_FAST_RCP 1
+#endif
+// reciprocal for pivots / scalings: one MUFU (1 ulp) instead of the correctly rounded sequence
+__device__ __forceinline__ float rcp(float x) {
+#if DMB_FAST_RCP
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#else
+  return __frcp_rn(x);
+#endif
+}
+
 // ------------------------------------------------------------------------------------------
 // mj_crb + mj_factorM: composite inertias (parents gather children, level by level), the
 // nM sparse inertia entries (lane = entry) and the in-place sparse L'DL factorisation.
@@ -184,7 +198,7 @@ __device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, floa
     if (c == 0) continue;
     const int adrk = M.dof_Madr[k];
     const float* rowk = &S.qLD[adrk + 1];
-    const float inv = __frcp_rn(S.qLD[adrk]);
+    const float inv = rcp(S.qLD[adrk]);
     const int npair = c * (c + 1) / 2;
 #pragma unroll
     for (int u = 0; u < 3; u++) {
@@ -199,7 +213,7 @@ __device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, floa
   // L entries = row / pivot; D^-1/2 for the half solves
   for (int e = lane; e < M.nM; e += 32) {
     const int i = M.M_i[e];
-    if (M.M_j[e] != i) S.qLD[e] *= __frcp_rn(S.qLD[M.dof_Madr[i]]);
+    if (M.M_j[e] != i) S.qLD[e] *= rcp(S.qLD[M.dof_Madr[i]]);
   }
   for (int d = lane; d < M.nv; d += 32) S.dsq[d] = rsqrtf(S.qLD[M.dof_Madr[d]]);
   __syncwarp();
@@ -754,6 +768,60 @@ __device__ __noinline__ void make_constraint(const ModelS& M, EnvS& S, int lane)
 // (dof d on lane d & 31, register `lo` for d < 32 and `hi` for d >= 32).  One broadcast shuffle
 // and one FFMA per dof: ~30 cycles of latency per dof instead of a shared-memory round trip.
 // ------------------------------------------------------------------------------------------
+#ifndef DMB_SOLVE_V2
+#define DMB_SOLVE_V2 1
+#endif
+#if DMB_SOLVE_V2
+// Dofs are numbered depth first, so "i is a descendant of a" is the range test a < i <= a + ndesc[a], and
+// L[i][a] sits at qLD[Lend[i] - depth(a)]: no per-(i, a) table lookups.
+// x <- L^-T x   (leaves -> root: dof i, largest id first, pushes its value to its ancestors)
+__device__ __forceinline__ void reg_solve_LT(const ModelS& M, const EnvS& S, int lane, float& lo, float& hi) {
+  const int nv = M.nv;
+  const bool has_lo = lane < nv, has_hi = lane + 32 < nv;
+  const unsigned nd_lo = has_lo ? (unsigned)M.dof_ndesc[lane] : 0u, nd_hi = has_hi ? (unsigned)M.dof_ndesc[lane + 32] : 0u;
+  const float* b_lo = S.qLD - (has_lo ? M.dof_nanc[lane] : 0);
+  const float* b_hi = S.qLD - (has_hi ? M.dof_nanc[lane + 32] : 0);
+  for (int i = nv - 1; i >= 32; i--) {
+    const int e = M.dof_Lend[i];
+    const float xi = __shfl_sync(DMB_FULL, hi, i - 32);
+    if ((unsigned)(i - lane - 1) < nd_lo) lo = fmaf(-b_lo[e], xi, lo);
+    if ((unsigned)(i - lane - 33) < nd_hi) hi = fmaf(-b_hi[e], xi, hi);
+  }
+#pragma unroll 4
+  for (int i = (nv < 32 ? nv : 32) - 1; i >= 1; i--) {
+    const int e = M.dof_Lend[i];
+    const float xi = __shfl_sync(DMB_FULL, lo, i);
+    if ((unsigned)(i - lane - 1) < nd_lo) lo = fmaf(-b_lo[e], xi, lo);
+  }
+}
+// x <- L^-1 x   level-parallel: in round r every dof with more than r ancestors pulls from its ancestor at
+// depth r, whose value has been final since round r-1 (12 rounds instead of nv-1 steps; same summation
+// order as the serial loop).  Dofs >= 32 (two on the humanoid) are finished by warp reductions.
+__device__ __forceinline__ void reg_solve_L(const ModelS& M, const EnvS& S, int lane, float& lo, float& hi) {
+  const int nv = M.nv;
+  const int dl = lane < nv ? lane : 0;
+  const int nd = lane < nv ? M.dof_nanc[dl] : 0;
+  const float* Lp = &S.qLD[M.dof_Lend[dl]];
+  const uint32_t* ap = reinterpret_cast<const uint32_t*>(M.dof_ancr[dl]);
+  static_assert(MAXANC == 12, "three packed words of ancestor ids");
+  const uint32_t aw[3] = {ap[0], ap[1], ap[2]};
+#pragma unroll
+  for (int r = 0; r < MAXANC; r++) {
+    const int src = (int)((aw[r >> 2] >> (8 * (r & 3))) & 0xffu);
+    const float xs = __shfl_sync(DMB_FULL, lo, src);
+    if (r < nd) lo = fmaf(-Lp[-r], xs, lo);
+  }
+  for (int d = 32; d < nv; d++) {
+    const int c = M.dof_nanc[d];
+    const float* Ld = &S.qLD[M.dof_Lend[d]];
+    const int a = lane < c ? M.dof_ancr[d][lane] : 0;
+    const float xl = __shfl_sync(DMB_FULL, lo, a & 31), xh = __shfl_sync(DMB_FULL, hi, a & 31);
+    const float term = lane < c ? Ld[-lane] * (a >= 32 ? xh : xl) : 0.f;
+    const float sum = warp_sum(term);
+    if (lane == d - 32) hi -= sum;
+  }
+}
+#else
 // x <- L^-T x   (leaves -> root: every dof pushes its value to its ancestors).  anc_rank[i][a]
 // is the position of ancestor a in row i of the factor (255 = not an ancestor): one byte load
 // replaces the 64-bit mask arithmetic.
@@ -787,6 +855,7 @@ __device__ __forceinline__ void reg_solve_L(const ModelS& M, const EnvS& S, int 
     hi = fmaf(-Lh, xi, hi);
   }
 }
+#endif
 // z <- D^1/2 L x  (image of an acceleration in the half-solved space), smem in / smem out
 __device__ void mul_L_sqrtD(const ModelS& M, EnvS& S, int lane, const float* x, float* z) {
   for (int i = lane; i < M.nv; i += 32) {
@@ -809,6 +878,11 @@ __device__ void mul_L_sqrtD(const ModelS& M, EnvS& S, int lane, const float* x, 
 __device__ __noinline__ void half_solve_rows(const ModelS& M, EnvS& S, int lane, int nrows) {
   const bool has_lo = lane < M.nv, has_hi = lane + 32 < M.nv;
   const float dlo = has_lo ? S.dsq[lane] : 0.f, dhi = has_hi ? S.dsq[lane + 32] : 0.f;
+#if DMB_SOLVE_V2
+  const unsigned nd_lo = has_lo ? (unsigned)M.dof_ndesc[lane] : 0u, nd_hi = has_hi ? (unsigned)M.dof_ndesc[lane + 32] : 0u;
+  const float* Lb_lo = S.qLD - (has_lo ? M.dof_nanc[lane] : 0);
+  const float* Lb_hi = S.qLD - (has_hi ? M.dof_nanc[lane + 32] : 0);
+#endif
   int r = 0;
   while (r < nrows) {
     const int src = S.e_src[r];
@@ -820,6 +894,42 @@ __device__ __noinline__ void half_solve_rows(const ModelS& M, EnvS& S, int lane,
       if (has_lo) { b_lo = y[YS + lane]; c_lo = y[2 * YS + lane]; }
       if (has_hi) { b_hi = y[YS + lane + 32]; c_hi = y[2 * YS + lane + 32]; }
     }
+#if DMB_SOLVE_V2
+    // support dofs, deepest first: ids >= 32 (they can feed both halves), then ids < 32 (only the low half)
+    const unsigned long long sup64 = S.rowmask[r];
+    unsigned sup_hi = (unsigned)(sup64 >> 32), sup = (unsigned)sup64 & ~1u;   // dof 0 has no ancestors
+    while (sup_hi) {
+      const int ih = 31 - __clz(sup_hi);
+      sup_hi &= ~(1u << ih);
+      const int i = ih + 32, e = M.dof_Lend[i];
+      const float Lv = (unsigned)(i - lane - 1) < nd_lo ? Lb_lo[e] : 0.f;
+      const float Lh = (unsigned)(i - lane - 33) < nd_hi ? Lb_hi[e] : 0.f;
+      const float xa = __shfl_sync(DMB_FULL, a_hi, ih);
+      a_lo = fmaf(-Lv, xa, a_lo); a_hi = fmaf(-Lh, xa, a_hi);
+      if (pyr) {
+        const float xb = __shfl_sync(DMB_FULL, b_hi, ih), xc = __shfl_sync(DMB_FULL, c_hi, ih);
+        b_lo = fmaf(-Lv, xb, b_lo); c_lo = fmaf(-Lv, xc, c_lo);
+        b_hi = fmaf(-Lh, xb, b_hi); c_hi = fmaf(-Lh, xc, c_hi);
+      }
+    }
+    if (pyr) {
+      while (sup) {
+        const int i = 31 - __clz(sup);
+        sup &= ~(1u << i);
+        const float Lv = (unsigned)(i - lane - 1) < nd_lo ? Lb_lo[M.dof_Lend[i]] : 0.f;
+        const float xa = __shfl_sync(DMB_FULL, a_lo, i), xb = __shfl_sync(DMB_FULL, b_lo, i), xc = __shfl_sync(DMB_FULL, c_lo, i);
+        a_lo = fmaf(-Lv, xa, a_lo); b_lo = fmaf(-Lv, xb, b_lo); c_lo = fmaf(-Lv, xc, c_lo);
+      }
+    } else {
+      while (sup) {
+        const int i = 31 - __clz(sup);
+        sup &= ~(1u << i);
+        const float Lv = (unsigned)(i - lane - 1) < nd_lo ? Lb_lo[M.dof_Lend[i]] : 0.f;
+        const float xa = __shfl_sync(DMB_FULL, a_lo, i);
+        a_lo = fmaf(-Lv, xa, a_lo);
+      }
+    }
+#else
     unsigned long long sup = S.rowmask[r];
     while (sup) {
       const int i = 63 - __clzll((long long)sup);
@@ -843,6 +953,7 @@ __device__ __noinline__ void half_solve_rows(const ModelS& M, EnvS& S, int lane,
         a_hi = fmaf(-Lh, xa, a_hi);
       }
     }
+#endif
     a_lo *= dlo; a_hi *= dhi;
     if (pyr) {
       const float mu = S.c_mu[src >> 2];
@@ -982,7 +1093,7 @@ __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, EnvS& S, int lane
     acol[i] = (a0 && i < nefc) ? S.AR[idx] : 0.f;
   }
   const float d0 = a0 ? S.AR[t0 + r0] : 1.f;
-  const float ninv0 = -1.0f / d0;
+  const float ninv0 = -rcp(d0);
   int iter = 0;
   while (iter < M.iterations) {
     float dm0 = 0.f, rm0 = 0.f;

@@ -53,6 +53,12 @@ struct ModelS {
   unsigned long long dof_velmask[NVC];  // dofs summed into the velocity seen by cdof_dot (mj_comVel)
   unsigned long long dof_ancmask[NVC];  // strict ancestors of each dof
   uint8_t anc_rank[NVC][NVC];           // anc_rank[d][a] = k if a is the k-th ancestor of d (nearest first), else 255
+  // depth-first dof numbering: the descendants of dof d are the ids d+1 .. d+dof_ndesc[d]; row d of the factor
+  // stores L[d][a] at qLD[dof_Lend[d] - depth(a)] with dof_Lend[d] = dof_Madr[d] + dof_nanc[d]
+  uint8_t dof_ancr[NVC][MAXANC];        // ancestor of d at depth r (root side first)
+  int8_t dof_ndesc[NVC];
+  int16_t dof_Lend[NVC];
+  int maxanc, pad_a0;
   float dof_armature[NVC], dof_damping[NVC], dof_invw[NVC], dof_gear[NVC], dof_ctrl_lo[NVC], dof_ctrl_hi[NVC];
   float dof_kp[NVC], dof_kd[NVC], dof_weight[NVC];
   // inertia entries
