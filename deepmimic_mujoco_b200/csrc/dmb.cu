@@ -906,6 +906,21 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
     int e = m->dof_Madr[d];
     for (int a = d; a >= 0; a = m->dof_parentid[a]) { S.M_i[e] = (uint8_t)d; S.M_j[e] = (uint8_t)a; e++; }
   }
+  for (int d = 0; d < m->nv; d++) {
+    for (int sft = 0; sft < 4; sft++) {  // 1st, 2nd, 4th, 8th ancestor
+      int a = d;
+      for (int k = 0; k < (1 << sft) && a >= 0; k++) a = m->dof_parentid[a];
+      S.dof_jump[sft][d] = (int8_t)a;
+    }
+    const int j = m->dof_jntid[d];
+    if (S.dof_kind[d] == DOF_HINGE) S.dof_vsrc[d] = (int8_t)m->dof_parentid[d];
+    else if (S.dof_kind[d] == DOF_FREE_ROT) S.dof_vsrc[d] = (int8_t)(m->jnt_dofadr[j] + 2);
+    else S.dof_vsrc[d] = -1;
+    const int b = m->dof_bodyid[d];
+    S.dof_lastof[d] = (int8_t)(d == m->body_dofadr[b] + m->body_dofnum[b] - 1 ? b : -1);
+  }
+  for (int b = 1; b < m->nbody; b++)
+    if (m->body_dofnum[b] < 1) { why = "every moving body needs at least one dof"; return DMB_ERR_MODEL; }
   for (int b = 0; b < m->nbody; b++) {
     unsigned long long mk = 0;
     for (int bb = b; bb > 0; bb = m->body_parent[bb])

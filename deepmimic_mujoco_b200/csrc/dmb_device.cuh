@@ -223,6 +223,88 @@ __device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, floa
 // mj_comVel + mj_rne(flg_acc=0) + passive + actuation: leaves the smooth generalised force
 // qfrc_smooth = passive - bias + actuator in S.vec0.
 // ------------------------------------------------------------------------------------------
+#ifndef DMB_SMOOTH_V2
+#define DMB_SMOOTH_V2 1
+#endif
+#if DMB_SMOOTH_V2
+// Inclusive sums of a spatial 6-vector along the dof ancestor chains, dof d on lane d & 31 (x: d < 32,
+// xh: d >= 32), by pointer jumping: 4 rounds cover chains of up to 16 dofs.
+__device__ __forceinline__ void chain_scan6(const ModelS& M, int lane, int nv, const int (&jmp)[4], float* x, float* xh) {
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const int src = jmp[s];
+#pragma unroll
+    for (int k = 0; k < 6; k++) { const float t = __shfl_sync(DMB_FULL, x[k], src & 31); if (src >= 0) x[k] += t; }
+  }
+  for (int d = 32; d < nv; d++) {  // the few dofs past lane 31 hang off finished sums
+    const int p = M.dof_jump[0][d];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+      const float tl = __shfl_sync(DMB_FULL, x[k], p & 31), th = __shfl_sync(DMB_FULL, xh[k], p & 31);
+      if (lane == d - 32 && p >= 0) xh[k] += p < 32 ? tl : th;
+    }
+  }
+}
+__device__ __noinline__ void smooth_forces(const ModelS& M, EnvS& S, int lane, float* dbg_bias) {
+  const int nv = M.nv;
+  const bool has_lo = lane < nv, has_hi = lane + 32 < nv;
+  const int dl = has_lo ? lane : 0, dh = has_hi ? lane + 32 : 0;
+  const int jmp[4] = {has_lo ? M.dof_jump[0][dl] : -1, has_lo ? M.dof_jump[1][dl] : -1, has_lo ? M.dof_jump[2][dl] : -1,
+                      has_lo ? M.dof_jump[3][dl] : -1};
+  // body velocities: V = chain sum of cdof * qvel (mj_comVel)
+  const float qvl = has_lo ? S.qvel[dl] : 0.f, qvh = has_hi ? S.qvel[dh] : 0.f;
+  float cl[6], ch[6], V[6], Vh[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) { cl[k] = S.cdof[6 * dl + k]; ch[k] = S.cdof[6 * dh + k]; V[k] = cl[k] * qvl; Vh[k] = ch[k] * qvh; }
+  chain_scan6(M, lane, nv, jmp, V, Vh);
+  // cdof_dot[d] = crossMotion(velocity seen by dof d, cdof[d]); A = chain sum of cdof_dot * qvel
+  const int sl = has_lo ? M.dof_vsrc[dl] : -1, sh = has_hi ? M.dof_vsrc[dh] : -1;
+  float E[6], Eh[6], A[6], Ah[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const float t = __shfl_sync(DMB_FULL, V[k], sl & 31);
+    const float tl = __shfl_sync(DMB_FULL, V[k], sh & 31), th = __shfl_sync(DMB_FULL, Vh[k], sh & 31);
+    E[k] = sl >= 0 ? t : 0.f;
+    Eh[k] = sh >= 0 ? (sh < 32 ? tl : th) : 0.f;
+  }
+  cross_motion(A, E, cl);
+  cross_motion(Ah, Eh, ch);
+#pragma unroll
+  for (int k = 0; k < 6; k++) { A[k] = sl >= 0 ? A[k] * qvl : 0.f; Ah[k] = sh >= 0 ? Ah[k] * qvh : 0.f; }
+  chain_scan6(M, lane, nv, jmp, A, Ah);
+  // hand the sums of each body's last dof to the body lanes (velocity -> S.cvel, acceleration -> scratch)
+  float* acc = S.u.a.cdofd;
+  if (lane < 6) S.cvel[lane] = 0.f;
+  const int bl = has_lo ? M.dof_lastof[dl] : -1, bh = has_hi ? M.dof_lastof[dh] : -1;
+  if (bl >= 0) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) { S.cvel[6 * bl + k] = V[k]; acc[6 * bl + k] = A[k]; }
+  }
+  if (bh >= 0) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) { S.cvel[6 * bh + k] = Vh[k]; acc[6 * bh + k] = Ah[k]; }
+  }
+  __syncwarp();
+  // body forces  f = I a + v x* (I v)  with a = -gravity + chain acceleration
+  if (lane < M.nbody) {
+    const int b = lane;
+    float f[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (b > 0) {
+      float v[6], a[6], t1[6], t2[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) { v[k] = S.cvel[6 * b + k]; a[k] = acc[6 * b + k]; }
+      a[3] -= M.gravity[0]; a[4] -= M.gravity[1]; a[5] -= M.gravity[2];
+      mul_inert_vec(f, &S.u.a.cinert[10 * b], a);
+      mul_inert_vec(t1, &S.u.a.cinert[10 * b], v);
+      cross_force(t2, v, t1);
+#pragma unroll
+      for (int k = 0; k < 6; k++) f[k] += t2[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; k++) S.u.a.cfrc[6 * b + k] = f[k];
+  }
+  __syncwarp();
+#else
 __device__ __noinline__ void smooth_forces(const ModelS& M, EnvS& S, int lane, float* dbg_bias) {
   // w[a] = cdof[a] * qvel[a]
   for (int d = lane; d < M.nv; d += 32) {
@@ -277,6 +359,7 @@ __device__ __noinline__ void smooth_forces(const ModelS& M, EnvS& S, int lane, f
     for (int k = 0; k < 6; k++) { S.cvel[6 * b + k] = v[k]; S.u.a.cfrc[6 * b + k] = f[k]; }
   }
   __syncwarp();
+#endif
   for (int lev = M.maxdepth - 1; lev >= 1; lev--) {
     const int b = lane;
     if (b >= 1 && b < M.nbody && M.body_depth[b] == lev) {
@@ -1083,30 +1166,42 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
 #ifndef DMB_PGS_REG
 #define DMB_PGS_REG 1
 #endif
+__device__ __forceinline__ float acol_diag(const EnvS& S, int t0, int r0) { return S.AR[t0 + r0]; }
 __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, EnvS& S, int lane, int nefc, float& f0, float& res0) {
   const int r0 = lane, t0 = tri(r0);
   const bool a0 = r0 < nefc;
   float acol[32];
 #pragma unroll
+  for (int i = 0; i < 32; i++) acol[i] = 0.f;
+#pragma unroll
   for (int i = 0; i < 32; i++) {
-    const int idx = i <= r0 ? t0 + i : tri(i) + r0;
-    acol[i] = (a0 && i < nefc) ? S.AR[idx] : 0.f;
+    if (i >= nefc) break;
+    if (a0) acol[i] = S.AR[i <= r0 ? t0 + i : tri(i) + r0];   // lanes without a row keep a zero column
   }
-  const float d0 = a0 ? S.AR[t0 + r0] : 1.f;
-  const float ninv0 = -rcp(d0);
+  const float ninv0 = a0 ? -rcp(acol_diag(S, t0, r0)) : -1.f;
   int iter = 0;
   while (iter < M.iterations) {
-    float dm0 = 0.f, rm0 = 0.f;
+    // The cost decrease of a whole sweep is  -0.5 (f_end - f_start)' (res_end + res_start)  (res = AR f + b,
+    // AR symmetric): exact like the per-row sum MuJoCo accumulates, without any per-row bookkeeping.
+    const float fs = f0, rs = res0;
 #pragma unroll
-    for (int i = 0; i < 32; i++) {
-      if (i >= nefc) break;
-      const float mine = fmaxf(-f0, res0 * ninv0);
-      const float delta = __shfl_sync(DMB_FULL, mine, i);
-      if (lane == i) { dm0 = mine; rm0 = res0; f0 += mine; }
-      res0 = fmaf(acol[i], delta, res0);
+    for (int i = 0; i < 32; i += 2) {
+      if (i >= nefc) break;   // rows are taken in pairs; a row past nefc has no owner and a zero column
+      {
+        const float mine = fmaxf(-f0, res0 * ninv0);
+        const float delta = __shfl_sync(DMB_FULL, mine, i);
+        if (lane == i) f0 += mine;
+        res0 = fmaf(acol[i], delta, res0);
+      }
+      {
+        const float mine = fmaxf(-f0, res0 * ninv0);
+        const float delta = __shfl_sync(DMB_FULL, mine, i + 1);
+        if (lane == i + 1) f0 += mine;
+        res0 = fmaf(acol[i + 1], delta, res0);
+      }
     }
     iter++;
-    const float imp = warp_sum(-(dm0 * (0.5f * dm0 * d0 + rm0))) * M.pgs_scale;
+    const float imp = warp_sum(-0.5f * (f0 - fs) * (res0 + rs)) * M.pgs_scale;
     if (imp < M.tolerance) break;
   }
   return iter;

@@ -59,6 +59,10 @@ struct ModelS {
   int8_t dof_ndesc[NVC];
   int16_t dof_Lend[NVC];
   int maxanc, pad_a0;
+  // chain prefix sums by pointer jumping: dof_jump[s][d] = the 2^s-th ancestor of dof d (-1: none);
+  // dof_vsrc[d] = dof whose inclusive chain sum is the velocity seen by cdof_dot[d] (mj_comVel; -1: zero);
+  // dof_lastof[d] = body whose last dof is d (-1: d is not the last dof of its body)
+  int8_t dof_jump[4][NVC], dof_vsrc[NVC], dof_lastof[NVC];
   float dof_armature[NVC], dof_damping[NVC], dof_invw[NVC], dof_gear[NVC], dof_ctrl_lo[NVC], dof_ctrl_hi[NVC];
   float dof_kp[NVC], dof_kd[NVC], dof_weight[NVC];
   // inertia entries
