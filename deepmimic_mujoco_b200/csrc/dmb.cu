@@ -32,6 +32,7 @@ struct DevPtrs {
   const float* mocap_cfg;  // [F][nq]
   const float* mocap_vel;  // [F][nv]
   const float* ref_aux;    // [F][DMB_REF_AUX]
+  long long* trace;        // DMB_TRACE=1: [grid][8] globaltimer at kernel start and after each scheduler round
 };
 
 // ---------------------------------------------------------------------------------------
@@ -478,6 +479,12 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
   // barrier and its own pull from the scheduler
   const int gsz = LOCKSTEP ? W / M.ngroups : 1, grp = LOCKSTEP ? warp / gsz : 0, gw = LOCKSTEP ? warp % gsz : 0;
   const int bar_id = 1 + grp, bar_n = gsz * 32;
+  int round = 0;
+  if (P.trace && threadIdx.x == 0) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.trace[blockIdx.x * 8] = t;
+  }
   for (;;) {
     // Scheduling: envs are handed out in order of decreasing constraint work (k_order); a group
     // takes gsz consecutive entries at a time so that its warps see similar work between the
@@ -628,6 +635,11 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
     emit_obs(M, S, clip, idx_init, idx_curr, ep_len, out.obs, out.rec, env, lane);
     store_state(M, S, st, env, lane);
     __syncwarp();
+    if (P.trace && threadIdx.x == 0 && ++round < 8) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      P.trace[blockIdx.x * 8 + round] = t;
+    }
   }
 }
 
@@ -787,6 +799,7 @@ struct dmb_handle_s {
   ModelS* dmodel = nullptr;
   float *d_cfg = nullptr, *d_vel = nullptr, *d_aux = nullptr;
   int *d_counter = nullptr, *d_cost = nullptr, *d_order = nullptr;
+  long long* d_trace = nullptr;
   int grid = 0, block = 0, smem = 0, envs_per_cta = 0;
   int nu = 0, obs_dim = 0;
   int lockstep = 1;
@@ -975,7 +988,7 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
   if (const char* pt = getenv("DMB_PATIENCE")) S.patience = atoi(pt);
   if (const char* cm = getenv("DMB_COST_MODE")) S.cost_mode = atoi(cm);
   if (const char* ak = getenv("DMB_ARRIVE_K")) S.arrive_k = atoi(ak);
-  S.sync_mask = 0x01;  // one barrier per RK stage (sweep on B200: best of 0x7f..0x01)
+  S.sync_mask = 0x41;  // barriers at the start of every RK stage and before the constraint solve (sweep on B200)
   if (const char* sm = getenv("DMB_SYNC_MASK")) S.sync_mask = (int)strtol(sm, nullptr, 0);
   if (mc->nclip < 1 || mc->nclip > DMB_MAX_CLIP) { why = "need 1..16 motion clips"; return DMB_ERR_ARG; }
   for (int k = 0; k < mc->nclip; k++) {
@@ -1086,14 +1099,32 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
     if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
   }
+  if (const char* tr = getenv("DMB_TRACE")) {
+    if (atoi(tr) != 0) {
+      e = cudaMalloc((void**)&h->d_trace, sizeof(long long) * 8 * (size_t)h->grid);
+      if (e == cudaSuccess) e = cudaMemset(h->d_trace, 0, sizeof(long long) * 8 * (size_t)h->grid);
+      if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, cudaGetErrorString(e)); }
+    }
+  }
   *out = h;
   return DMB_OK;
+}
+
+/* DMB_TRACE=1 diagnostics: globaltimer (ns) of every CTA of the last dmb_step at kernel start and after each of
+ * its scheduler rounds, [grid][8] int64 on the host; returns the grid size (0 when tracing is off). */
+int32_t dmb_get_trace(dmb_handle_t h, int64_t* host_out, int32_t max_ctas) {
+  if (!h || !host_out) return DMB_ERR_ARG;
+  if (!h->d_trace) return 0;
+  const int n = h->grid < max_ctas ? h->grid : max_ctas;
+  if (cudaMemcpy(host_out, h->d_trace, sizeof(long long) * 8 * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) return DMB_ERR_CUDA;
+  cudaMemset(h->d_trace, 0, sizeof(long long) * 8 * (size_t)h->grid);
+  return n;
 }
 
 int dmb_destroy(dmb_handle_t h) {
   if (!h) return DMB_ERR_ARG;
   cudaSetDevice(h->device);
-  cudaFree(h->d_counter); cudaFree(h->d_cost); cudaFree(h->d_order); cudaFree(h->dmodel); cudaFree(h->d_cfg); cudaFree(h->d_vel); cudaFree(h->d_aux);
+  cudaFree(h->d_counter); cudaFree(h->d_cost); cudaFree(h->d_order); cudaFree(h->dmodel); cudaFree(h->d_cfg); cudaFree(h->d_vel); cudaFree(h->d_aux); cudaFree(h->d_trace);
   delete h;
   return DMB_OK;
 }
@@ -1102,7 +1133,7 @@ static bool state_ok(const dmb_state_t* st) {
   return st && st->qpos && st->qvel && st->warm && st->clip && st->idx_init && st->idx_curr && st->reset_count &&
          st->ep_len && st->ep_ret && st->flags;
 }
-static DevPtrs devptrs(dmb_handle_t h) { DevPtrs P; P.counter = h->d_counter; P.cost = h->d_cost; P.order = h->d_order; P.model = h->dmodel; P.mocap_cfg = h->d_cfg; P.mocap_vel = h->d_vel; P.ref_aux = h->d_aux; return P; }
+static DevPtrs devptrs(dmb_handle_t h) { DevPtrs P; P.counter = h->d_counter; P.cost = h->d_cost; P.order = h->d_order; P.model = h->dmodel; P.mocap_cfg = h->d_cfg; P.mocap_vel = h->d_vel; P.ref_aux = h->d_aux; P.trace = h->d_trace; return P; }
 
 int dmb_reset(dmb_handle_t h, const dmb_state_t* st, const uint8_t* mask, int32_t mode, float* obs, void* stream) {
   if (!h) return DMB_ERR_ARG;

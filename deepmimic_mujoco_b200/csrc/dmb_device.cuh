@@ -156,6 +156,9 @@ __device__ __forceinline__ float rcp(float x) {
 // mj_crb + mj_factorM: composite inertias (parents gather children, level by level), the
 // nM sparse inertia entries (lane = entry) and the in-place sparse L'DL factorisation.
 // ------------------------------------------------------------------------------------------
+// All shared-memory reads of a step are issued before its writes (values staged in registers): the
+// compiler cannot prove that the tile's arrays do not alias, and a load queued behind an earlier store
+// would serialise the ~30-cycle shared-memory round trips of independent lanes' work.
 __device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, float* dbg_qM) {
   const int b = lane;
   if (lane < M.nbody) {
@@ -166,30 +169,50 @@ __device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, floa
   for (int lev = M.maxdepth - 1; lev >= 1; lev--) {
     if (b >= 1 && b < M.nbody && M.body_depth[b] == lev) {
       const int nc = M.body_nchild[b];
-      for (int c = 0; c < nc; c++) {
-        const int ch = M.body_child[b][c];
+      if (nc > 0) {
+        float acc[10];
 #pragma unroll
-        for (int k = 0; k < 10; k++) S.u.a.crb[10 * b + k] += S.u.a.crb[10 * ch + k];
+        for (int k = 0; k < 10; k++) acc[k] = S.u.a.crb[10 * b + k];
+        for (int c = 0; c < nc; c++) {
+          const int ch = M.body_child[b][c];
+#pragma unroll
+          for (int k = 0; k < 10; k++) acc[k] += S.u.a.crb[10 * ch + k];
+        }
+#pragma unroll
+        for (int k = 0; k < 10; k++) S.u.a.crb[10 * b + k] = acc[k];
       }
     }
     __syncwarp();
   }
   for (int d = lane; d < M.nv; d += 32) mul_inert_vec(&S.u.a.buf6[6 * d], &S.u.a.crb[10 * M.dof_bodyid[d]], &S.cdof[6 * d]);
   __syncwarp();
-  for (int e = lane; e < M.nM; e += 32) {
-    const int i = M.M_i[e], j = M.M_j[e];
-    const float* a = &S.cdof[6 * j];
-    const float* bf = &S.u.a.buf6[6 * i];
-    float s = a[0] * bf[0] + a[1] * bf[1] + a[2] * bf[2] + a[3] * bf[3] + a[4] * bf[4] + a[5] * bf[5];
-    if (i == j) s += M.dof_armature[i];
-    S.qLD[e] = s;
-    if (dbg_qM) dbg_qM[e] = s;
+  constexpr int NR = NMX / 32;  // rounds of 32 inertia entries
+  {
+    float val[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      const int e = lane + 32 * r;
+      val[r] = 0.f;
+      if (e < M.nM) {
+        const int i = M.M_i[e], j = M.M_j[e];
+        const float* a = &S.cdof[6 * j];
+        const float* bf = &S.u.a.buf6[6 * i];
+        float s = a[0] * bf[0] + a[1] * bf[1] + a[2] * bf[2] + a[3] * bf[3] + a[4] * bf[4] + a[5] * bf[5];
+        if (i == j) s += M.dof_armature[i];
+        val[r] = s;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      const int e = lane + 32 * r;
+      if (e < M.nM) { S.qLD[e] = val[r]; if (dbg_qM) dbg_qM[e] = val[r]; }
+    }
   }
   __syncwarp();
   // sparse L'DL (mj_factorM): for k = nv-1..0 eliminate dof k from all its ancestors.  Each lane
   // keeps the (p, q) decode of its <= 3 update slots in registers; anc_rowbase[k][p] is the packed
-  // address of the row of k's p-th ancestor (one table load instead of a dependent pair); rows are
-  // left unscaled during the elimination and divided by their pivot in one parallel pass at the end.
+  // address of the row of k's p-th ancestor; rows are left unscaled during the elimination and divided
+  // by their pivot in one parallel pass at the end.
   int tp[3], tq[3];
 #pragma unroll
   for (int u = 0; u < 3; u++) { const int t = lane + 32 * u; tp[u] = t < 78 ? M.tri_p[t] : 0; tq[u] = t < 78 ? M.tri_q[t] : 0; }
@@ -198,24 +221,56 @@ __device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, floa
     if (c == 0) continue;
     const int adrk = M.dof_Madr[k];
     const float* rowk = &S.qLD[adrk + 1];
-    const float inv = rcp(S.qLD[adrk]);
     const int npair = c * (c + 1) / 2;
-#pragma unroll
-    for (int u = 0; u < 3; u++) {
-      if (lane + 32 * u < npair) {
-        const int p = tp[u], q = tq[u];  // p <= q
-        float* dst = &S.qLD[M.anc_rowbase[k][p] + (q - p)];
-        *dst -= rowk[p] * rowk[q] * inv;
-      }
+    const float piv = S.qLD[adrk];
+    float rp[3], rq[3], dv[3];
+    int da[3];
+#define DMB_LDL_LOAD(u)                                                          \
+    {                                                                              \
+      const bool on = lane + 32 * (u) < npair;                                     \
+      const int p = on ? tp[u] : 0, q = on ? tq[u] : 0;                            \
+      da[u] = M.anc_rowbase[k][p] + (q - p);                                       \
+      rp[u] = rowk[p]; rq[u] = rowk[q]; dv[u] = S.qLD[da[u]];                      \
     }
+#define DMB_LDL_STORE(u) if (lane + 32 * (u) < npair) S.qLD[da[u]] = fmaf(-(rp[u] * inv), rq[u], dv[u]);
+    if (npair <= 32) {
+      DMB_LDL_LOAD(0)
+      const float inv = rcp(piv);
+      DMB_LDL_STORE(0)
+    } else if (npair <= 64) {
+      DMB_LDL_LOAD(0) DMB_LDL_LOAD(1)
+      const float inv = rcp(piv);
+      DMB_LDL_STORE(0) DMB_LDL_STORE(1)
+    } else {
+      DMB_LDL_LOAD(0) DMB_LDL_LOAD(1) DMB_LDL_LOAD(2)
+      const float inv = rcp(piv);
+      DMB_LDL_STORE(0) DMB_LDL_STORE(1) DMB_LDL_STORE(2)
+    }
+#undef DMB_LDL_LOAD
+#undef DMB_LDL_STORE
     __syncwarp();
   }
-  // L entries = row / pivot; D^-1/2 for the half solves
-  for (int e = lane; e < M.nM; e += 32) {
-    const int i = M.M_i[e];
-    if (M.M_j[e] != i) S.qLD[e] *= rcp(S.qLD[M.dof_Madr[i]]);
-  }
+  // D^-1/2 for the half solves; L entries = row / pivot (1/D = (D^-1/2)^2)
   for (int d = lane; d < M.nv; d += 32) S.dsq[d] = rsqrtf(S.qLD[M.dof_Madr[d]]);
+  __syncwarp();
+  {
+    float val[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      const int e = lane + 32 * r;
+      val[r] = 0.f;
+      if (e < M.nM) {
+        const int i = M.M_i[e];
+        const float sq = S.dsq[i], x = S.qLD[e];
+        val[r] = M.M_j[e] != i ? x * (sq * sq) : x;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      const int e = lane + 32 * r;
+      if (e < M.nM) S.qLD[e] = val[r];
+    }
+  }
   __syncwarp();
 }
 
@@ -364,10 +419,17 @@ __device__ __noinline__ void smooth_forces(const ModelS& M, EnvS& S, int lane, f
     const int b = lane;
     if (b >= 1 && b < M.nbody && M.body_depth[b] == lev) {
       const int nc = M.body_nchild[b];
-      for (int c = 0; c < nc; c++) {
-        const int ch = M.body_child[b][c];
+      if (nc > 0) {
+        float acc[6];
 #pragma unroll
-        for (int k = 0; k < 6; k++) S.u.a.cfrc[6 * b + k] += S.u.a.cfrc[6 * ch + k];
+        for (int k = 0; k < 6; k++) acc[k] = S.u.a.cfrc[6 * b + k];
+        for (int c = 0; c < nc; c++) {
+          const int ch = M.body_child[b][c];
+#pragma unroll
+          for (int k = 0; k < 6; k++) acc[k] += S.u.a.cfrc[6 * ch + k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) S.u.a.cfrc[6 * b + k] = acc[k];
       }
     }
     __syncwarp();
@@ -1166,6 +1228,9 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
 #ifndef DMB_PGS_REG
 #define DMB_PGS_REG 1
 #endif
+#ifndef DMB_PGS_LAG
+#define DMB_PGS_LAG 0
+#endif
 __device__ __forceinline__ float acol_diag(const EnvS& S, int t0, int r0) { return S.AR[t0 + r0]; }
 __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, EnvS& S, int lane, int nefc, float& f0, float& res0) {
   const int r0 = lane, t0 = tri(r0);
@@ -1180,6 +1245,9 @@ __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, EnvS& S, int lane
   }
   const float ninv0 = a0 ? -rcp(acol_diag(S, t0, r0)) : -1.f;
   int iter = 0;
+#if DMB_PGS_LAG
+  float prev_imp = 3.0e38f;
+#endif
   while (iter < M.iterations) {
     // The cost decrease of a whole sweep is  -0.5 (f_end - f_start)' (res_end + res_start)  (res = AR f + b,
     // AR symmetric): exact like the per-row sum MuJoCo accumulates, without any per-row bookkeeping.
@@ -1201,8 +1269,15 @@ __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, EnvS& S, int lane
       }
     }
     iter++;
+#if DMB_PGS_LAG
+    // The 5-shuffle reduction of this sweep's decrease overlaps with the next sweep; the loop stops one sweep
+    // after the decrease fell below the tolerance (one more sweep than MuJoCo's test, never fewer).
+    if (prev_imp < M.tolerance) break;
+    prev_imp = warp_sum(-0.5f * (f0 - fs) * (res0 + rs)) * M.pgs_scale;
+#else
     const float imp = warp_sum(-0.5f * (f0 - fs) * (res0 + rs)) * M.pgs_scale;
     if (imp < M.tolerance) break;
+#endif
   }
   return iter;
 }

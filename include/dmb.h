@@ -124,6 +124,11 @@ int32_t dmb_debug_offset(const char* name);
 /* launch geometry chosen at create time (for DESIGN.md / bench reporting) */
 int dmb_launch_info(dmb_handle_t h, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* envs_per_cta);
 
+/* Diagnostics (DMB_TRACE=1 in the environment at create time): per-CTA timeline of the last dmb_step,
+ * host int64 [grid][8] = globaltimer ns at kernel start and after each scheduler round; returns the number
+ * of CTAs written (0 when tracing is off).  Synchronises the device. */
+int32_t dmb_get_trace(dmb_handle_t h, int64_t* host_out, int32_t max_ctas);
+
 const char* dmb_last_error(dmb_handle_t h);
 
 #ifdef __cplusplus
