@@ -1196,6 +1196,16 @@ int dmb_mocap_sample(dmb_handle_t h, const int32_t* clip, const double* frame_co
 
 int32_t dmb_obs_dim(dmb_handle_t h) { return h ? h->obs_dim : DMB_ERR_ARG; }
 
+#if DMB_PHASE_TIMERS
+/* diagnostic builds only (-DDMB_PHASE_TIMERS=1): read and clear the per-phase cycle counters */
+int32_t dmb_phase_cycles(uint64_t* host_out16) {
+  unsigned long long z[32] = {0};
+  if (cudaMemcpyFromSymbol(host_out16, dmb::g_phase_cycles, sizeof(z)) != cudaSuccess) return DMB_ERR_CUDA;
+  cudaMemcpyToSymbol(dmb::g_phase_cycles, z, sizeof(z));
+  return 32;
+}
+#endif
+
 int dmb_launch_info(dmb_handle_t h, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* envs_per_cta) {
   if (!h) return DMB_ERR_ARG;
   if (grid) *grid = h->grid;

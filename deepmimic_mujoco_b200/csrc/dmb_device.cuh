@@ -11,6 +11,28 @@
 
 namespace dmb {
 
+// DMB_PHASE_TIMERS (diagnostic builds only): lane 0 of every warp adds the clock64 deltas between tick points
+// into g_phase_cycles[i] (see tools/gpu_phase_timers.py)
+#ifndef DMB_PHASE_TIMERS
+#define DMB_PHASE_TIMERS 0
+#endif
+#if DMB_PHASE_TIMERS
+__device__ unsigned long long g_phase_cycles[32];
+__device__ __forceinline__ void dmb_tick(int i, int lane) {
+  __shared__ long long s_tick[32];
+  if (lane == 0) {
+    const long long t = clock64();
+    const int w = threadIdx.x >> 5;
+    if (i > 0) atomicAdd(&g_phase_cycles[i], (unsigned long long)(t - s_tick[w]));
+    s_tick[w] = t;
+  }
+}
+#define DMB_TICK(i) dmb_tick(i, lane)
+#else
+#define DMB_TICK(i) do { } while (0)
+#endif
+
+
 // ------------------------------------------------------------------------------------------
 // mj_kinematics: lane = body, one tree level per round.  Also writes the world-frame hinge
 // axes into cdof[.][0:3] (the angular part of cdof) and the geom poses (lane = geom).
@@ -184,6 +206,7 @@ __device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, floa
     }
     __syncwarp();
   }
+  DMB_TICK(11);
   for (int d = lane; d < M.nv; d += 32) mul_inert_vec(&S.u.a.buf6[6 * d], &S.u.a.crb[10 * M.dof_bodyid[d]], &S.cdof[6 * d]);
   __syncwarp();
   constexpr int NR = NMX / 32;  // rounds of 32 inertia entries
@@ -213,6 +236,7 @@ __device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, floa
   // keeps the (p, q) decode of its <= 3 update slots in registers; anc_rowbase[k][p] is the packed
   // address of the row of k's p-th ancestor; rows are left unscaled during the elimination and divided
   // by their pivot in one parallel pass at the end.
+  DMB_TICK(12);
   int tp[3], tq[3];
 #pragma unroll
   for (int u = 0; u < 3; u++) { const int t = lane + 32 * u; tp[u] = t < 78 ? M.tri_p[t] : 0; tq[u] = t < 78 ? M.tri_q[t] : 0; }
@@ -250,6 +274,7 @@ __device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, floa
 #undef DMB_LDL_STORE
     __syncwarp();
   }
+  DMB_TICK(13);
   // D^-1/2 for the half solves; L entries = row / pivot (1/D = (D^-1/2)^2)
   for (int d = lane; d < M.nv; d += 32) S.dsq[d] = rsqrtf(S.qLD[M.dof_Madr[d]]);
   __syncwarp();
@@ -1313,6 +1338,7 @@ __device__ __noinline__ void solve_constraints(const ModelS& M, EnvS& S, int lan
     float cost = f0 * 0.5f * (res0 + b0) + f1 * 0.5f * (res1 + b1);
     cost = warp_sum(cost);
     if (cost > 0.f) { f0 = 0.f; f1 = 0.f; res0 = b0; res1 = b1; }
+    DMB_TICK(14);
 #if DMB_PGS_REG
     iter = nefc > 32 ? pgs_sweeps<true>(M, S, lane, nefc, f0, f1, res0, res1)
                      : pgs_sweeps_reg(M, S, lane, nefc, f0, res0);
@@ -1320,6 +1346,7 @@ __device__ __noinline__ void solve_constraints(const ModelS& M, EnvS& S, int lan
     iter = nefc > 32 ? pgs_sweeps<true>(M, S, lane, nefc, f0, f1, res0, res1)
                      : pgs_sweeps<false>(M, S, lane, nefc, f0, f1, res0, res1);
 #endif
+    DMB_TICK(15);
     if (a0) S.e_f[r0] = f0;
     if (a1) S.e_f[r1] = f1;
     __syncwarp();
@@ -1387,42 +1414,53 @@ template <bool LOCKSTEP>
 __device__ __noinline__ float forward_eval(const ModelS& M, EnvS& S, int lane, float* dbgrow, bool active, int bar_id,
                                          int bar_n, int* arrive) {
 #define DMB_PHASE_SYNC(bit) do { if (LOCKSTEP && (M.sync_mask & (bit))) { if (M.arrive_k > 0) arrival_barrier(arrive, bar_n >> 5, M.arrive_k, lane); else if (M.patience > 0) patient_barrier(arrive, bar_n >> 5, M.patience, lane); else group_barrier(bar_id, bar_n); } } while (0)
+  DMB_TICK(0);
   DMB_PHASE_SYNC(1);
+  DMB_TICK(1);
   if (active) {
     kinematics(M, S, lane);
+    DMB_TICK(16);
     com_pos(M, S, lane);
     if (dbgrow) {
       for (int i = lane; i < M.nbody * 3; i += 32) { dbgrow[dbg::xpos + i] = S.u.a.xpos[i]; dbgrow[dbg::xipos + i] = S.u.a.xipos[i]; }
       for (int i = lane; i < M.nbody * 4; i += 32) dbgrow[dbg::xquat + i] = S.u.a.xquat[i];
     }
   }
+  DMB_TICK(2);
   DMB_PHASE_SYNC(2);
   if (active) crb_factor(M, S, lane, dbgrow ? dbgrow + dbg::qM : nullptr);
+  DMB_TICK(3);
   DMB_PHASE_SYNC(4);
   if (active) {
     smooth_forces(M, S, lane, dbgrow ? dbgrow + dbg::qfrc_bias : nullptr);
+    DMB_TICK(17);
     // y_s = D^-1/2 L^-T qfrc_smooth (registers)
     float lo = lane < M.nv ? S.vec0[lane] : 0.f, hi = lane + 32 < M.nv ? S.vec0[lane + 32] : 0.f;
     reg_solve_LT(M, S, lane, lo, hi);
     if (lane < M.nv) S.ys[lane] = lo * S.dsq[lane];
     if (lane + 32 < M.nv) S.ys[lane + 32] = hi * S.dsq[lane + 32];
   }
+  DMB_TICK(4);
   DMB_PHASE_SYNC(8);
   if (active) {
     geom_poses(M, S, lane);
     collision(M, S, lane);
   }
+  DMB_TICK(5);
   DMB_PHASE_SYNC(16);
   int nefc = 0;
   if (active) {
     make_constraint(M, S, lane);
     nefc = S.nefc;
   }
+  DMB_TICK(6);
   DMB_PHASE_SYNC(32);
   if (active && nefc > 0) {
     half_solve_rows(M, S, lane, nefc);
+    DMB_TICK(7);
     gram(M, S, lane, nefc);
   }
+  DMB_TICK(8);
   if (active && dbgrow) {
     // qacc_smooth = L^-1 D^-1/2 y_s for the dump (not needed by the solver)
     float lo = lane < M.nv ? S.ys[lane] * S.dsq[lane] : 0.f, hi = lane + 32 < M.nv ? S.ys[lane + 32] * S.dsq[lane + 32] : 0.f;
@@ -1439,7 +1477,9 @@ __device__ __noinline__ float forward_eval(const ModelS& M, EnvS& S, int lane, f
     __syncwarp();
   }
   DMB_PHASE_SYNC(64);
+  DMB_TICK(9);
   if (active) solve_constraints(M, S, lane, nefc);
+  DMB_TICK(10);
 #undef DMB_PHASE_SYNC
   return active ? S.com[2] : 0.f;
 }
