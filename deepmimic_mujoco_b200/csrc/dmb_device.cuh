@@ -1268,42 +1268,39 @@ __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, EnvS& S, int lane
     if (i >= nefc) break;
     if (a0) acol[i] = S.AR[i <= r0 ? t0 + i : tri(i) + r0];   // lanes without a row keep a zero column
   }
-  const float ninv0 = a0 ? -rcp(acol_diag(S, t0, r0)) : -1.f;
+  // Rows are kept scaled by -1/AR_ii (sres = -res / AR_ii, scaled column acol * -1/AR_ii), so the increment is
+  // max(-f, sres) and the serial chain per row is FMNMX -> SHFL -> FFMA.
+  const float d0 = a0 ? acol_diag(S, t0, r0) : 1.f;
+  const float ninv0 = -rcp(d0);
+#pragma unroll
+  for (int i = 0; i < 32; i++) acol[i] *= ninv0;
+  float sres = res0 * ninv0;
   int iter = 0;
-#if DMB_PGS_LAG
-  float prev_imp = 3.0e38f;
-#endif
   while (iter < M.iterations) {
     // The cost decrease of a whole sweep is  -0.5 (f_end - f_start)' (res_end + res_start)  (res = AR f + b,
     // AR symmetric): exact like the per-row sum MuJoCo accumulates, without any per-row bookkeeping.
-    const float fs = f0, rs = res0;
+    const float fs = f0, ss = sres;
 #pragma unroll
     for (int i = 0; i < 32; i += 2) {
       if (i >= nefc) break;   // rows are taken in pairs; a row past nefc has no owner and a zero column
       {
-        const float mine = fmaxf(-f0, res0 * ninv0);
+        const float mine = fmaxf(-f0, sres);
         const float delta = __shfl_sync(DMB_FULL, mine, i);
         if (lane == i) f0 += mine;
-        res0 = fmaf(acol[i], delta, res0);
+        sres = fmaf(acol[i], delta, sres);
       }
       {
-        const float mine = fmaxf(-f0, res0 * ninv0);
+        const float mine = fmaxf(-f0, sres);
         const float delta = __shfl_sync(DMB_FULL, mine, i + 1);
         if (lane == i + 1) f0 += mine;
-        res0 = fmaf(acol[i + 1], delta, res0);
+        sres = fmaf(acol[i + 1], delta, sres);
       }
     }
     iter++;
-#if DMB_PGS_LAG
-    // The 5-shuffle reduction of this sweep's decrease overlaps with the next sweep; the loop stops one sweep
-    // after the decrease fell below the tolerance (one more sweep than MuJoCo's test, never fewer).
-    if (prev_imp < M.tolerance) break;
-    prev_imp = warp_sum(-0.5f * (f0 - fs) * (res0 + rs)) * M.pgs_scale;
-#else
-    const float imp = warp_sum(-0.5f * (f0 - fs) * (res0 + rs)) * M.pgs_scale;
+    const float imp = warp_sum(0.5f * d0 * (f0 - fs) * (sres + ss)) * M.pgs_scale;
     if (imp < M.tolerance) break;
-#endif
   }
+  res0 = -sres * d0;
   return iter;
 }
 
