@@ -894,6 +894,7 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
     for (int k = 0; k < c; k++) S.anc_rowbase[d][k] = (int16_t)m->dof_Madr[S.dof_anc[d][k]];
     S.dof_Madr[d] = (int16_t)m->dof_Madr[d];
     S.dof_Lend[d] = (int16_t)(m->dof_Madr[d] + c);
+    S.ldl_meta[d] = (uint32_t)c | ((uint32_t)(c * (c + 1) / 2) << 8) | ((uint32_t)m->dof_Madr[d] << 16);
     for (int k = 0; k < c; k++) S.dof_ancr[d][k] = (uint8_t)S.dof_anc[d][c - 1 - k];
     if (c > S.maxanc) S.maxanc = c;
     {  // descendants must be the contiguous id range d+1 .. d+ndesc (depth-first numbering, as MuJoCo compiles it)

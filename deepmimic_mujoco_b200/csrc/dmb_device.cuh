@@ -237,41 +237,41 @@ __device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, floa
   // address of the row of k's p-th ancestor; rows are left unscaled during the elimination and divided
   // by their pivot in one parallel pass at the end.
   DMB_TICK(12);
+  // Per-lane constants of the (p, q) slots; per-step constants come packed in one word (ldl_meta).  Lanes whose
+  // slot lies outside the step's pair range still load (their p, q address valid words of the tile) and skip the store.
   int tp[3], tq[3];
 #pragma unroll
   for (int u = 0; u < 3; u++) { const int t = lane + 32 * u; tp[u] = t < 78 ? M.tri_p[t] : 0; tq[u] = t < 78 ? M.tri_q[t] : 0; }
-  for (int k = M.nv - 1; k >= 0; k--) {
-    const int c = M.dof_nanc[k];
-    if (c == 0) continue;
-    const int adrk = M.dof_Madr[k];
-    const float* rowk = &S.qLD[adrk + 1];
-    const int npair = c * (c + 1) / 2;
-    const float piv = S.qLD[adrk];
-    float rp[3], rq[3], dv[3];
-    int da[3];
-#define DMB_LDL_LOAD(u)                                                          \
-    {                                                                              \
-      const bool on = lane + 32 * (u) < npair;                                     \
-      const int p = on ? tp[u] : 0, q = on ? tq[u] : 0;                            \
-      da[u] = M.anc_rowbase[k][p] + (q - p);                                       \
-      rp[u] = rowk[p]; rq[u] = rowk[q]; dv[u] = S.qLD[da[u]];                      \
-    }
-#define DMB_LDL_STORE(u) if (lane + 32 * (u) < npair) S.qLD[da[u]] = fmaf(-(rp[u] * inv), rq[u], dv[u]);
+  const int qmp0 = tq[0] - tp[0], qmp1 = tq[1] - tp[1], qmp2 = tq[2] - tp[2];
+  for (int k = M.nv - 1; k >= 1; k--) {
+    const unsigned meta = M.ldl_meta[k];
+    const int npair = (int)((meta >> 8) & 0xffu);
+    if (npair == 0) continue;
+    const float* rowk = &S.qLD[(meta >> 16) + 1];
+    const int16_t* rb = M.anc_rowbase[k];
+    const float piv = rowk[-1];
     if (npair <= 32) {
-      DMB_LDL_LOAD(0)
+      const int d0 = rb[tp[0]] + qmp0;
+      const float p0 = rowk[tp[0]], q0 = rowk[tq[0]], v0 = S.qLD[d0];
       const float inv = rcp(piv);
-      DMB_LDL_STORE(0)
+      if (lane < npair) S.qLD[d0] = fmaf(-(p0 * inv), q0, v0);
     } else if (npair <= 64) {
-      DMB_LDL_LOAD(0) DMB_LDL_LOAD(1)
+      const int d0 = rb[tp[0]] + qmp0, d1 = rb[tp[1]] + qmp1;
+      const float p0 = rowk[tp[0]], q0 = rowk[tq[0]], v0 = S.qLD[d0];
+      const float p1 = rowk[tp[1]], q1 = rowk[tq[1]], v1 = S.qLD[d1];
       const float inv = rcp(piv);
-      DMB_LDL_STORE(0) DMB_LDL_STORE(1)
+      S.qLD[d0] = fmaf(-(p0 * inv), q0, v0);
+      if (lane + 32 < npair) S.qLD[d1] = fmaf(-(p1 * inv), q1, v1);
     } else {
-      DMB_LDL_LOAD(0) DMB_LDL_LOAD(1) DMB_LDL_LOAD(2)
+      const int d0 = rb[tp[0]] + qmp0, d1 = rb[tp[1]] + qmp1, d2 = rb[tp[2]] + qmp2;
+      const float p0 = rowk[tp[0]], q0 = rowk[tq[0]], v0 = S.qLD[d0];
+      const float p1 = rowk[tp[1]], q1 = rowk[tq[1]], v1 = S.qLD[d1];
+      const float p2 = rowk[tp[2]], q2 = rowk[tq[2]], v2 = S.qLD[d2];
       const float inv = rcp(piv);
-      DMB_LDL_STORE(0) DMB_LDL_STORE(1) DMB_LDL_STORE(2)
+      S.qLD[d0] = fmaf(-(p0 * inv), q0, v0);
+      S.qLD[d1] = fmaf(-(p1 * inv), q1, v1);
+      if (lane + 64 < npair) S.qLD[d2] = fmaf(-(p2 * inv), q2, v2);
     }
-#undef DMB_LDL_LOAD
-#undef DMB_LDL_STORE
     __syncwarp();
   }
   DMB_TICK(13);

@@ -59,6 +59,7 @@ struct ModelS {
   int8_t dof_ndesc[NVC];
   int16_t dof_Lend[NVC];
   int maxanc, pad_a0;
+  uint32_t ldl_meta[NVC];               // L'DL step k: chain length | pair count << 8 | row address << 16
   // chain prefix sums by pointer jumping: dof_jump[s][d] = the 2^s-th ancestor of dof d (-1: none);
   // dof_vsrc[d] = dof whose inclusive chain sum is the velocity seen by cdof_dot[d] (mj_comVel; -1: zero);
   // dof_lastof[d] = body whose last dof is d (-1: d is not the last dof of its body)
