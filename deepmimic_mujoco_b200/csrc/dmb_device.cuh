@@ -1151,33 +1151,37 @@ __device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
 __device__ __noinline__ void gram(const ModelS& M, EnvS& S, int lane, int nefc) {
   const int npair = tri(nefc), ntask = npair + nefc;
   for (int t = lane; t < ntask; t += 32) {
+    // one loop for both kinds of task (a lane with a matrix entry and a lane with an entry of b would otherwise
+    // run two loops one after the other): dot product of row r with row c, or with y_s
+    int r, c = 0;
+    const float* z = S.ys;
+    unsigned long long mk;
     if (t < npair) {
-      int r = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+      r = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
       if (tri(r + 1) <= t) r++;
       if (tri(r) > t) r--;
-      const int c = t - tri(r);
-      const float* yr = &S.u.Y[r * YS];
-      const float* yc = &S.u.Y[c * YS];
-      unsigned long long mk = S.rowmask[r] & S.rowmask[c];
-      float acc = 0.f;
-      while (mk) {
-        const int k = __ffsll((long long)mk) - 1;
-        mk &= mk - 1;
-        acc += yr[k] * yc[k];
-      }
-      S.AR[t] = (c == r) ? acc + S.e_R[r] : acc;
+      c = t - tri(r);
+      z = &S.u.Y[c * YS];
+      mk = S.rowmask[r] & S.rowmask[c];
     } else {
-      const int r = t - npair;
-      const float* yr = &S.u.Y[r * YS];
-      unsigned long long mk = S.rowmask[r];
-      float acc = 0.f;
-      while (mk) {
-        const int k = __ffsll((long long)mk) - 1;
-        mk &= mk - 1;
-        acc += yr[k] * S.ys[k];
-      }
-      S.e_b[r] = acc - S.e_aref[r];
+      r = t - npair;
+      mk = S.rowmask[r];
     }
+    const float* yr = &S.u.Y[r * YS];
+    float acc = 0.f;
+    unsigned lo = (unsigned)mk, hi = (unsigned)(mk >> 32);
+    while (hi) {  // dofs >= 32
+      const int k = 31 - __clz(hi);
+      hi ^= 1u << k;
+      acc = fmaf(yr[32 + k], z[32 + k], acc);
+    }
+    while (lo) {
+      const int k = 31 - __clz(lo);
+      lo ^= 1u << k;
+      acc = fmaf(yr[k], z[k], acc);
+    }
+    if (t < npair) S.AR[t] = (c == r) ? acc + S.e_R[r] : acc;
+    else S.e_b[r] = acc - S.e_aref[r];
   }
   __syncwarp();
 }
