@@ -871,6 +871,9 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
     for (int k = 0; k < 3; k++) S.jnt_axis[j][k] = (float)m->jnt_axis[j][k];
     S.jnt_range[j][0] = (float)m->jnt_range[j][0]; S.jnt_range[j][1] = (float)m->jnt_range[j][1];
     S.jnt_qpos0[j] = m->jnt_type[j] == DMB_JNT_HINGE ? (float)m->qpos0[m->jnt_qposadr[j]] : 0.f;
+    if (m->jnt_type[j] == DMB_JNT_FREE && m->body_parent[m->jnt_bodyid[j]] != 0) {
+      why = "free joints are only supported on top-level bodies"; return DMB_ERR_MODEL;
+    }
     if (m->jnt_type[j] == DMB_JNT_HINGE && m->jnt_qposadr[j] != m->jnt_dofadr[j] + 1) {
       why = "hinge qpos/dof addressing must be qposadr == dofadr + 1 (single leading free joint)"; return DMB_ERR_MODEL;
     }
@@ -933,6 +936,13 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
     const int b = m->dof_bodyid[d];
     S.dof_lastof[d] = (int8_t)(d == m->body_dofadr[b] + m->body_dofnum[b] - 1 ? b : -1);
   }
+  if (maxdepth > 8) { why = "body tree deeper than 8"; return DMB_ERR_MODEL; }
+  for (int b = 0; b < m->nbody; b++)
+    for (int sft = 0; sft < 3; sft++) {
+      int a = b;
+      for (int k = 0; k < (1 << sft) && a > 0; k++) a = m->body_parent[a];
+      S.body_jump[sft][b] = (int8_t)(b > 0 && a > 0 ? a : -1);
+    }
   for (int b = 1; b < m->nbody; b++)
     if (m->body_dofnum[b] < 1) { why = "every moving body needs at least one dof"; return DMB_ERR_MODEL; }
   for (int b = 0; b < m->nbody; b++) {

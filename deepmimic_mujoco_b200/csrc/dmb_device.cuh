@@ -37,6 +37,94 @@ __device__ __forceinline__ void dmb_tick(int i, int lane) {
 // mj_kinematics: lane = body, one tree level per round.  Also writes the world-frame hinge
 // axes into cdof[.][0:3] (the angular part of cdof) and the geom poses (lane = geom).
 // ------------------------------------------------------------------------------------------
+#ifndef DMB_KIN_V2
+#define DMB_KIN_V2 1
+#endif
+#if DMB_KIN_V2
+// rotate v by the unit quaternion q:  v + 2 w (u x v) + 2 u x (u x v)
+__device__ __forceinline__ V3 qrotv(Q4 q, V3 v) {
+  const V3 u = v3(q.x, q.y, q.z);
+  const V3 t = 2.f * cross(u, v);
+  return v + q.w * t + cross(u, t);
+}
+// Pose composition is associative, so the world poses are a prefix "sum" of the local transforms along the body
+// chains: local (body_pos, body_quat * hinges), then log2(depth) rounds of pointer jumping, lane = body.  The
+// world-frame hinge axes follow from the final body quaternion by peeling the hinges off again (an axis is
+// invariant under its own hinge rotation).
+__device__ __noinline__ void kinematics(const ModelS& M, EnvS& S, int lane) {
+  const int b = lane;
+  const bool act = b >= 1 && b < M.nbody;
+  const int bb = act ? b : 0;
+  float sn[JPB], cs[JPB];
+  V3 ax[JPB];
+  const int jadr = M.body_jntadr[bb], jnum = act ? M.body_jntnum[bb] : 0;
+  V3 pos = ld3(M.body_pos[bb]);
+  Q4 quat; quat.w = M.body_quat[bb][0]; quat.x = M.body_quat[bb][1]; quat.y = M.body_quat[bb][2]; quat.z = M.body_quat[bb][3];
+#pragma unroll
+  for (int k = 0; k < JPB; k++) {
+    sn[k] = 0.f; cs[k] = 1.f; ax[k] = v3(1.f, 0.f, 0.f);
+    if (k < jnum) {
+      const int j = jadr + k, qa = M.jnt_qposadr[j];
+      if (M.jnt_type[j] == DMB_JNT_FREE) {
+        pos = v3(S.qpos[qa], S.qpos[qa + 1], S.qpos[qa + 2]);
+        quat.w = S.qpos[qa + 3]; quat.x = S.qpos[qa + 4]; quat.y = S.qpos[qa + 5]; quat.z = S.qpos[qa + 6];
+        quat = qnormalize(quat);
+      } else {
+        ax[k] = ld3(M.jnt_axis[j]);
+        sincosf(0.5f * (S.qpos[qa] - M.jnt_qpos0[j]), &sn[k], &cs[k]);
+        Q4 ql; ql.w = cs[k]; ql.x = sn[k] * ax[k].x; ql.y = sn[k] * ax[k].y; ql.z = sn[k] * ax[k].z;
+        quat = qmul(quat, ql);
+      }
+    }
+  }
+  // prefix composition along the chain: (p, q) <- (p_src + R(q_src) p, q_src q); a free joint makes the pose absolute
+  // (free joints only exist on top-level bodies, so nothing is ever composed onto an absolute pose)
+  const int j0 = act ? M.body_jump[0][bb] : -1, j1 = act ? M.body_jump[1][bb] : -1, j2 = act ? M.body_jump[2][bb] : -1;
+#pragma unroll
+  for (int s = 0; s < 3; s++) {
+    if ((1 << s) >= M.maxdepth) break;
+    const int src = s == 0 ? j0 : (s == 1 ? j1 : j2);
+    const float px = __shfl_sync(DMB_FULL, pos.x, src & 31), py = __shfl_sync(DMB_FULL, pos.y, src & 31), pz = __shfl_sync(DMB_FULL, pos.z, src & 31);
+    Q4 qs;
+    qs.w = __shfl_sync(DMB_FULL, quat.w, src & 31); qs.x = __shfl_sync(DMB_FULL, quat.x, src & 31);
+    qs.y = __shfl_sync(DMB_FULL, quat.y, src & 31); qs.z = __shfl_sync(DMB_FULL, quat.z, src & 31);
+    if (src >= 0) {
+      pos = v3(px, py, pz) + qrotv(qs, pos);
+      quat = qmul(qs, quat);
+    }
+  }
+  if (lane == 0) {
+    S.u.a.xpos[0] = S.u.a.xpos[1] = S.u.a.xpos[2] = 0.f;
+    S.u.a.xquat[0] = 1.f; S.u.a.xquat[1] = S.u.a.xquat[2] = S.u.a.xquat[3] = 0.f;
+    S.u.a.xmat[0] = 1.f; S.u.a.xmat[1] = 0.f; S.u.a.xmat[2] = 0.f; S.u.a.xmat[3] = 0.f; S.u.a.xmat[4] = 1.f; S.u.a.xmat[5] = 0.f;
+    S.u.a.xmat[6] = 0.f; S.u.a.xmat[7] = 0.f; S.u.a.xmat[8] = 1.f;
+    S.u.a.xipos[0] = S.u.a.xipos[1] = S.u.a.xipos[2] = 0.f;
+  }
+  if (act) {
+    quat = qnormalize(quat);
+    st3(&S.u.a.xpos[3 * b], pos);
+    S.u.a.xquat[4 * b] = quat.w; S.u.a.xquat[4 * b + 1] = quat.x; S.u.a.xquat[4 * b + 2] = quat.y; S.u.a.xquat[4 * b + 3] = quat.z;
+    float m[9];
+    quat2mat(m, quat);
+#pragma unroll
+    for (int k = 0; k < 9; k++) S.u.a.xmat[9 * b + k] = m[k];
+    st3(&S.u.a.xipos[3 * b], pos + mat_vec(m, ld3(M.body_ipos[b])));
+    // world hinge axes, last joint first: axis_k = R(q after hinge k) a_k, then q <- q * conj(hinge k)
+    Q4 q = quat;
+#pragma unroll
+    for (int k = JPB - 1; k >= 0; k--) {
+      if (k < jnum && M.jnt_type[jadr + k] == DMB_JNT_HINGE) {
+        st3(&S.cdof[6 * M.jnt_dofadr[jadr + k]], qrotv(q, ax[k]));
+        if (k > 0) {
+          Q4 qc; qc.w = cs[k]; qc.x = -sn[k] * ax[k].x; qc.y = -sn[k] * ax[k].y; qc.z = -sn[k] * ax[k].z;
+          q = qmul(q, qc);
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+#else
 __device__ __noinline__ void kinematics(const ModelS& M, EnvS& S, int lane) {
   const int b = lane;
   const bool act = b >= 1 && b < M.nbody;
@@ -98,6 +186,8 @@ __device__ __noinline__ void kinematics(const ModelS& M, EnvS& S, int lane) {
     __syncwarp();
   }
 }
+
+#endif
 
 // ------------------------------------------------------------------------------------------
 // mj_comPos: whole-model CoM (warp-shuffle reduction over bodies), cinert (lane = body),

@@ -64,6 +64,7 @@ struct ModelS {
   // dof_vsrc[d] = dof whose inclusive chain sum is the velocity seen by cdof_dot[d] (mj_comVel; -1: zero);
   // dof_lastof[d] = body whose last dof is d (-1: d is not the last dof of its body)
   int8_t dof_jump[4][NVC], dof_vsrc[NVC], dof_lastof[NVC];
+  int8_t body_jump[3][NB];              // 1st, 2nd, 4th ancestor body of each body (-1: none / world)
   float dof_armature[NVC], dof_damping[NVC], dof_invw[NVC], dof_gear[NVC], dof_ctrl_lo[NVC], dof_ctrl_hi[NVC];
   float dof_kp[NVC], dof_kd[NVC], dof_weight[NVC];
   // inertia entries
