@@ -304,13 +304,15 @@ def run_ours(a):
     for b in h_act:
         b.copy_(torch.rand(E, sim.nu) - 0.5)
     d_act = torch.empty(E, sim.nu, dtype=torch.float32, device=dev)
-    h_rec = torch.empty(n_global if gather is not None else E, sim.obs_dim + 2, dtype=torch.float32).pin_memory()
+    # every rank's host reads the record of ITS OWN envs; the gathered [N,58] record stays on the device
+    h_rec = torch.empty(E, sim.obs_dim + 2, dtype=torch.float32).pin_memory()
 
     def e2e_step(i):
         d_act.copy_(h_act[i % 4], non_blocking=True)
         env.step(d_act)
-        src = gather() if gather is not None else sim.rec
-        h_rec.copy_(src, non_blocking=True)
+        if gather is not None:
+            gather()
+        h_rec.copy_(sim.rec, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the caller consumes obs/reward/done on the host
 
     for i in range(3):
@@ -351,8 +353,8 @@ def run_ours(a):
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "traffic": traffic, "peak_source": peak_src,
                              "note": "compute/latency-bound fp32 kernel: ~1e3 FLOP/B, see DESIGN.md"},
-                "e2e": {"value": n_global * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": E * sim.nu * 4,
-                        "d2h_bytes_per_step": h_rec.numel() * 4},
+                "e2e": {"value": n_global * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": world * E * sim.nu * 4,
+                        "d2h_bytes_per_step": world * h_rec.numel() * 4},   # job totals over all ranks
                 "gpu_launches": 2 * K,  # k_order (scheduler sort) + k_step (fused env step) per step
                 "clocks": clocks}
         if not a.no_cpu_baseline:
