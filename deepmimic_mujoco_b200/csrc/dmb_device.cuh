@@ -11,6 +11,26 @@
 
 namespace dmb {
 
+// The big per-stage phases are folded into the single forward_eval call site (one function body: the compiler
+// keeps addresses and model constants in registers across phases and vectorises shared loads; +10 % on B200).
+// DMB_INLINE_PHASES=0 keeps them out of line; DMB_INLINE_KIN=1 also inlines kinematics / comPos (two call sites).
+#ifndef DMB_INLINE_PHASES
+#define DMB_INLINE_PHASES 1
+#endif
+#ifndef DMB_INLINE_KIN
+#define DMB_INLINE_KIN 0
+#endif
+#if DMB_INLINE_KIN
+#define DMB_KIN_FN __forceinline__
+#else
+#define DMB_KIN_FN __noinline__
+#endif
+#if DMB_INLINE_PHASES
+#define DMB_PHASE_FN __forceinline__
+#else
+#define DMB_PHASE_FN __noinline__
+#endif
+
 // DMB_PHASE_TIMERS (diagnostic builds only): lane 0 of every warp adds the clock64 deltas between tick points
 // into g_phase_cycles[i] (see tools/gpu_phase_timers.py)
 #ifndef DMB_PHASE_TIMERS
@@ -51,7 +71,7 @@ __device__ __forceinline__ V3 qrotv(Q4 q, V3 v) {
 // chains: local (body_pos, body_quat * hinges), then log2(depth) rounds of pointer jumping, lane = body.  The
 // world-frame hinge axes follow from the final body quaternion by peeling the hinges off again (an axis is
 // invariant under its own hinge rotation).
-__device__ __noinline__ void kinematics(const ModelS& M, EnvS& S, int lane) {
+__device__ DMB_KIN_FN void kinematics(const ModelS& M, EnvS& S, int lane) {
   const int b = lane;
   const bool act = b >= 1 && b < M.nbody;
   const int bb = act ? b : 0;
@@ -125,7 +145,7 @@ __device__ __noinline__ void kinematics(const ModelS& M, EnvS& S, int lane) {
   __syncwarp();
 }
 #else
-__device__ __noinline__ void kinematics(const ModelS& M, EnvS& S, int lane) {
+__device__ DMB_KIN_FN void kinematics(const ModelS& M, EnvS& S, int lane) {
   const int b = lane;
   const bool act = b >= 1 && b < M.nbody;
   if (lane == 0) {
@@ -193,7 +213,7 @@ __device__ __noinline__ void kinematics(const ModelS& M, EnvS& S, int lane) {
 // mj_comPos: whole-model CoM (warp-shuffle reduction over bodies), cinert (lane = body),
 // cdof (lane = dof).
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void com_pos(const ModelS& M, EnvS& S, int lane) {
+__device__ DMB_KIN_FN void com_pos(const ModelS& M, EnvS& S, int lane) {
   const int b = lane;
   const bool act = b >= 1 && b < M.nbody;
   float ms = act ? M.body_mass[b] : 0.f;
@@ -271,7 +291,7 @@ __device__ __forceinline__ float rcp(float x) {
 // All shared-memory reads of a step are issued before its writes (values staged in registers): the
 // compiler cannot prove that the tile's arrays do not alias, and a load queued behind an earlier store
 // would serialise the ~30-cycle shared-memory round trips of independent lanes' work.
-__device__ __noinline__ void crb_factor(const ModelS& M, EnvS& S, int lane, float* dbg_qM) {
+__device__ DMB_PHASE_FN void crb_factor(const ModelS& M, EnvS& S, int lane, float* dbg_qM) {
   const int b = lane;
   if (lane < M.nbody) {
 #pragma unroll
@@ -415,7 +435,7 @@ __device__ __forceinline__ void chain_scan6(const ModelS& M, int lane, int nv, c
     }
   }
 }
-__device__ __noinline__ void smooth_forces(const ModelS& M, EnvS& S, int lane, float* dbg_bias) {
+__device__ DMB_PHASE_FN void smooth_forces(const ModelS& M, EnvS& S, int lane, float* dbg_bias) {
   const int nv = M.nv;
   const bool has_lo = lane < nv, has_hi = lane + 32 < nv;
   const int dl = has_lo ? lane : 0, dh = has_hi ? lane + 32 : 0;
@@ -475,7 +495,7 @@ __device__ __noinline__ void smooth_forces(const ModelS& M, EnvS& S, int lane, f
   }
   __syncwarp();
 #else
-__device__ __noinline__ void smooth_forces(const ModelS& M, EnvS& S, int lane, float* dbg_bias) {
+__device__ DMB_PHASE_FN void smooth_forces(const ModelS& M, EnvS& S, int lane, float* dbg_bias) {
   // w[a] = cdof[a] * qvel[a]
   for (int d = lane; d < M.nv; d += 32) {
     const float qv = S.qvel[d];
@@ -786,7 +806,7 @@ __device__ __forceinline__ void make_frame(float* f, V3 n, V3 y) {
 // mj_collision: broad phase (lane = candidate pair, 4 rounds) -> compacted survivor list ->
 // narrow phase (lane = survivor) -> contacts compacted in pair order by warp prefix sums.
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void collision(const ModelS& M, EnvS& S, int lane) {
+__device__ DMB_PHASE_FN void collision(const ModelS& M, EnvS& S, int lane) {
   const float margin = M.margin;
   int nsurv = 0;
   for (int base = 0; base < M.npair; base += 32) {
@@ -888,7 +908,7 @@ __device__ __noinline__ void collision(const ModelS& M, EnvS& S, int lane) {
 // Limit rows come first (joint order, lower then upper), then contacts in contact order:
 // 1 frictionless row (condim 1) or 4 pyramid edges (condim 3).
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void make_constraint(const ModelS& M, EnvS& S, int lane) {
+__device__ DMB_PHASE_FN void make_constraint(const ModelS& M, EnvS& S, int lane) {
   int* e_src = S.e_src;
   // ---- joint limits: lane = joint
   int cnt = 0;
@@ -1135,13 +1155,14 @@ __device__ void mul_L_sqrtD(const ModelS& M, EnvS& S, int lane, const float* x, 
 // are eliminated together (factor entries and index work shared) and then expanded to the four
 // edge rows  n +- mu t1,  n +- mu t2  (the elimination is linear).
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void half_solve_rows(const ModelS& M, EnvS& S, int lane, int nrows) {
+__device__ DMB_PHASE_FN void half_solve_rows(const ModelS& M, EnvS& S, int lane, int nrows) {
   const bool has_lo = lane < M.nv, has_hi = lane + 32 < M.nv;
   const float dlo = has_lo ? S.dsq[lane] : 0.f, dhi = has_hi ? S.dsq[lane + 32] : 0.f;
 #if DMB_SOLVE_V2
   const unsigned nd_lo = has_lo ? (unsigned)M.dof_ndesc[lane] : 0u, nd_hi = has_hi ? (unsigned)M.dof_ndesc[lane + 32] : 0u;
   const float* Lb_lo = S.qLD - (has_lo ? M.dof_nanc[lane] : 0);
   const float* Lb_hi = S.qLD - (has_hi ? M.dof_nanc[lane + 32] : 0);
+  const int16_t* Lend = M.dof_Lend;
 #endif
   int r = 0;
   while (r < nrows) {
@@ -1172,19 +1193,25 @@ __device__ __noinline__ void half_solve_rows(const ModelS& M, EnvS& S, int lane,
         b_hi = fmaf(-Lh, xb, b_hi); c_hi = fmaf(-Lh, xc, c_hi);
       }
     }
+    // (the factor entry is loaded unconditionally -- a non-descendant lane reads some other word of its tile --
+    // and masked afterwards: no divergent branch around the load; bfind gives the top support bit directly)
     if (pyr) {
       while (sup) {
-        const int i = 31 - __clz(sup);
-        sup &= ~(1u << i);
-        const float Lv = (unsigned)(i - lane - 1) < nd_lo ? Lb_lo[M.dof_Lend[i]] : 0.f;
+        int i;
+        asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(sup));
+        sup ^= 1u << i;
+        const float Lraw = Lb_lo[Lend[i]];
+        const float Lv = (unsigned)(i - lane - 1) < nd_lo ? Lraw : 0.f;
         const float xa = __shfl_sync(DMB_FULL, a_lo, i), xb = __shfl_sync(DMB_FULL, b_lo, i), xc = __shfl_sync(DMB_FULL, c_lo, i);
         a_lo = fmaf(-Lv, xa, a_lo); b_lo = fmaf(-Lv, xb, b_lo); c_lo = fmaf(-Lv, xc, c_lo);
       }
     } else {
       while (sup) {
-        const int i = 31 - __clz(sup);
-        sup &= ~(1u << i);
-        const float Lv = (unsigned)(i - lane - 1) < nd_lo ? Lb_lo[M.dof_Lend[i]] : 0.f;
+        int i;
+        asm("bfind.u32 %0, %1;" : "=r"(i) : "r"(sup));
+        sup ^= 1u << i;
+        const float Lraw = Lb_lo[Lend[i]];
+        const float Lv = (unsigned)(i - lane - 1) < nd_lo ? Lraw : 0.f;
         const float xa = __shfl_sync(DMB_FULL, a_lo, i);
         a_lo = fmaf(-Lv, xa, a_lo);
       }
@@ -1238,7 +1265,7 @@ __device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
 // Gram matrix AR = Y Y' + diag(R) (packed lower triangle) and b = Y y_s - aref.
 // lane = matrix entry: the nefc(nefc+1)/2 pairs (+ nefc entries for b) are dealt out 32 at a time;
 // each lane runs the sparse dot product over the intersection of the two row supports.
-__device__ __noinline__ void gram(const ModelS& M, EnvS& S, int lane, int nefc) {
+__device__ DMB_PHASE_FN void gram(const ModelS& M, EnvS& S, int lane, int nefc) {
   const int npair = tri(nefc), ntask = npair + nefc;
   for (int t = lane; t < ntask; t += 32) {
     // one loop for both kinds of task (a lane with a matrix entry and a lane with an entry of b would otherwise
@@ -1401,7 +1428,7 @@ __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, EnvS& S, int lane
 // ------------------------------------------------------------------------------------------
 // mj_fwdConstraint: warmstart + PGS on the dual, then qacc = L^-1 D^-1/2 (y_s + Y' f).
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void solve_constraints(const ModelS& M, EnvS& S, int lane, int nefc) {
+__device__ DMB_PHASE_FN void solve_constraints(const ModelS& M, EnvS& S, int lane, int nefc) {
   int iter = 0;
   if (nefc > 0) {
     const int r0 = lane, r1 = lane + 32;
@@ -1502,7 +1529,7 @@ __device__ __forceinline__ void patient_barrier(int* cnt, int W, int patience, i
 }
 
 template <bool LOCKSTEP>
-__device__ __noinline__ float forward_eval(const ModelS& M, EnvS& S, int lane, float* dbgrow, bool active, int bar_id,
+__device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, float* dbgrow, bool active, int bar_id,
                                          int bar_n, int* arrive) {
 #define DMB_PHASE_SYNC(bit) do { if (LOCKSTEP && (M.sync_mask & (bit))) { if (M.arrive_k > 0) arrival_barrier(arrive, bar_n >> 5, M.arrive_k, lane); else if (M.patience > 0) patient_barrier(arrive, bar_n >> 5, M.patience, lane); else group_barrier(bar_id, bar_n); } } while (0)
   DMB_TICK(0);
