@@ -1381,20 +1381,24 @@ __device__ __forceinline__ float acol_diag(const EnvS& S, int t0, int r0) { retu
 __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, EnvS& S, int lane, int nefc, float& f0, float& res0) {
   const int r0 = lane, t0 = tri(r0);
   const bool a0 = r0 < nefc;
+  // Rows are kept scaled by -1/AR_ii (sres = -res / AR_ii, scaled column acol * -1/AR_ii), so the increment is
+  // max(-f, sres) and the serial chain per row is FMNMX -> SHFL -> FFMA.  The column is fetched in chunks of 8
+  // rows behind a uniform branch (most envs have fewer than 8 rows); lanes without a row keep a zero column.
+  const float d0 = a0 ? acol_diag(S, t0, r0) : 1.f;
+  const float ninv0 = -rcp(d0);
   float acol[32];
 #pragma unroll
   for (int i = 0; i < 32; i++) acol[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; i++) {
-    if (i >= nefc) break;
-    if (a0) acol[i] = S.AR[i <= r0 ? t0 + i : tri(i) + r0];   // lanes without a row keep a zero column
-  }
-  // Rows are kept scaled by -1/AR_ii (sres = -res / AR_ii, scaled column acol * -1/AR_ii), so the increment is
-  // max(-f, sres) and the serial chain per row is FMNMX -> SHFL -> FFMA.
-  const float d0 = a0 ? acol_diag(S, t0, r0) : 1.f;
-  const float ninv0 = -rcp(d0);
+  for (int c = 0; c < 4; c++) {
+    if (8 * c < nefc) {
 #pragma unroll
-  for (int i = 0; i < 32; i++) acol[i] *= ninv0;
+      for (int j = 0; j < 8; j++) {
+        const int i = 8 * c + j;
+        if (a0 && i < nefc) acol[i] = S.AR[i <= r0 ? t0 + i : tri(i) + r0] * ninv0;
+      }
+    }
+  }
   float sres = res0 * ninv0;
   int iter = 0;
   while (iter < M.iterations) {
