@@ -892,8 +892,6 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
       S.dof_anc[d][c++] = (int8_t)a;
     }
     S.dof_nanc[d] = (int8_t)c;
-    for (int a = 0; a < NVC; a++) S.anc_rank[d][a] = 255;
-    for (int k = 0; k < c; k++) S.anc_rank[d][S.dof_anc[d][k]] = (uint8_t)k;
     for (int k = 0; k < c; k++) S.anc_rowbase[d][k] = (int16_t)m->dof_Madr[S.dof_anc[d][k]];
     S.dof_Madr[d] = (int16_t)m->dof_Madr[d];
     S.dof_Lend[d] = (int16_t)(m->dof_Madr[d] + c);
@@ -913,12 +911,6 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
     S.dof_invw[d] = (float)m->dof_invweight0[d];
     S.dof_act[d] = -1; S.dof_gear[d] = 1.f; S.dof_ctrl_lo[d] = 0.f; S.dof_ctrl_hi[d] = 0.f;
     S.dof_weight[d] = (float)m->dof_weight[d];
-    // velocity seen by cdof_dot (mj_comVel): hinge -> all chain ancestors; free rot -> the 3
-    // translational dofs only; free trans -> irrelevant (cdof_dot = 0)
-    unsigned long long mk = 0;
-    if (S.dof_kind[d] == DOF_HINGE) for (int a = m->dof_parentid[d]; a >= 0; a = m->dof_parentid[a]) mk |= 1ull << a;
-    else if (S.dof_kind[d] == DOF_FREE_ROT) for (int k = 0; k < 3; k++) mk |= 1ull << (m->jnt_dofadr[j] + k);
-    S.dof_velmask[d] = mk;
     { unsigned long long am = 0; for (int a = m->dof_parentid[d]; a >= 0; a = m->dof_parentid[a]) am |= 1ull << a; S.dof_ancmask[d] = am; }
     int e = m->dof_Madr[d];
     for (int a = d; a >= 0; a = m->dof_parentid[a]) { S.M_i[e] = (uint8_t)d; S.M_j[e] = (uint8_t)a; e++; }

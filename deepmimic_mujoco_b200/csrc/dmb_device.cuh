@@ -57,10 +57,6 @@ __device__ __forceinline__ void dmb_tick(int i, int lane) {
 // mj_kinematics: lane = body, one tree level per round.  Also writes the world-frame hinge
 // axes into cdof[.][0:3] (the angular part of cdof) and the geom poses (lane = geom).
 // ------------------------------------------------------------------------------------------
-#ifndef DMB_KIN_V2
-#define DMB_KIN_V2 1
-#endif
-#if DMB_KIN_V2
 // rotate v by the unit quaternion q:  v + 2 w (u x v) + 2 u x (u x v)
 __device__ __forceinline__ V3 qrotv(Q4 q, V3 v) {
   const V3 u = v3(q.x, q.y, q.z);
@@ -144,70 +140,6 @@ __device__ DMB_KIN_FN void kinematics(const ModelS& M, EnvS& S, int lane) {
   }
   __syncwarp();
 }
-#else
-__device__ DMB_KIN_FN void kinematics(const ModelS& M, EnvS& S, int lane) {
-  const int b = lane;
-  const bool act = b >= 1 && b < M.nbody;
-  if (lane == 0) {
-    S.u.a.xpos[0] = S.u.a.xpos[1] = S.u.a.xpos[2] = 0.f;
-    S.u.a.xquat[0] = 1.f; S.u.a.xquat[1] = S.u.a.xquat[2] = S.u.a.xquat[3] = 0.f;
-    S.u.a.xmat[0] = 1.f; S.u.a.xmat[1] = 0.f; S.u.a.xmat[2] = 0.f; S.u.a.xmat[3] = 0.f; S.u.a.xmat[4] = 1.f; S.u.a.xmat[5] = 0.f;
-    S.u.a.xmat[6] = 0.f; S.u.a.xmat[7] = 0.f; S.u.a.xmat[8] = 1.f;
-    S.u.a.xipos[0] = S.u.a.xipos[1] = S.u.a.xipos[2] = 0.f;
-  }
-  // half-angle sin/cos of this body's hinge joints (independent of the parent pose)
-  float sn[JPB], cs[JPB];
-  int jadr = 0, jnum = 0, depth = -1;
-  if (act) {
-    jadr = M.body_jntadr[b]; jnum = M.body_jntnum[b]; depth = M.body_depth[b];
-#pragma unroll
-    for (int k = 0; k < JPB; k++) {
-      sn[k] = 0.f; cs[k] = 1.f;
-      if (k < jnum && M.jnt_type[jadr + k] == DMB_JNT_HINGE) {
-        int qa = M.jnt_qposadr[jadr + k];
-        sincosf(0.5f * (S.qpos[qa] - M.jnt_qpos0[jadr + k]), &sn[k], &cs[k]);
-      }
-    }
-  }
-  __syncwarp();
-  for (int lev = 1; lev <= M.maxdepth; lev++) {
-    if (act && depth == lev) {
-      const int p = M.body_parent[b];
-      V3 pos = ld3(&S.u.a.xpos[3 * p]) + mat_vec(&S.u.a.xmat[9 * p], ld3(M.body_pos[b]));
-      Q4 qp; qp.w = S.u.a.xquat[4 * p]; qp.x = S.u.a.xquat[4 * p + 1]; qp.y = S.u.a.xquat[4 * p + 2]; qp.z = S.u.a.xquat[4 * p + 3];
-      Q4 qb; qb.w = M.body_quat[b][0]; qb.x = M.body_quat[b][1]; qb.y = M.body_quat[b][2]; qb.z = M.body_quat[b][3];
-      Q4 quat = qmul(qp, qb);
-#pragma unroll
-      for (int k = 0; k < JPB; k++) {
-        if (k < jnum) {
-          const int j = jadr + k;
-          if (M.jnt_type[j] == DMB_JNT_FREE) {
-            const int qa = M.jnt_qposadr[j];
-            pos = v3(S.qpos[qa], S.qpos[qa + 1], S.qpos[qa + 2]);
-            quat.w = S.qpos[qa + 3]; quat.x = S.qpos[qa + 4]; quat.y = S.qpos[qa + 5]; quat.z = S.qpos[qa + 6];
-            quat = qnormalize(quat);
-          } else {
-            V3 ax = ld3(M.jnt_axis[j]);
-            st3(&S.cdof[6 * M.jnt_dofadr[j]], qrot(quat, ax));
-            Q4 ql; ql.w = cs[k]; ql.x = sn[k] * ax.x; ql.y = sn[k] * ax.y; ql.z = sn[k] * ax.z;
-            quat = qmul(quat, ql);
-          }
-        }
-      }
-      quat = qnormalize(quat);
-      st3(&S.u.a.xpos[3 * b], pos);
-      S.u.a.xquat[4 * b] = quat.w; S.u.a.xquat[4 * b + 1] = quat.x; S.u.a.xquat[4 * b + 2] = quat.y; S.u.a.xquat[4 * b + 3] = quat.z;
-      float m[9];
-      quat2mat(m, quat);
-#pragma unroll
-      for (int k = 0; k < 9; k++) S.u.a.xmat[9 * b + k] = m[k];
-      st3(&S.u.a.xipos[3 * b], pos + mat_vec(m, ld3(M.body_ipos[b])));
-    }
-    __syncwarp();
-  }
-}
-
-#endif
 
 // ------------------------------------------------------------------------------------------
 // mj_comPos: whole-model CoM (warp-shuffle reduction over bodies), cinert (lane = body),
@@ -413,10 +345,6 @@ __device__ DMB_PHASE_FN void crb_factor(const ModelS& M, EnvS& S, int lane, floa
 // mj_comVel + mj_rne(flg_acc=0) + passive + actuation: leaves the smooth generalised force
 // qfrc_smooth = passive - bias + actuator in S.vec0.
 // ------------------------------------------------------------------------------------------
-#ifndef DMB_SMOOTH_V2
-#define DMB_SMOOTH_V2 1
-#endif
-#if DMB_SMOOTH_V2
 // Inclusive sums of a spatial 6-vector along the dof ancestor chains, dof d on lane d & 31 (x: d < 32,
 // xh: d >= 32), by pointer jumping: 4 rounds cover chains of up to 16 dofs.
 __device__ __forceinline__ void chain_scan6(const ModelS& M, int lane, int nv, const int (&jmp)[4], float* x, float* xh) {
@@ -494,62 +422,6 @@ __device__ DMB_PHASE_FN void smooth_forces(const ModelS& M, EnvS& S, int lane, f
     for (int k = 0; k < 6; k++) S.u.a.cfrc[6 * b + k] = f[k];
   }
   __syncwarp();
-#else
-__device__ DMB_PHASE_FN void smooth_forces(const ModelS& M, EnvS& S, int lane, float* dbg_bias) {
-  // w[a] = cdof[a] * qvel[a]
-  for (int d = lane; d < M.nv; d += 32) {
-    const float qv = S.qvel[d];
-#pragma unroll
-    for (int k = 0; k < 6; k++) S.u.a.buf6[6 * d + k] = S.cdof[6 * d + k] * qv;
-  }
-  __syncwarp();
-  // cdof_dot[d] = crossMotion(velocity seen by dof d, cdof[d])
-  for (int d = lane; d < M.nv; d += 32) {
-    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    unsigned long long mk = M.dof_velmask[d];
-    while (mk) {
-      const int a = __ffsll((long long)mk) - 1;
-      mk &= mk - 1;
-#pragma unroll
-      for (int k = 0; k < 6; k++) v[k] += S.u.a.buf6[6 * a + k];
-    }
-    if (M.dof_kind[d] == DOF_FREE_TRANS) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) S.u.a.cdofd[6 * d + k] = 0.f;
-    } else {
-      cross_motion(&S.u.a.cdofd[6 * d], v, &S.cdof[6 * d]);
-    }
-  }
-  __syncwarp();
-  // body velocities and accelerations (sums over the dof chain), body forces
-  if (lane < M.nbody) {
-    const int b = lane;
-    float v[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float a[6] = {0.f, 0.f, 0.f, -M.gravity[0], -M.gravity[1], -M.gravity[2]};
-    unsigned long long mk = M.body_dofmask[b];
-    while (mk) {
-      const int d = __ffsll((long long)mk) - 1;
-      mk &= mk - 1;
-      const float qv = S.qvel[d];
-#pragma unroll
-      for (int k = 0; k < 6; k++) { v[k] += S.u.a.buf6[6 * d + k]; a[k] += S.u.a.cdofd[6 * d + k] * qv; }
-    }
-    float f[6], t1[6], t2[6];
-    if (b == 0) {
-#pragma unroll
-      for (int k = 0; k < 6; k++) { f[k] = 0.f; v[k] = 0.f; }
-    } else {
-      mul_inert_vec(f, &S.u.a.cinert[10 * b], a);
-      mul_inert_vec(t1, &S.u.a.cinert[10 * b], v);
-      cross_force(t2, v, t1);
-#pragma unroll
-      for (int k = 0; k < 6; k++) f[k] += t2[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 6; k++) { S.cvel[6 * b + k] = v[k]; S.u.a.cfrc[6 * b + k] = f[k]; }
-  }
-  __syncwarp();
-#endif
   for (int lev = M.maxdepth - 1; lev >= 1; lev--) {
     const int b = lane;
     if (b >= 1 && b < M.nbody && M.body_depth[b] == lev) {
@@ -1048,10 +920,6 @@ __device__ DMB_PHASE_FN void make_constraint(const ModelS& M, EnvS& S, int lane)
 // (dof d on lane d & 31, register `lo` for d < 32 and `hi` for d >= 32).  One broadcast shuffle
 // and one FFMA per dof: ~30 cycles of latency per dof instead of a shared-memory round trip.
 // ------------------------------------------------------------------------------------------
-#ifndef DMB_SOLVE_V2
-#define DMB_SOLVE_V2 1
-#endif
-#if DMB_SOLVE_V2
 // Dofs are numbered depth first, so "i is a descendant of a" is the range test a < i <= a + ndesc[a], and
 // L[i][a] sits at qLD[Lend[i] - depth(a)]: no per-(i, a) table lookups.
 // x <- L^-T x   (leaves -> root: dof i, largest id first, pushes its value to its ancestors)
@@ -1101,41 +969,6 @@ __device__ __forceinline__ void reg_solve_L(const ModelS& M, const EnvS& S, int 
     if (lane == d - 32) hi -= sum;
   }
 }
-#else
-// x <- L^-T x   (leaves -> root: every dof pushes its value to its ancestors).  anc_rank[i][a]
-// is the position of ancestor a in row i of the factor (255 = not an ancestor): one byte load
-// replaces the 64-bit mask arithmetic.
-__device__ __forceinline__ void reg_solve_LT(const ModelS& M, const EnvS& S, int lane, float& lo, float& hi) {
-  const bool has_hi = lane + 32 < M.nv;
-  for (int i = M.nv - 1; i > 0; i--) {
-    if (M.dof_nanc[i] == 0) continue;
-    // factor entries first (independent of x): the serial chain per dof is one shuffle + one FFMA
-    const float* Lrow = &S.qLD[M.dof_Madr[i] + 1];
-    const unsigned r = M.anc_rank[i][lane];
-    const float Lv = r != 255u ? Lrow[r] : 0.f;
-    float Lh = 0.f;
-    if (i > 32 && has_hi) { const unsigned rh = M.anc_rank[i][lane + 32]; if (rh != 255u) Lh = Lrow[rh]; }
-    const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
-    lo = fmaf(-Lv, xi, lo);
-    hi = fmaf(-Lh, xi, hi);
-  }
-}
-// x <- L^-1 x   (root -> leaves: every dof pulls from its ancestors, one ancestor per step)
-__device__ __forceinline__ void reg_solve_L(const ModelS& M, const EnvS& S, int lane, float& lo, float& hi) {
-  const bool has_lo = lane < M.nv, has_hi = lane + 32 < M.nv;
-  const float* Llo = &S.qLD[has_lo ? M.dof_Madr[lane] + 1 : 0];
-  const float* Lhi = &S.qLD[has_hi ? M.dof_Madr[lane + 32] + 1 : 0];
-  const uint8_t* rlo = M.anc_rank[has_lo ? lane : 0];
-  const uint8_t* rhi = M.anc_rank[has_hi ? lane + 32 : 0];
-  for (int i = 0; i < M.nv - 1; i++) {
-    const unsigned r = has_lo ? rlo[i] : 255u, rh = has_hi ? rhi[i] : 255u;
-    const float Lv = r != 255u ? Llo[r] : 0.f, Lh = rh != 255u ? Lhi[rh] : 0.f;
-    const float xi = __shfl_sync(DMB_FULL, i >= 32 ? hi : lo, i & 31);
-    lo = fmaf(-Lv, xi, lo);
-    hi = fmaf(-Lh, xi, hi);
-  }
-}
-#endif
 // z <- D^1/2 L x  (image of an acceleration in the half-solved space), smem in / smem out
 __device__ void mul_L_sqrtD(const ModelS& M, EnvS& S, int lane, const float* x, float* z) {
   for (int i = lane; i < M.nv; i += 32) {
@@ -1158,12 +991,10 @@ __device__ void mul_L_sqrtD(const ModelS& M, EnvS& S, int lane, const float* x, 
 __device__ DMB_PHASE_FN void half_solve_rows(const ModelS& M, EnvS& S, int lane, int nrows) {
   const bool has_lo = lane < M.nv, has_hi = lane + 32 < M.nv;
   const float dlo = has_lo ? S.dsq[lane] : 0.f, dhi = has_hi ? S.dsq[lane + 32] : 0.f;
-#if DMB_SOLVE_V2
   const unsigned nd_lo = has_lo ? (unsigned)M.dof_ndesc[lane] : 0u, nd_hi = has_hi ? (unsigned)M.dof_ndesc[lane + 32] : 0u;
   const float* Lb_lo = S.qLD - (has_lo ? M.dof_nanc[lane] : 0);
   const float* Lb_hi = S.qLD - (has_hi ? M.dof_nanc[lane + 32] : 0);
   const int16_t* Lend = M.dof_Lend;
-#endif
   int r = 0;
   while (r < nrows) {
     const int src = S.e_src[r];
@@ -1175,7 +1006,6 @@ __device__ DMB_PHASE_FN void half_solve_rows(const ModelS& M, EnvS& S, int lane,
       if (has_lo) { b_lo = y[YS + lane]; c_lo = y[2 * YS + lane]; }
       if (has_hi) { b_hi = y[YS + lane + 32]; c_hi = y[2 * YS + lane + 32]; }
     }
-#if DMB_SOLVE_V2
     // support dofs, deepest first: ids >= 32 (they can feed both halves), then ids < 32 (only the low half)
     const unsigned long long sup64 = S.rowmask[r];
     unsigned sup_hi = (unsigned)(sup64 >> 32), sup = (unsigned)sup64 & ~1u;   // dof 0 has no ancestors
@@ -1216,31 +1046,6 @@ __device__ DMB_PHASE_FN void half_solve_rows(const ModelS& M, EnvS& S, int lane,
         a_lo = fmaf(-Lv, xa, a_lo);
       }
     }
-#else
-    unsigned long long sup = S.rowmask[r];
-    while (sup) {
-      const int i = 63 - __clzll((long long)sup);
-      sup &= ~(1ull << i);
-      if (M.dof_nanc[i] == 0) continue;
-      const float* Lrow = &S.qLD[M.dof_Madr[i] + 1];
-      const unsigned rk = M.anc_rank[i][lane];
-      const float Lv = rk != 255u ? Lrow[rk] : 0.f;
-      float Lh = 0.f;
-      if (i > 32 && has_hi) { const unsigned rh = M.anc_rank[i][lane + 32]; if (rh != 255u) Lh = Lrow[rh]; }
-      const int sl = i & 31;
-      if (pyr) {
-        const float xa = __shfl_sync(DMB_FULL, i >= 32 ? a_hi : a_lo, sl);
-        const float xb = __shfl_sync(DMB_FULL, i >= 32 ? b_hi : b_lo, sl);
-        const float xc = __shfl_sync(DMB_FULL, i >= 32 ? c_hi : c_lo, sl);
-        a_lo = fmaf(-Lv, xa, a_lo); b_lo = fmaf(-Lv, xb, b_lo); c_lo = fmaf(-Lv, xc, c_lo);
-        a_hi = fmaf(-Lh, xa, a_hi); b_hi = fmaf(-Lh, xb, b_hi); c_hi = fmaf(-Lh, xc, c_hi);
-      } else {
-        const float xa = __shfl_sync(DMB_FULL, i >= 32 ? a_hi : a_lo, sl);
-        a_lo = fmaf(-Lv, xa, a_lo);
-        a_hi = fmaf(-Lh, xa, a_hi);
-      }
-    }
-#endif
     a_lo *= dlo; a_hi *= dhi;
     if (pyr) {
       const float mu = S.c_mu[src >> 2];
@@ -1371,12 +1176,6 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
 // row updates with no shared-memory access and no index arithmetic.  The increment is computed as
 // max(-f, -res/AR_ii) (= max(0, f - res/AR_ii) - f without the extra dependent subtraction), so the
 // serial chain per row is FMUL -> FMNMX -> SHFL -> FFMA.
-#ifndef DMB_PGS_REG
-#define DMB_PGS_REG 1
-#endif
-#ifndef DMB_PGS_LAG
-#define DMB_PGS_LAG 0
-#endif
 __device__ __forceinline__ float acol_diag(const EnvS& S, int t0, int r0) { return S.AR[t0 + r0]; }
 __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, EnvS& S, int lane, int nefc, float& f0, float& res0) {
   const int r0 = lane, t0 = tri(r0);
@@ -1461,13 +1260,8 @@ __device__ DMB_PHASE_FN void solve_constraints(const ModelS& M, EnvS& S, int lan
     cost = warp_sum(cost);
     if (cost > 0.f) { f0 = 0.f; f1 = 0.f; res0 = b0; res1 = b1; }
     DMB_TICK(14);
-#if DMB_PGS_REG
     iter = nefc > 32 ? pgs_sweeps<true>(M, S, lane, nefc, f0, f1, res0, res1)
                      : pgs_sweeps_reg(M, S, lane, nefc, f0, res0);
-#else
-    iter = nefc > 32 ? pgs_sweeps<true>(M, S, lane, nefc, f0, f1, res0, res1)
-                     : pgs_sweeps<false>(M, S, lane, nefc, f0, f1, res0, res1);
-#endif
     DMB_TICK(15);
     if (a0) S.e_f[r0] = f0;
     if (a1) S.e_f[r1] = f1;

@@ -50,9 +50,7 @@ struct ModelS {
   int8_t dof_bodyid[NVC], dof_kind[NVC], dof_axisk[NVC], dof_nanc[NVC], dof_anc[NVC][MAXANC], dof_act[NVC];
   int16_t dof_Madr[NVC];
   int16_t anc_rowbase[NVC][MAXANC];     // dof_Madr of the p-th ancestor of each dof
-  unsigned long long dof_velmask[NVC];  // dofs summed into the velocity seen by cdof_dot (mj_comVel)
   unsigned long long dof_ancmask[NVC];  // strict ancestors of each dof
-  uint8_t anc_rank[NVC][NVC];           // anc_rank[d][a] = k if a is the k-th ancestor of d (nearest first), else 255
   // depth-first dof numbering: the descendants of dof d are the ids d+1 .. d+dof_ndesc[d]; row d of the factor
   // stores L[d][a] at qLD[dof_Lend[d] - depth(a)] with dof_Lend[d] = dof_Madr[d] + dof_nanc[d]
   uint8_t dof_ancr[NVC][MAXANC];        // ancestor of d at depth r (root side first)
