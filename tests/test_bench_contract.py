@@ -1,0 +1,35 @@
+"""bench.py contract checks that need no GPU: the reference arm (CPU oracle port on the host cores) prints exactly
+one JSON line on stdout with the keys the driver reads; the GPU arm refuses to run without CUDA."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import common
+
+BENCH = os.path.join(common.ROOT, "bench.py")
+
+
+def test_reference_arm_prints_one_json_line():
+    p = subprocess.run([sys.executable, BENCH, "--impl", "reference", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=common.ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("env steps/sec") and d["unit"] == "env-steps/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 2
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU-only check")
+def test_gpu_arm_fails_loudly_without_cuda():
+    p = subprocess.run([sys.executable, BENCH, "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                       timeout=600, cwd=common.ROOT)
+    assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)

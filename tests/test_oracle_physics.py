@@ -72,6 +72,56 @@ def test_free_flight_momentum():
             assert np.abs(acc - [0, 0, -9.81]).max() < 5e-2
 
 
+def _momenta(o, mt):
+    """Whole-body linear momentum and angular momentum about the CoM from the oracle's body data."""
+    d = o.d
+    com = d.arr("com").copy()
+    P, L = np.zeros(3), np.zeros(3)
+    for b in range(1, mt.nbody):
+        R = np.array(d.arr("xmat")[b]).reshape(3, 3)
+        I = mt.body_inertia[b]
+        Ib = np.array([[I[0], I[3], I[4]], [I[3], I[1], I[5]], [I[4], I[5], I[2]]])
+        w, vl = np.array(d.arr("cvel")[b][:3]), np.array(d.arr("cvel")[b][3:])
+        r = np.array(d.arr("xipos")[b]) - com
+        vb = vl + np.cross(w, r)
+        P += mt.body_mass[b] * vb
+        L += R @ Ib @ R.T @ w + mt.body_mass[b] * np.cross(r, vb)
+    return P, L
+
+
+def test_free_flight_conserves_angular_momentum():
+    """Airborne, arbitrary motor torques, joint damping, joint limits and self-contacts are all internal: the
+    angular momentum about the CoM is conserved and the linear momentum changes by m g t, up to the integration
+    error, which must shrink ~4x when the step is halved (mj_integratePos advances the free-joint quaternion with
+    the combined angular velocity: 2nd order, see test_rk4_convergence_order).  Pins inertia tensors,
+    Coriolis/centrifugal terms and the quaternion integrator independently of MuJoCo."""
+    mt = common.tables()
+    rng = np.random.default_rng(5)
+    q, v = common.airborne_states(rng, 4, frac=0.4, vel=3.0)
+    ctrl = rng.uniform(-0.5, 0.5, (4, mt.nu))
+    T = 0.025
+
+    def drift(i, dt):
+        m = common.model(); m.timestep = dt
+        o = po.Oracle(m)
+        o.set_state(q[i], v[i], ctrl=ctrl[i]); o.forward()
+        P0, L0 = _momenta(o, mt)
+        for _ in range(int(round(T / dt))):
+            o.step()
+        o.forward()
+        assert all(c.geom1 != 0 for c in o.d.contact[: o.d.ncon])       # never touched the floor
+        P1, L1 = _momenta(o, mt)
+        eL = np.abs(L1 - L0).max() / max(1.0, np.abs(L0).max())
+        eP = np.abs(P1 - P0 - mt.body_mass.sum() * np.array([0, 0, -9.81]) * T).max() / max(1.0, np.abs(P0).max())
+        return eL, eP
+
+    for i in range(4):
+        eL1, eP1 = drift(i, 1e-3)
+        eL2, eP2 = drift(i, 5e-4)
+        assert eL1 < 2e-6 and eP1 < 2e-7, (i, eL1, eP1)
+        assert eL2 < eL1 / 3 + 1e-10 and eP2 < eP1 / 3 + 1e-11, (i, eL1, eL2, eP1, eP2)
+
+
 def test_standing_contacts_support_weight():
     mt, o = common.tables(), make()
     qpos = mt.qpos0.copy(); qpos[2] -= 0.0225  # soles 2.5 mm into the floor
