@@ -357,7 +357,7 @@ def run_ours(a):
                         "d2h_bytes_per_step": world * h_rec.numel() * 4},   # job totals over all ranks
                 "gpu_launches": 2 * K,  # k_order (scheduler sort) + k_step (fused env step) per step
                 "clocks": clocks}
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:   # the CPU baseline is reported by the single-GPU run only
             cpu = CpuRollout(1, a.motion, a.reward_mode)
             v, n, w = cpu.run(150000)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
