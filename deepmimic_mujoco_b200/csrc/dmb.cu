@@ -3,14 +3,16 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
 //
 // Kernel design (DESIGN.md has the full account):
-//   * one warp per env, W envs per CTA, persistent grid (<= #SMs CTAs, each warp strides
-//     over envs);
+//   * one warp per env, W envs per CTA, persistent grid (<= #SMs CTAs); CTAs pull W envs at a
+//     time from a queue sorted by last step's constraint work (k_order) and walk the RK stages in
+//     lockstep (one instruction stream per SM);
 //   * the fp32 model tables are staged once per CTA in shared memory; each warp owns an
 //     EnvS tile (qpos/qvel, kinematic tree, sparse inertia factor, contact list, the
 //     half-solved constraint Jacobian Y and the packed Delassus matrix AR) -- per-env state
 //     crosses HBM exactly once per step in each direction (coalesced env-major rows);
-//   * the whole RK4 step (4 forward evaluations incl. collision and PGS), mocap lookup,
-//     reward, termination and auto-reset are fused in this one kernel.
+//   * the whole RK4 step (4 forward evaluations incl. collision and PGS), mocap lookup /
+//     interpolation, reward, termination, auto-reset and the observation (56-d or the 197-d
+//     DeepMimic state) are fused in this one kernel.
 #include <cuda_runtime.h>
 
 #include <cmath>
