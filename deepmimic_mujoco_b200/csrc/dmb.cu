@@ -297,7 +297,8 @@ __device__ __forceinline__ void integrate_pos(const ModelS& M, EnvS& S, int lane
 // registers (dof d on lane d & 31).  forward_eval has a single call site (code size matters:
 // the kernel is instruction-fetch bound).  Returns the CoM height of the last stage evaluation.
 template <bool LOCKSTEP>
-__device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bool active, int bar_id, int bar_n, int* arrive) {
+__device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bool active, int bar_id, int bar_n, int* arrive,
+                                          EnvS* tiles, int* share_cnt) {
   const float h = M.timestep;
   const int d0 = lane, d1 = lane + 32;
   const bool a0 = active && d0 < M.nv, a1 = active && d1 < M.nv;
@@ -316,7 +317,7 @@ __device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bo
       if (active) integrate_pos(M, S, lane, h);
       __syncwarp();
     }
-    zc = forward_eval<LOCKSTEP>(M, S, lane, nullptr, active, bar_id, bar_n, arrive + st);
+    zc = forward_eval<LOCKSTEP>(M, S, lane, nullptr, active, bar_id, bar_n, arrive + st, tiles, share_cnt);
     const float bw = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);
     if (a0) { sv0 += bw * S.qvel[d0]; sa0 += bw * S.qacc[d0]; }
     if (a1) { sv1 += bw * S.qvel[d1]; sa1 += bw * S.qacc[d1]; }
@@ -477,6 +478,12 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
   const int od = M.obs_dim;
   __shared__ int s_base[8];
   __shared__ int s_arrive[4];
+#if DMB_SHARE
+  __shared__ int s_share[2];   // task counters of the CTA-wide work sharing
+  if (threadIdx.x < 2) s_share[threadIdx.x] = 0;
+#else
+  int* const s_share = nullptr;
+#endif
   // lockstep groups: the CTA's warps are split into M.ngroups groups, each with its own named
   // barrier and its own pull from the scheduler
   const int gsz = LOCKSTEP ? W / M.ngroups : 1, grp = LOCKSTEP ? warp / gsz : 0, gw = LOCKSTEP ? warp % gsz : 0;
@@ -514,7 +521,8 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
       bad = state_bad(M, S, lane);
       if (!bad) set_ctrl(M, S, action, env, lane);
     }
-    const float zc = rk4_step<LOCKSTEP>(M, S, lane, have && !bad, bar_id, bar_n, s_arrive);
+    const float zc = rk4_step<LOCKSTEP>(M, S, lane, have && !bad, bar_id, bar_n, s_arrive, tiles,
+                                        (LOCKSTEP && M.ngroups == 1) ? s_share : nullptr);
     if (!have) continue;
     if (!bad) bad = state_bad(M, S, lane);
     // reward (dp_env_v3.py:117 / 89-104).  Reference pose: phase_mode 0 = table row of the integer frame
@@ -762,7 +770,7 @@ __global__ void k_forward_debug(DevPtrs P, dmb_state_t st, const float* __restri
     float* row = dbgout + (size_t)env * dbg::stride;
     for (int i = lane; i < dbg::stride; i += 32) row[i] = 0.f;
     __syncwarp();
-    const float zc = forward_eval<false>(M, S, lane, row, true, 0, 0, nullptr);
+    const float zc = forward_eval<false>(M, S, lane, row, true, 0, 0, nullptr, nullptr, nullptr);
     for (int i = lane; i < M.nbody * 6; i += 32) row[dbg::cvel + i] = S.cvel[i];
     for (int i = lane; i < M.nv; i += 32) row[dbg::qacc + i] = S.qacc[i];
     for (int r = lane; r < S.nefc; r += 32) row[dbg::efc_force + r] = S.e_f[r];

@@ -20,6 +20,10 @@ namespace dmb {
 #ifndef DMB_INLINE_KIN
 #define DMB_INLINE_KIN 0
 #endif
+// DMB_SHARE=1: CTA-wide sharing of the half-solve / Gram work among the warps of a CTA, see forward_eval (+2.4 %)
+#ifndef DMB_SHARE
+#define DMB_SHARE 1
+#endif
 #if DMB_INLINE_KIN
 #define DMB_KIN_FN __forceinline__
 #else
@@ -988,15 +992,15 @@ __device__ void mul_L_sqrtD(const ModelS& M, EnvS& S, int lane, const float* x, 
 // are eliminated together (factor entries and index work shared) and then expanded to the four
 // edge rows  n +- mu t1,  n +- mu t2  (the elimination is linear).
 // ------------------------------------------------------------------------------------------
-__device__ DMB_PHASE_FN void half_solve_rows(const ModelS& M, EnvS& S, int lane, int nrows) {
+__device__ DMB_PHASE_FN void half_solve_rows(const ModelS& M, EnvS& S, int lane, int r_begin, int r_end) {
   const bool has_lo = lane < M.nv, has_hi = lane + 32 < M.nv;
   const float dlo = has_lo ? S.dsq[lane] : 0.f, dhi = has_hi ? S.dsq[lane + 32] : 0.f;
   const unsigned nd_lo = has_lo ? (unsigned)M.dof_ndesc[lane] : 0u, nd_hi = has_hi ? (unsigned)M.dof_ndesc[lane + 32] : 0u;
   const float* Lb_lo = S.qLD - (has_lo ? M.dof_nanc[lane] : 0);
   const float* Lb_hi = S.qLD - (has_hi ? M.dof_nanc[lane + 32] : 0);
   const int16_t* Lend = M.dof_Lend;
-  int r = 0;
-  while (r < nrows) {
+  int r = r_begin;   // r_begin must be the first row of a group (a limit row, a frictionless row or a pyramid)
+  while (r < r_end) {
     const int src = S.e_src[r];
     const bool pyr = src >= 0 && S.c_dim[src >> 2] == 3;
     float* y = &S.u.Y[r * YS];
@@ -1070,9 +1074,9 @@ __device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
 // Gram matrix AR = Y Y' + diag(R) (packed lower triangle) and b = Y y_s - aref.
 // lane = matrix entry: the nefc(nefc+1)/2 pairs (+ nefc entries for b) are dealt out 32 at a time;
 // each lane runs the sparse dot product over the intersection of the two row supports.
-__device__ DMB_PHASE_FN void gram(const ModelS& M, EnvS& S, int lane, int nefc) {
-  const int npair = tri(nefc), ntask = npair + nefc;
-  for (int t = lane; t < ntask; t += 32) {
+__device__ DMB_PHASE_FN void gram(const ModelS& M, EnvS& S, int lane, int nefc, int t_begin, int t_end) {
+  const int npair = tri(nefc), ntask = min(npair + nefc, t_end);
+  for (int t = t_begin + lane; t < ntask; t += 32) {
     // one loop for both kinds of task (a lane with a matrix entry and a lane with an entry of b would otherwise
     // run two loops one after the other): dot product of row r with row c, or with y_s
     int r, c = 0;
@@ -1328,7 +1332,7 @@ __device__ __forceinline__ void patient_barrier(int* cnt, int W, int patience, i
 
 template <bool LOCKSTEP>
 __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, float* dbgrow, bool active, int bar_id,
-                                         int bar_n, int* arrive) {
+                                         int bar_n, int* arrive, EnvS* tiles, int* share_cnt) {
 #define DMB_PHASE_SYNC(bit) do { if (LOCKSTEP && (M.sync_mask & (bit))) { if (M.arrive_k > 0) arrival_barrier(arrive, bar_n >> 5, M.arrive_k, lane); else if (M.patience > 0) patient_barrier(arrive, bar_n >> 5, M.patience, lane); else group_barrier(bar_id, bar_n); } } while (0)
   DMB_TICK(0);
   DMB_PHASE_SYNC(1);
@@ -1370,11 +1374,61 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
     nefc = S.nefc;
   }
   DMB_TICK(6);
-  DMB_PHASE_SYNC(32);
-  if (active && nefc > 0) {
-    half_solve_rows(M, S, lane, nefc);
-    DMB_TICK(7);
-    gram(M, S, lane, nefc);
+#if DMB_SHARE
+  if (LOCKSTEP && share_cnt) {
+    // CTA-wide work sharing of the two phases whose cost scales with the row count: every tile of the
+    // CTA is in shared memory, so any warp can half-solve a row group or compute a chunk of Gram entries of any env.
+    // Tasks are numbered tile by tile and handed out by an atomic counter; warps without an env help too.
+    const int W = bar_n >> 5;
+    if (!active && lane == 0) { S.nefc = 0; S.nlimit = 0; S.ncon = 0; }
+    group_barrier(bar_id, bar_n);                                   // A: the rows of every tile are assembled
+    {
+      int ng = 0, nl = 0;
+      if (lane < W) { nl = tiles[lane].nlimit; ng = tiles[lane].nefc > 0 ? nl + tiles[lane].ncon : 0; }
+      const int incl = warp_incl_scan(ng, lane);
+      const int total = __shfl_sync(DMB_FULL, incl, 31);
+      for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&share_cnt[0], 1);
+        t = __shfl_sync(DMB_FULL, t, 0);
+        if (t >= total) break;
+        const int w = __popc(__ballot_sync(DMB_FULL, incl <= t));    // tile that owns task t
+        const int g = t - (w > 0 ? __shfl_sync(DMB_FULL, incl, w - 1) : 0);
+        const int nlw = __shfl_sync(DMB_FULL, nl, w);
+        EnvS& T = tiles[w];
+        const int row = g < nlw ? g : T.c_adr[g - nlw];
+        half_solve_rows(M, T, lane, row, row + 1);
+      }
+    }
+    group_barrier(bar_id, bar_n);                                   // B: every Y row is half-solved
+    if (threadIdx.x == 0) share_cnt[0] = 0;
+    {
+      int nt = 0, ne = 0;
+      if (lane < W) { ne = tiles[lane].nefc; nt = (tri(ne) + ne + 31) >> 5; }
+      const int incl = warp_incl_scan(nt, lane);
+      const int total = __shfl_sync(DMB_FULL, incl, 31);
+      for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&share_cnt[1], 1);
+        t = __shfl_sync(DMB_FULL, t, 0);
+        if (t >= total) break;
+        const int w = __popc(__ballot_sync(DMB_FULL, incl <= t));
+        const int c = t - (w > 0 ? __shfl_sync(DMB_FULL, incl, w - 1) : 0);
+        const int new_ = __shfl_sync(DMB_FULL, ne, w);
+        gram(M, tiles[w], lane, new_, 32 * c, 32 * c + 32);
+      }
+    }
+    group_barrier(bar_id, bar_n);                                   // C: every AR / b entry is in place
+    if (threadIdx.x == 0) share_cnt[1] = 0;
+  } else
+#endif
+  {
+    DMB_PHASE_SYNC(32);
+    if (active && nefc > 0) {
+      half_solve_rows(M, S, lane, 0, nefc);
+      DMB_TICK(7);
+      gram(M, S, lane, nefc, 0, 1 << 30);
+    }
   }
   DMB_TICK(8);
   if (active && dbgrow) {
@@ -1392,6 +1446,9 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
     }
     __syncwarp();
   }
+#if DMB_SHARE
+  if (!(LOCKSTEP && share_cnt))
+#endif
   DMB_PHASE_SYNC(64);
   DMB_TICK(9);
   if (active) solve_constraints(M, S, lane, nefc);
