@@ -248,8 +248,12 @@ def run_ours(a):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    # stdout carries exactly one JSON line: NCCL's own banner / debug lines (NCCL_DEBUG=VERSION|INFO) go to stderr
+    # stdout carries exactly one JSON line: everything any library prints to fd 1 while we run (NCCL's version
+    # banner, debug lines) is sent to stderr, and the JSON line is written to the saved descriptor at the end
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -363,11 +367,15 @@ def run_ours(a):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{n} env-steps of the same workload on 1 env (float64 oracle port), {w:.1f} s",
                                     "host_cores": host_cores()}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     env.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    os.close(real_stdout)
 
 
 if __name__ == "__main__":
