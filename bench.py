@@ -251,9 +251,15 @@ def run_ours(a):
     # stdout carries exactly one JSON line: everything any library prints to fd 1 while we run (NCCL's version
     # banner, debug lines) is sent to stderr, and the JSON line is written to the saved descriptor at the end
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    sys.stdout.flush()
-    real_stdout = os.dup(1)
-    os.dup2(2, 1)
+    real_stdout = None
+    try:
+        sys.stdout.flush()
+        real_stdout = os.dup(1)
+        os.dup2(2, 1)
+    except OSError:                      # no usable stderr: keep stdout as it is
+        if real_stdout is not None:
+            os.close(real_stdout)
+        real_stdout = None
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -368,14 +374,18 @@ def run_ours(a):
                                     "sample": f"{n} env-steps of the same workload on 1 env (float64 oracle port), {w:.1f} s",
                                     "host_cores": host_cores()}
         sys.stdout.flush()
-        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        if real_stdout is not None:
+            os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    sys.stdout.flush()
-    os.dup2(real_stdout, 1)
-    os.close(real_stdout)
+    if real_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
 
 
 if __name__ == "__main__":
