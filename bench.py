@@ -239,6 +239,37 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------
+def redirect_stdout_to_stderr():
+    """stdout must carry exactly one JSON line: send whatever any library prints to fd 1 while we run (NCCL's
+    version banner, debug lines) to stderr.  Returns the saved descriptor of the real stdout (None if stderr is
+    not usable and nothing was changed)."""
+    saved = None
+    try:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+    except OSError:
+        if saved is not None:
+            os.close(saved)
+        saved = None
+    return saved
+
+
+def emit_json(line, saved_fd):
+    sys.stdout.flush()
+    if saved_fd is not None:
+        os.write(saved_fd, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line), flush=True)
+
+
+def restore_stdout(saved_fd):
+    if saved_fd is not None:
+        sys.stdout.flush()
+        os.dup2(saved_fd, 1)
+        os.close(saved_fd)
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -251,15 +282,7 @@ def run_ours(a):
     # stdout carries exactly one JSON line: everything any library prints to fd 1 while we run (NCCL's version
     # banner, debug lines) is sent to stderr, and the JSON line is written to the saved descriptor at the end
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    real_stdout = None
-    try:
-        sys.stdout.flush()
-        real_stdout = os.dup(1)
-        os.dup2(2, 1)
-    except OSError:                      # no usable stderr: keep stdout as it is
-        if real_stdout is not None:
-            os.close(real_stdout)
-        real_stdout = None
+    real_stdout = redirect_stdout_to_stderr()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -373,19 +396,12 @@ def run_ours(a):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
                                     "sample": f"{n} env-steps of the same workload on 1 env (float64 oracle port), {w:.1f} s",
                                     "host_cores": host_cores()}
-        sys.stdout.flush()
-        if real_stdout is not None:
-            os.write(real_stdout, (json.dumps(line) + "\n").encode())
-        else:
-            print(json.dumps(line), flush=True)
+        emit_json(line, real_stdout)
     env.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    if real_stdout is not None:
-        sys.stdout.flush()
-        os.dup2(real_stdout, 1)
-        os.close(real_stdout)
+    restore_stdout(real_stdout)
 
 
 if __name__ == "__main__":

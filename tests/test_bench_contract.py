@@ -33,3 +33,15 @@ def test_gpu_arm_fails_loudly_without_cuda():
     p = subprocess.run([sys.executable, BENCH, "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
                        timeout=600, cwd=common.ROOT)
     assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
+
+
+def test_stdout_carries_only_the_json_line():
+    """The GPU arm sends library chatter on fd 1 (NCCL banner) to stderr and writes its JSON line to the real stdout."""
+    code = ("import os, sys; sys.path.insert(0, %r); import bench\n"
+            "fd = bench.redirect_stdout_to_stderr()\n"
+            "print('python chatter'); os.system('echo child chatter')\n"
+            "bench.emit_json({'metric': 'm', 'value': 1.5}, fd); bench.restore_stdout(fd); print('after')\n") % common.ROOT
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.splitlines() == ['{"metric": "m", "value": 1.5}', "after"]
+    assert "python chatter" in p.stderr and "child chatter" in p.stderr
