@@ -1,7 +1,14 @@
 #!/usr/bin/env python3
 """bench.py -- env steps/s of the batched humanoid walk rollout (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--envs-per-gpu E]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|3|4|5]
+                  [--envs-per-gpu E | --envs-global G --scaling strong] [--motions a,b,c]
+
+--config selects a BASELINE.json configuration (default 2, the one the metric is quoted on; the driver's lines):
+  2  4096-env walk imitation per GPU, weak scaling            3  16384-env spinkick, early termination, 1 GPU
+  4  65536-env walk = 8192 envs per GPU x 8 (weak); with --scaling strong --envs-global 65536 the same global
+     batch on 1/2/4/8 GPUs                                    5  mixed walk/dance_b/spinkick, clip = env index % 3,
+                                                                 per-env RSI phase, 4096 envs per GPU (32768 on 8)
 
 A "step" is one pass of the hot path over one batch: every env of the rank takes one env step
 (PD/torque -> RK4 mj_step with collision + PGS -> mocap reward -> termination -> auto reset), i.e.
@@ -42,12 +49,35 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=4096)
-    ap.add_argument("--motion", default="walk")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--envs-per-gpu", type=int, default=None)
+    ap.add_argument("--envs-global", type=int, default=None)
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--motions", default=None, help="comma-separated clip names; env i uses clip i %% len")
+    ap.add_argument("--motion", default=None, help="single clip (same as --motions with one name)")
+    ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--term-mode", type=int, default=0, help="1 = add the DeepMimic fall-contact termination rule")
+    ap.add_argument("--sync-gather", action="store_true", help="all-gather on the compute stream (no overlap)")
     ap.add_argument("--reward-mode", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    # BASELINE.json configs[1..4]: (envs per GPU, clips, seed)
+    envs, motions, seed = {2: (4096, "walk", 0), 3: (16384, "spinkick", 1), 4: (8192, "walk", 0),
+                           5: (4096, "walk,dance_b,spinkick", 2)}[a.config]
+    a.motions = [m for m in (a.motions or a.motion or motions).split(",") if m]
+    a.motion = a.motions[0]
+    a.seed = seed if a.seed is None else a.seed
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.scaling == "strong":
+        g = a.envs_global or envs * (8 if a.config in (4, 5) else 1)
+        if g % world:
+            raise SystemExit("--envs-global must be a multiple of the number of GPUs")
+        a.envs_global, a.envs_per_gpu = g, g // world
+    else:
+        a.envs_per_gpu = a.envs_per_gpu or (a.envs_global // world if a.envs_global else envs)
+        a.envs_global = a.envs_per_gpu * world
+    return a
 
 
 def measured_peak_hbm():
@@ -155,7 +185,7 @@ class ClockSampler(threading.Thread):
 _W = {}
 
 
-def _worker_init(motion, reward_mode):
+def _worker_init(motions, reward_mode):
     """Per-process persistent oracle env (one env per host core)."""
     import ctypes as C
     import multiprocessing as mp
@@ -167,11 +197,12 @@ def _worker_init(motion, reward_mode):
     wid = ident[0] if ident else 0
     m = pack_model(default_model_tables(), max_con=16, max_efc=40)
     cfg = default_config(reward_mode=reward_mode, auto_reset=1)
-    aux = compute_ref_aux([motion]) if reward_mode == 4 else None
-    mcs, keep = make_mocap_struct(load_motions([motion]), aux)
+    motions = [motions] if isinstance(motions, str) else list(motions)
+    aux = compute_ref_aux(motions) if reward_mode == 4 else None
+    mcs, keep = make_mocap_struct(load_motions(motions), aux)
     L = po.lib()
     e = po.DmoEnv()
-    L.dmo_env_init(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), 1234, wid, 0)
+    L.dmo_env_init(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), 1234, wid, wid % len(motions))
     L.dmo_env_reset(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), 0)
     L.dmo_rollout(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), 300, 99)  # warm-up
     _W.update(L=L, m=m, cfg=cfg, mcs=mcs, keep=keep, e=e, C=C, t=0)
@@ -188,14 +219,14 @@ def _worker_run(nsteps):
 class CpuRollout:
     """The float64 oracle port on `cores` host cores, one persistent env per core."""
 
-    def __init__(self, cores, motion, reward_mode):
+    def __init__(self, cores, motions, reward_mode):
         import multiprocessing as mp
         self.cores = cores
         self.pool = None
         if cores == 1:
-            _worker_init(motion, reward_mode)
+            _worker_init(motions, reward_mode)
         else:
-            self.pool = mp.get_context("fork").Pool(cores, initializer=_worker_init, initargs=(motion, reward_mode))
+            self.pool = mp.get_context("fork").Pool(cores, initializer=_worker_init, initargs=(motions, reward_mode))
 
     def run(self, nsteps):
         res = [_worker_run(nsteps)] if self.pool is None else self.pool.map(_worker_run, [nsteps] * self.cores, chunksize=1)
@@ -209,13 +240,30 @@ class CpuRollout:
             self.pool.join()
 
 
+def python_driven_cpu(motion, reward_mode, nsteps):
+    """the same float64 port driven from Python, one ctypes call per env step (what a
+    mujoco-py user pays per step), random actions from numpy, reset on done.  Returns env-steps/s."""
+    import ctypes as C
+    import numpy as np
+    _worker_init(motion, reward_mode)
+    L, m, cfg, mcs, e = _W["L"], _W["m"], _W["cfg"], _W["mcs"], _W["e"]
+    import oracle.pyoracle as po
+    rng = np.random.default_rng(0)
+    acts = rng.uniform(-0.5, 0.5, size=(256, m.nu))
+    obs = np.zeros(256); rew = C.c_double()
+    t0 = time.perf_counter()
+    for t in range(nsteps):
+        L.dmo_env_step(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), po.dptr(acts[t & 255]), po.dptr(obs), C.byref(rew))
+    return nsteps / (time.perf_counter() - t0)
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = host_cores()
     per_step = 1000  # env-steps per core per bench "step": a bounded sample of the same workload
-    cpu = CpuRollout(cores, a.motion, a.reward_mode)
+    cpu = CpuRollout(cores, a.motions, a.reward_mode)
     t_all, n_all, nst = 0.0, 0, 0
     t_begin = time.perf_counter()
     for i in range(a.warmup + a.steps):
@@ -228,8 +276,8 @@ def run_reference(a):
     value = n_all / t_all
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": nst,
             "warmup": a.warmup, "ms_per_step": 1e3 * t_all / max(1, nst), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"1 env per host core x {cores} cores, {a.motion} imitation, random-action rollout "
+            "scaling": a.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"BASELINE config {a.config}: 1 env per host core x {cores} cores, {'+'.join(a.motions)} imitation, random-action rollout "
                                    "(CPU restatement of the reference step; mujoco-py/MuJoCo 2.0 unavailable)",
                        "envs": cores, "reward_mode": a.reward_mode},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
@@ -273,7 +321,7 @@ def restore_stdout(saved_fd):
 def run_ours(a):
     import torch
     import torch.distributed as dist
-    from deepmimic_mujoco_b200.dist import RecordGather
+    from deepmimic_mujoco_b200.dist import RecordGather, mixed_clip_ids
     from deepmimic_mujoco_b200.env import DPVecEnv
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -291,8 +339,11 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=dev)
     E = a.envs_per_gpu
     n_global = E * world
-    env = DPVecEnv(E, motions=(a.motion,), device=dev, seed=0, first_env_id=rank * E, reward_mode=a.reward_mode,
-                   auto_reset=True)
+    first = rank * E
+    nclip = len(a.motions)
+    clip_ids = mixed_clip_ids(first, first + E, nclip) if nclip > 1 else None   # clip = global env index % nclip
+    env = DPVecEnv(E, motions=tuple(a.motions), device=dev, seed=a.seed, first_env_id=first, reward_mode=a.reward_mode,
+                   auto_reset=True, clip_ids=clip_ids, term_mode=a.term_mode)
     sim = env.sim
     env.reset()
     gather = RecordGather(sim.rec, n_global) if world > 1 else None
@@ -301,13 +352,23 @@ def run_ours(a):
     flush = None if a.no_flush else torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
     K, W = a.steps, max(a.warmup, 3)
 
+    # One step = the fused env-step kernel + (N > 1) the NCCL all-gather of its [E, 58] record.  The gather of step
+    # t runs on a side stream and overlaps step t + 1 (double-buffered record): the compute stream joins it right
+    # after the kernel of step t + 1, so every gather lies inside some step's timed interval.
     def one_step(i):
         env.step(pool[i % 16])
         if gather is not None:
-            gather()
+            if a.sync_gather:
+                gather(sim.rec)
+            else:
+                if i > 0:
+                    gather.wait()
+                gather.launch(sim.rec)
 
     for i in range(W):
         one_step(i)
+    if gather is not None:
+        gather.drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -318,6 +379,7 @@ def run_ours(a):
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     evk = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    evd = torch.cuda.Event(enable_timing=True)
     for i in range(K):
         if flush is not None:
             flush.zero_()
@@ -325,12 +387,20 @@ def run_ours(a):
         env.step(pool[i % 16])
         evk[i].record()
         if gather is not None:
-            gather()
+            if a.sync_gather:
+                gather(sim.rec)
+            else:
+                if i > 0:
+                    gather.wait()          # gather of step i-1, launched before this step's flush
+                gather.launch(sim.rec)
         ev1[i].record()
+    if gather is not None:
+        gather.drain()                     # the last gather has nothing to hide behind: it is timed on its own
+    evd.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    t_dev = sum(s.elapsed_time(e) for s, e in zip(ev0, ev1)) * 1e-3
+    t_dev = (sum(s.elapsed_time(e) for s, e in zip(ev0, ev1)) + ev1[-1].elapsed_time(evd)) * 1e-3
     t_kernel = sum(s.elapsed_time(e) for s, e in zip(ev0, evk)) * 1e-3
     # ---- end-to-end: host (pinned) actions in, record out, every step, through DPVecEnv.step
     h_act = [torch.empty(E, sim.nu, dtype=torch.float32).pin_memory() for _ in range(4)]
@@ -344,7 +414,8 @@ def run_ours(a):
         d_act.copy_(h_act[i % 4], non_blocking=True)
         env.step(d_act)
         if gather is not None:
-            gather()
+            gather.launch(sim.rec)
+            gather.wait()                  # the caller consumes this step's gathered record: no overlap here
         h_rec.copy_(sim.rec, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the caller consumes obs/reward/done on the host
 
@@ -359,6 +430,27 @@ def run_ours(a):
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     clocks = sampler.stop() if sampler else None
+    # ---- N = 1 gym surface (the reference's own use: trpo.py with one env): DPEnv.step latency, numpy in / out
+    gym_sps = None
+    if rank == 0 and world == 1 and a.config == 2:
+        try:
+            from deepmimic_mujoco_b200.env import DPEnv
+            e1 = DPEnv(motion=a.motion, device=dev, seed=0)
+            e1.reset()
+            acts = [e1.action_space.sample() for _ in range(64)]
+            for i in range(30):
+                if e1.step(acts[i % 64])[2]:
+                    e1.reset()
+            torch.cuda.synchronize()
+            tg = time.perf_counter()
+            ng = 300
+            for i in range(ng):
+                if e1.step(acts[i % 64])[2]:
+                    e1.reset(); e1.reset_model_init()
+            gym_sps = ng / (time.perf_counter() - tg)
+            e1.close()
+        except Exception as ex:   # diagnostics only
+            gym_sps = f"failed: {ex}"
     if world > 1:
         tt = torch.tensor([t_dev, t_kernel, t_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -374,13 +466,21 @@ def run_ours(a):
                 traffic = json.load(open(tp)).get(str(E))
             except Exception:
                 traffic = None
+        wl = "+".join(a.motions)
+        rec_w = sim.obs_dim + 2
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": 1e3 * t_dev / K, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{E}-env {a.motion} imitation per GPU, random-action rollout, RK4+PGS(50), "
-                                       f"reward_mode={a.reward_mode}, CoM termination + RSI auto-reset",
-                           "envs_global": n_global, "envs_per_gpu": E, "parallelism": f"env-shard x{world}",
-                           "collective": "nccl all_gather [N,58] f32 per step" if world > 1 else "none",
+                "config": {"workload": f"BASELINE config {a.config}: {E}-env {wl} imitation per GPU, random-action rollout, "
+                                       f"RK4+PGS(50), reward_mode={a.reward_mode}, CoM termination"
+                                       f"{' + fall-contact rule' if a.term_mode == 1 else ''} + RSI auto-reset"
+                                       f"{', clip = env index % ' + str(nclip) if nclip > 1 else ''}",
+                           "baseline_config": a.config, "envs_global": n_global, "envs_per_gpu": E,
+                           "parallelism": f"env-shard x{world}",
+                           "collective": (f"nccl all_gather [N,{rec_w}] f32 per step, "
+                                          + ("on the compute stream" if a.sync_gather else
+                                             "side stream, overlapped with the next step (double-buffered record)"))
+                                         if world > 1 else "none",
                            "l2": "no flush" if a.no_flush else "L2 flushed between timed steps (192 MiB memset, untimed)",
                            "launch": sim.launch_info()},
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -390,12 +490,22 @@ def run_ours(a):
                         "d2h_bytes_per_step": world * h_rec.numel() * 4},   # job totals over all ranks
                 "gpu_launches": 2 * K,  # k_order (scheduler sort) + k_step (fused env step) per step
                 "clocks": clocks}
+        if world > 1:
+            line["nvlink"] = {"gather_bytes_in_per_rank_per_step": (world - 1) * E * rec_w * 4,
+                              "gather_bytes_out_per_rank_per_step": E * rec_w * 4}
+        if gym_sps is not None:
+            line["gym_surface_n1"] = {"value": gym_sps, "unit": "env-steps/s",
+                                      "what": "DPEnv.step (N = 1, numpy in/out, H2D + 2 launches + D2H per step)"}
         if not a.no_cpu_baseline and world == 1:   # the CPU baseline is reported by the single-GPU run only
-            cpu = CpuRollout(1, a.motion, a.reward_mode)
+            cpu = CpuRollout(1, a.motions, a.reward_mode)
             v, n, w = cpu.run(150000)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": f"{n} env-steps of the same workload on 1 env (float64 oracle port), {w:.1f} s",
+                                    "sample": f"{n} env-steps of the same workload on 1 env (float64 oracle port, C loop), {w:.1f} s",
                                     "host_cores": host_cores()}
+            pv = python_driven_cpu(a.motions[0], a.reward_mode, 20000)
+            line["cpu_baseline"]["python_driven"] = {"value": pv, "unit": UNIT,
+                                                     "what": "same port, one ctypes call per env step (mujoco-py-like call overhead)"}
+            cpu.close()
         emit_json(line, real_stdout)
     env.close()
     if world > 1:

@@ -35,25 +35,40 @@ struct DevPtrs {
   const float* mocap_vel;  // [F][nv]
   const float* ref_aux;    // [F][DMB_REF_AUX]
   long long* trace;        // DMB_TRACE=1: [grid][8] globaltimer at kernel start and after each scheduler round
+  float* gscratch;         // [grid * W][gs::stride] row storage of stages with more than RF constraint rows
 };
 
 // ---------------------------------------------------------------------------------------
 // state I/O helpers (lane-coalesced env-major rows)
 // ---------------------------------------------------------------------------------------
+// The three state rows of an env (qpos / qvel / qacc_warmstart, DMB_QSTRIDE = DMB_VSTRIDE = 36 floats = nine
+// 16-byte words each) move with ONE 128-bit load / store per lane: lanes 0-8 qpos, 9-17 qvel, 18-26 warmstart.
+static_assert(DMB_QSTRIDE == NQC && DMB_VSTRIDE == NVC && NQC % 4 == 0 && NVC % 4 == 0, "state rows are whole float4s");
+static_assert(offsetof(EnvS, qvel) % 16 == 0 && offsetof(EnvS, qacc) % 16 == 0 && sizeof(EnvS) % 16 == 0, "float4 alignment");
 __device__ __forceinline__ void load_state(const ModelS& M, EnvS& S, const dmb_state_t& st, int env, int lane) {
-  for (int i = lane; i < M.nq; i += 32) S.qpos[i] = st.qpos[(size_t)env * DMB_QSTRIDE + i];
-  for (int i = lane; i < M.nv; i += 32) {
-    S.qvel[i] = st.qvel[(size_t)env * DMB_VSTRIDE + i];
-    S.warm[i] = st.warm[(size_t)env * DMB_VSTRIDE + i];
+  constexpr int NW = NQC / 4;   // float4 words per row
+  if (lane < 3 * NW) {
+    const int a = lane / NW, w = lane - a * NW;
+    const float* src = a == 0 ? st.qpos : (a == 1 ? st.qvel : st.warm);
+    float* dst = a == 0 ? S.qpos : (a == 1 ? S.qvel : S.qacc);
+    reinterpret_cast<float4*>(dst)[w] = __ldg(reinterpret_cast<const float4*>(src + (size_t)env * NQC) + w);
   }
   if (lane == 0) { S.flags = 0; S.cost = 0; }
   __syncwarp();
 }
 __device__ __forceinline__ void store_state(const ModelS& M, EnvS& S, const dmb_state_t& st, int env, int lane) {
-  for (int i = lane; i < DMB_QSTRIDE; i += 32) st.qpos[(size_t)env * DMB_QSTRIDE + i] = i < M.nq ? S.qpos[i] : 0.f;
-  for (int i = lane; i < DMB_VSTRIDE; i += 32) {
-    st.qvel[(size_t)env * DMB_VSTRIDE + i] = i < M.nv ? S.qvel[i] : 0.f;
-    st.warm[(size_t)env * DMB_VSTRIDE + i] = i < M.nv ? S.warm[i] : 0.f;
+  constexpr int NW = NQC / 4;
+  if (lane < 3 * NW) {
+    const int a = lane / NW, w = lane - a * NW;
+    float* dst = a == 0 ? st.qpos : (a == 1 ? st.qvel : st.warm);
+    const float* src = a == 0 ? S.qpos : (a == 1 ? S.qvel : S.qacc);
+    const int n = a == 0 ? M.nq : M.nv;   // the padding words of a row are kept at zero
+    float4 v = reinterpret_cast<const float4*>(src)[w];
+    if (4 * w + 0 >= n) v.x = 0.f;
+    if (4 * w + 1 >= n) v.y = 0.f;
+    if (4 * w + 2 >= n) v.z = 0.f;
+    if (4 * w + 3 >= n) v.w = 0.f;
+    reinterpret_cast<float4*>(dst + (size_t)env * NQC)[w] = v;
   }
 }
 // obs = qpos[7:] || qvel[6:]   (dp_env_v3.py:62-65)
@@ -77,7 +92,7 @@ __device__ __noinline__ void kin_vel_prep(const ModelS& M, EnvS& S, int lane) {
   for (int d = lane; d < M.nv; d += 32) {
     const float qv = S.qvel[d];
 #pragma unroll
-    for (int k = 0; k < 6; k++) S.u.a.buf6[6 * d + k] = S.cdof[6 * d + k] * qv;
+    for (int k = 0; k < 6; k++) S.o.k.buf6[6 * d + k] = S.o.k.cdof[6 * d + k] * qv;
   }
   __syncwarp();
 }
@@ -90,7 +105,7 @@ __device__ __forceinline__ void body_cvel(const ModelS& M, const EnvS& S, int b,
     const int d = __ffsll((long long)mk) - 1;
     mk &= mk - 1;
 #pragma unroll
-    for (int k = 0; k < 6; k++) v[k] += S.u.a.buf6[6 * d + k];
+    for (int k = 0; k < 6; k++) v[k] += S.o.k.buf6[6 * d + k];
   }
 }
 
@@ -201,24 +216,25 @@ __device__ __forceinline__ float phase_of(const ModelS& M, int clip, int idx_ini
 // DeepMimic state (obs_mode 1; cCtController::BuildStatePose / BuildStateVel, code.md:287-504, and
 // record_state, mujoco_env.py:91-124): [phase, root height, npart x (pos 3, quat 4), npart x
 // (lin vel 3, ang vel 3)] in the root heading frame, lane = body part.  The row is staged in the
-// (dead) Delassus tile and written out coalesced.
+// (dead) composite-inertia arrays of the tile and written out coalesced.
 __device__ __noinline__ void write_obs_dm(const ModelS& M, EnvS& S, float phase, float* obs, float* rec, int env, int lane) {
   kin_vel_prep(M, S, lane);
-  float* buf = S.AR;
-  const float* R = &S.u.a.xmat[9];
+  float* buf = S.o.k.cinert;   // cinert + crb (contiguous, 320 floats) are dead after com_pos
+  static_assert(2 + 13 * DMB_MAX_PART <= 2 * NB * 10 && offsetof(PhaseK, crb) == offsetof(PhaseK, cinert) + sizeof(float) * NB * 10, "obs staging");
+  const float* R = &S.o.k.xmat[9];
   const float heading = atan2f(R[3], R[0]);
   float sh, ch, shh, chh;
   sincosf(heading, &sh, &ch);
   sincosf(0.5f * heading, &shh, &chh);
-  if (lane == 0) { buf[0] = phase; buf[1] = S.u.a.xpos[5]; }
+  if (lane == 0) { buf[0] = phase; buf[1] = S.o.k.xpos[5]; }
   if (lane < M.npart) {
     const int g = M.part_geom[lane], b = M.geom_bodyid[g];
-    const V3 gp = ld3(&S.u.a.xpos[3 * b]) + mat_vec(&S.u.a.xmat[9 * b], ld3(M.geom_pos[g]));
-    const V3 rel = gp - ld3(&S.u.a.xpos[3]);
+    const V3 gp = ld3(&S.o.k.xpos[3 * b]) + mat_vec(&S.o.k.xmat[9 * b], ld3(M.geom_pos[g]));
+    const V3 rel = gp - ld3(&S.o.k.xpos[3]);
     float* o = buf + 2 + 7 * lane;
     o[0] = ch * rel.x + sh * rel.y; o[1] = -sh * rel.x + ch * rel.y; o[2] = rel.z;
     Q4 qh; qh.w = chh; qh.x = 0.f; qh.y = 0.f; qh.z = -shh;
-    Q4 qb; qb.w = S.u.a.xquat[4 * b]; qb.x = S.u.a.xquat[4 * b + 1]; qb.y = S.u.a.xquat[4 * b + 2]; qb.z = S.u.a.xquat[4 * b + 3];
+    Q4 qb; qb.w = S.o.k.xquat[4 * b]; qb.x = S.o.k.xquat[4 * b + 1]; qb.y = S.o.k.xquat[4 * b + 2]; qb.z = S.o.k.xquat[4 * b + 3];
     Q4 q = qmul(qh, qb);
     const float sg = q.w < 0.f ? -1.f : 1.f;
     o[3] = sg * q.w; o[4] = sg * q.x; o[5] = sg * q.y; o[6] = sg * q.z;
@@ -298,7 +314,7 @@ __device__ __forceinline__ void integrate_pos(const ModelS& M, EnvS& S, int lane
 // the kernel is instruction-fetch bound).  Returns the CoM height of the last stage evaluation.
 template <bool LOCKSTEP>
 __device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bool active, int bar_id, int bar_n, int* arrive,
-                                          EnvS* tiles, int* share_cnt) {
+                                          EnvS* tiles, int* share_cnt, float* gcta) {
   const float h = M.timestep;
   const int d0 = lane, d1 = lane + 32;
   const bool a0 = active && d0 < M.nv, a1 = active && d1 < M.nv;
@@ -317,7 +333,7 @@ __device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bo
       if (active) integrate_pos(M, S, lane, h);
       __syncwarp();
     }
-    zc = forward_eval<LOCKSTEP>(M, S, lane, nullptr, active, bar_id, bar_n, arrive + st, tiles, share_cnt);
+    zc = forward_eval<LOCKSTEP>(M, S, lane, nullptr, active, bar_id, bar_n, arrive + st, tiles, share_cnt, gcta);
     const float bw = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);
     if (a0) { sv0 += bw * S.qvel[d0]; sa0 += bw * S.qacc[d0]; }
     if (a1) { sv1 += bw * S.qvel[d1]; sa1 += bw * S.qacc[d1]; }
@@ -330,13 +346,18 @@ __device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bo
   return zc;
 }
 
+// clip ids come from a caller-owned tensor: out-of-range ids are clamped (BatchedSim rejects them up front)
+__device__ __forceinline__ int clip_of(const ModelS& M, const dmb_state_t& st, int env) {
+  const int c = st.clip[env];
+  return c < 0 ? 0 : (c >= M.nclip ? M.nclip - 1 : c);
+}
 // reference-state initialisation (dp_env_v3.py:67-71,148-164); Philox keyed by (seed, env id)
 __device__ int reset_env(const ModelS& M, EnvS& S, const DevPtrs& P, const dmb_state_t& st, int env, int lane,
                          unsigned long long seed, unsigned first_env_id, int mode) {
   const unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
   const unsigned eid = first_env_id + (unsigned)env;
   const unsigned rc = st.reset_count[env];
-  const int clip = st.clip[env];
+  const int clip = clip_of(M, st, env);
   const int len = M.clip_len[clip], start = M.clip_start[clip];
   unsigned r[4];
   philox4x32(k0, k1, eid, rc, 0u, 0u, r);
@@ -352,7 +373,7 @@ __device__ int reset_env(const ModelS& M, EnvS& S, const DevPtrs& P, const dmb_s
       if (i < M.nq) S.qpos[i] = M.qpos0[i] + nz; else S.qvel[i - M.nq] = nz;
     }
   }
-  for (int i = lane; i < M.nv; i += 32) S.warm[i] = 0.f;
+  for (int i = lane; i < M.nv; i += 32) S.qacc[i] = 0.f;   // qacc_warmstart
   if (lane == 0) {
     st.idx_init[env] = idx; st.idx_curr[env] = idx; st.reset_count[env] = rc + 1u;
     st.ep_len[env] = 0; st.ep_ret[env] = 0.f;
@@ -379,7 +400,7 @@ __device__ __noinline__ PoseFeat pose_features(const ModelS& M, EnvS& S, int lan
     const int b = lane;
     float v[6];
     body_cvel(M, S, b, v);
-    const V3 r = ld3(&S.u.a.xipos[3 * b]) - ld3(S.com);
+    const V3 r = ld3(&S.o.k.xipos[3 * b]) - ld3(S.com);
     const V3 vb = v3(v[3], v[4], v[5]) + cross(v3(v[0], v[1], v[2]), r);
     const float ms = M.body_mass[b];
     px = ms * vb.x; py = ms * vb.y; pz = ms * vb.z;
@@ -387,13 +408,13 @@ __device__ __noinline__ PoseFeat pose_features(const ModelS& M, EnvS& S, int lan
   out.vx = warp_sum(px) * M.inv_total_mass; out.vy = warp_sum(py) * M.inv_total_mass; out.vz = warp_sum(pz) * M.inv_total_mass;
   out.ex = out.ey = out.ez = 0.f;
   if (lane < M.nee) {
-    const float* R = &S.u.a.xmat[9];
+    const float* R = &S.o.k.xmat[9];
     const float heading = atan2f(R[3], R[0]);
     float sh, ch;
     sincosf(heading, &sh, &ch);
     const int b = M.ee_body[lane];
-    const V3 w = ld3(&S.u.a.xpos[3 * b]) + mat_vec(&S.u.a.xmat[9 * b], ld3(M.ee_pos[lane]));
-    const float rx = w.x - S.u.a.xpos[3], ry = w.y - S.u.a.xpos[4];
+    const V3 w = ld3(&S.o.k.xpos[3 * b]) + mat_vec(&S.o.k.xmat[9 * b], ld3(M.ee_pos[lane]));
+    const float rx = w.x - S.o.k.xpos[3], ry = w.y - S.o.k.xpos[4];
     out.ex = ch * rx + sh * ry; out.ey = -sh * rx + ch * ry; out.ez = w.z;
   }
   return out;
@@ -401,7 +422,9 @@ __device__ __noinline__ PoseFeat pose_features(const ModelS& M, EnvS& S, int lan
 
 // 5-term DeepMimic imitation reward (code.md:979-1146 adapted to the hinge model; weights and
 // scales from dp_env_v3.py:42-53) against the reference pose rq / rv with features `ref`.
-__device__ float reward_imitate(const ModelS& M, EnvS& S, int lane, const float* rq, const float* rv, PoseFeat ref) {
+// (offx, offy): root offset of the reference accumulated over completed passes of the clip (phase_mode 0)
+__device__ float reward_imitate(const ModelS& M, EnvS& S, int lane, const float* rq, const float* rv, PoseFeat ref,
+                                float offx, float offy) {
   const PoseFeat cur = pose_features(M, S, lane);
   float ee = 0.f;
   if (lane < M.nee) {
@@ -436,7 +459,7 @@ __device__ float reward_imitate(const ModelS& M, EnvS& S, int lane, const float*
   float rp = 0.f, rvv = 0.f, rw = 0.f;
 #pragma unroll
   for (int i = 0; i < 3; i++) {
-    const float a = S.qpos[i] - rq[i], b = S.qvel[i] - rv[i], c = S.qvel[3 + i] - rv[3 + i];
+    const float a = S.qpos[i] - (rq[i] + (i == 0 ? offx : (i == 1 ? offy : 0.f))), b = S.qvel[i] - rv[i], c = S.qvel[3 + i] - rv[3 + i];
     rp += a * a; rvv += b * b; rw += c * c;
   }
   const float root_err = rp + 0.1f * th_root * th_root + 0.01f * rvv + 0.001f * rw;
@@ -457,17 +480,37 @@ __device__ __forceinline__ bool state_bad(const ModelS& M, const EnvS& S, int la
 // ---------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------
+// Model tables global -> shared: one TMA bulk copy (cp.async.bulk, completion on an mbarrier) issued by thread 0
+// instead of a word-by-word copy loop on every thread of the CTA.
+static_assert(sizeof(ModelS) % 16 == 0, "cp.async.bulk moves multiples of 16 bytes");
 __device__ __forceinline__ void stage_model(ModelS* dst, const ModelS* src) {
-  const int n = (int)(sizeof(ModelS) / 4);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) ((int*)dst)[i] = ((const int*)src)[i];
-  __syncthreads();
+  __shared__ __align__(8) unsigned long long s_mbar;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_mbar);
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  constexpr unsigned bytes = (unsigned)sizeof(ModelS);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(bar) : "memory");
+  }
+  __syncthreads();   // the barrier is initialised and armed before anybody polls it
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar) : "memory");
+  }
 }
 
+#ifndef DMB_MAXTHREADS
+#define DMB_MAXTHREADS 896   // 28 warps: 72 registers per thread
+#endif
 static_assert(YS % 2 == 1, "odd row stride");
 constexpr size_t MODEL_BYTES = (sizeof(ModelS) + 15) & ~(size_t)15;
 
 template <bool LOCKSTEP>
-__global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, const float* __restrict__ action, dmb_step_out_t out, int N,
+__global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state_t st, const float* __restrict__ action, dmb_step_out_t out, int N,
                        unsigned long long seed, unsigned first_env_id) {
   extern __shared__ __align__(16) unsigned char smem[];
   ModelS& M = *reinterpret_cast<ModelS*>(smem);
@@ -488,6 +531,11 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
   // barrier and its own pull from the scheduler
   const int gsz = LOCKSTEP ? W / M.ngroups : 1, grp = LOCKSTEP ? warp / gsz : 0, gw = LOCKSTEP ? warp % gsz : 0;
   const int bar_id = 1 + grp, bar_n = gsz * 32;
+  float* const gcta = P.gscratch + (size_t)blockIdx.x * W * gs::stride;
+  // Single round (every env resident at once, e.g. 4096 envs on 148 x 28 warps): the cost-sorted list is dealt out
+  // round robin, so that every CTA holds the same mix of heavy and light envs and no SM carries more instructions
+  // than the others.  Otherwise CTAs pull W consecutive entries at a time, heaviest first.
+  const bool spread = LOCKSTEP && M.spread && N <= (int)gridDim.x * W;
   int round = 0;
   if (P.trace && threadIdx.x == 0) {
     long long t;
@@ -499,7 +547,14 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
     // takes gsz consecutive entries at a time so that its warps see similar work between the
     // lockstep barriers; without lockstep every warp pulls for itself.
     int env = N;
-    if (LOCKSTEP) {
+    if (spread) {
+      if (round > 0) break;
+      if (threadIdx.x < 4) s_arrive[threadIdx.x] = 0;
+      if (threadIdx.x == 0) s_base[0] = 0;
+      __syncthreads();
+      const int idx = warp * (int)gridDim.x + (int)blockIdx.x;
+      if (idx < N) env = P.order[idx];
+    } else if (LOCKSTEP) {
       group_barrier(bar_id, bar_n);
       if (threadIdx.x < 4) s_arrive[threadIdx.x] = 0;   // per-stage arrival counters (soft barrier)
       if (gw == 0 && lane == 0) s_base[grp] = atomicAdd(P.counter, gsz);
@@ -522,14 +577,14 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
       if (!bad) set_ctrl(M, S, action, env, lane);
     }
     const float zc = rk4_step<LOCKSTEP>(M, S, lane, have && !bad, bar_id, bar_n, s_arrive, tiles,
-                                        (LOCKSTEP && M.ngroups == 1) ? s_share : nullptr);
-    if (!have) continue;
+                                        (LOCKSTEP && M.ngroups == 1) ? s_share : nullptr, gcta);
+    if (!have) { round++; continue; }
     if (!bad) bad = state_bad(M, S, lane);
     // reward (dp_env_v3.py:117 / 89-104).  Reference pose: phase_mode 0 = table row of the integer frame
     // counter; phase_mode 1 = interpolated at the post-step mocap time into S.x_q0 / S.x_dv (dead here)
     float rew = 1.0f;
     int idx_curr = st.idx_curr[env], idx_init = st.idx_init[env];
-    const int clip = st.clip[env];
+    const int clip = clip_of(M, st, env);
     const int len = M.clip_len[clip], start = M.clip_start[clip];
     int ep_len = st.ep_len[env] + 1;
     const int rmode = M.reward_mode;
@@ -552,6 +607,7 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
         rew = expf(-warp_sum(e));
       } else if (rmode == 4) {
         PoseFeat ref;
+        float offx = 0.f, offy = 0.f;
         if (M.phase_mode == 1) {
           // features of the interpolated reference pose: swap it into the tile, run the kinematics, swap back
           const int i1 = lane + 32;
@@ -571,8 +627,13 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
           ref.ex = ref.ey = ref.ez = 0.f;
           if (lane < M.nee) { ref.ex = aux[3 * lane]; ref.ey = aux[3 * lane + 1]; ref.ez = aux[3 * lane + 2]; }
           ref.vx = aux[12]; ref.vy = aux[13]; ref.vz = aux[14];
+          // the frame counter wraps, the reference root keeps moving: every completed pass over the clip adds
+          // the last frame's root xy (MocapDM.play, mocap_v2.py:168-182); ep_len already counts this step
+          const float* cl = P.mocap_cfg + (size_t)(start + len - 1) * M.nq;
+          const float cyc = (float)((idx_init + ep_len - 1) / len);
+          offx = cyc * cl[0]; offy = cyc * cl[1];
         }
-        rew = reward_imitate(M, S, lane, rq, rv, ref);
+        rew = reward_imitate(M, S, lane, rq, rv, ref, offx, offy);
       } else {
         // v2 / v1 rewards (dp_env_v2.py:116-183, dp_env_v1.py:82-152); the control cost is on the raw action
         float acs = 0.f;
@@ -616,7 +677,7 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
     bool done = bad || zc < M.z_min || zc > M.z_max;
     if (M.term_mode == 1 && !bad) {  // DeepMimic fall-contact rule on the contacts of the last RK4 stage
       bool fall = false;
-      if (lane < S.ncon) fall = M.geom_type[S.c_g1[lane]] == DMB_GEOM_PLANE && ((M.fall_body_mask >> M.geom_bodyid[S.c_g2[lane]]) & 1u);
+      if (lane < S.ncon) fall = M.geom_type[cm_g1(S.c_meta[lane])] == DMB_GEOM_PLANE && ((M.fall_body_mask >> M.geom_bodyid[cm_g2(S.c_meta[lane])]) & 1u);
       done = done || __any_sync(DMB_FULL, fall);
     }
     const int flags = S.flags | (bad ? 4 : 0);
@@ -639,13 +700,14 @@ __global__ void __launch_bounds__(448, 1) k_step(DevPtrs P, dmb_state_t st, cons
       ep_len = 0;
     } else if (bad) {  // keep a finite state in HBM
       for (int i = lane; i < M.nq; i += 32) S.qpos[i] = M.qpos0[i];
-      for (int i = lane; i < M.nv; i += 32) { S.qvel[i] = 0.f; S.warm[i] = 0.f; }
+      for (int i = lane; i < M.nv; i += 32) { S.qvel[i] = 0.f; S.qacc[i] = 0.f; }
       __syncwarp();
     }
     emit_obs(M, S, clip, idx_init, idx_curr, ep_len, out.obs, out.rec, env, lane);
     store_state(M, S, st, env, lane);
     __syncwarp();
-    if (P.trace && threadIdx.x == 0 && ++round < 8) {
+    ++round;
+    if (P.trace && threadIdx.x == 0 && round < 8) {
       long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       P.trace[blockIdx.x * 8 + round] = t;
@@ -676,7 +738,7 @@ __global__ void k_order(const int* __restrict__ cost, int* __restrict__ order, i
   for (int i = threadIdx.x; i < N; i += blockDim.x) order[atomicAdd(&cursor[min(255, max(0, cost[i]))], 1)] = i;
 }
 
-__global__ void k_reset(DevPtrs P, dmb_state_t st, const unsigned char* __restrict__ mask, int mode, float* obs, int N,
+__global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_reset(DevPtrs P, dmb_state_t st, const unsigned char* __restrict__ mask, int mode, float* obs, int N,
                         unsigned long long seed, unsigned first_env_id) {
   extern __shared__ __align__(16) unsigned char smem[];
   ModelS& M = *reinterpret_cast<ModelS*>(smem);
@@ -688,7 +750,7 @@ __global__ void k_reset(DevPtrs P, dmb_state_t st, const unsigned char* __restri
     if (mask && !mask[env]) continue;
     const int idx = reset_env(M, S, P, st, env, lane, seed, first_env_id, mode < 0 ? M.reset_mode : mode);
     if (lane == 0) st.flags[env] = 0;
-    if (obs) emit_obs(M, S, st.clip[env], idx, idx, 0, obs, nullptr, env, lane);
+    if (obs) emit_obs(M, S, clip_of(M, st, env), idx, idx, 0, obs, nullptr, env, lane);
     store_state(M, S, st, env, lane);
     __syncwarp();
   }
@@ -706,7 +768,7 @@ __global__ void k_obs(DevPtrs P, dmb_state_t st, float* obs, int N) {
 }
 
 // DeepMimic state of the stored state (obs_mode 1): one warp per env, needs the tile for the kinematics
-__global__ void k_obs_dm(DevPtrs P, dmb_state_t st, float* obs, int N) {
+__global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_obs_dm(DevPtrs P, dmb_state_t st, float* obs, int N) {
   extern __shared__ __align__(16) unsigned char smem[];
   ModelS& M = *reinterpret_cast<ModelS*>(smem);
   EnvS* tiles = reinterpret_cast<EnvS*>(smem + MODEL_BYTES);
@@ -715,7 +777,7 @@ __global__ void k_obs_dm(DevPtrs P, dmb_state_t st, float* obs, int N) {
   EnvS& S = tiles[warp];
   for (int env = blockIdx.x * W + warp; env < N; env += gridDim.x * W) {
     load_state(M, S, st, env, lane);
-    emit_obs(M, S, st.clip[env], st.idx_init[env], st.idx_curr[env], st.ep_len[env], obs, nullptr, env, lane);
+    emit_obs(M, S, clip_of(M, st, env), st.idx_init[env], st.idx_curr[env], st.ep_len[env], obs, nullptr, env, lane);
     __syncwarp();
   }
 }
@@ -748,7 +810,7 @@ __global__ void k_mocap_sample(DevPtrs P, const int* __restrict__ clip, const do
   }
 }
 
-__global__ void k_forward_debug(DevPtrs P, dmb_state_t st, const float* __restrict__ ctrl, float* dbgout, int N) {
+__global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_forward_debug(DevPtrs P, dmb_state_t st, const float* __restrict__ ctrl, float* dbgout, int N) {
   extern __shared__ __align__(16) unsigned char smem[];
   ModelS& M = *reinterpret_cast<ModelS*>(smem);
   EnvS* tiles = reinterpret_cast<EnvS*>(smem + MODEL_BYTES);
@@ -770,17 +832,9 @@ __global__ void k_forward_debug(DevPtrs P, dmb_state_t st, const float* __restri
     float* row = dbgout + (size_t)env * dbg::stride;
     for (int i = lane; i < dbg::stride; i += 32) row[i] = 0.f;
     __syncwarp();
-    const float zc = forward_eval<false>(M, S, lane, row, true, 0, 0, nullptr, nullptr, nullptr);
-    for (int i = lane; i < M.nbody * 6; i += 32) row[dbg::cvel + i] = S.cvel[i];
+    const float zc = forward_eval<false>(M, S, lane, row, true, 0, 0, nullptr, nullptr, nullptr,
+                                         P.gscratch + (size_t)blockIdx.x * W * gs::stride);
     for (int i = lane; i < M.nv; i += 32) row[dbg::qacc + i] = S.qacc[i];
-    for (int r = lane; r < S.nefc; r += 32) row[dbg::efc_force + r] = S.e_f[r];
-    for (int c = lane; c < S.ncon; c += 32) {
-      float* cr = row + dbg::contact + 16 * c;
-      cr[0] = S.c_dist[c];
-      for (int k = 0; k < 3; k++) cr[1 + k] = S.c_pos[3 * c + k];
-      for (int k = 0; k < 9; k++) cr[4 + k] = S.c_frame[9 * c + k];
-      cr[13] = (float)S.c_g1[c]; cr[14] = (float)S.c_g2[c]; cr[15] = (float)S.c_dim[c];
-    }
     if (lane == 0) {
       row[dbg::com] = S.com[0]; row[dbg::com + 1] = S.com[1]; row[dbg::com + 2] = S.com[2];
       row[dbg::ncon] = (float)S.ncon; row[dbg::nefc] = (float)S.nefc; row[dbg::iter] = (float)S.iter;
@@ -788,7 +842,7 @@ __global__ void k_forward_debug(DevPtrs P, dmb_state_t st, const float* __restri
       st.flags[env] = S.flags;
     }
     // mj_forward leaves qacc_warmstart = qacc
-    for (int i = lane; i < DMB_VSTRIDE; i += 32) st.warm[(size_t)env * DMB_VSTRIDE + i] = i < M.nv ? S.warm[i] : 0.f;
+    for (int i = lane; i < DMB_VSTRIDE; i += 32) st.warm[(size_t)env * DMB_VSTRIDE + i] = i < M.nv ? S.qacc[i] : 0.f;
     __syncwarp();
   }
 }
@@ -807,7 +861,7 @@ struct dmb_handle_s {
   unsigned first_env_id = 0;
   ModelS hmodel;
   ModelS* dmodel = nullptr;
-  float *d_cfg = nullptr, *d_vel = nullptr, *d_aux = nullptr;
+  float *d_cfg = nullptr, *d_vel = nullptr, *d_aux = nullptr, *d_scratch = nullptr;
   int *d_counter = nullptr, *d_cost = nullptr, *d_order = nullptr;
   long long* d_trace = nullptr;
   int grid = 0, block = 0, smem = 0, envs_per_cta = 0;
@@ -835,6 +889,9 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
       m->nM > NMX || m->nv > 64) { why = "model exceeds kernel capacities"; return DMB_ERR_MODEL; }
   if (m->max_efc > MAXROW || m->max_con > MAXC || m->max_con > 32 || m->max_efc < m->njnt) {
     why = "max_efc must be <= 40 and >= njnt, max_con <= 16 (kernel capacities)"; return DMB_ERR_MODEL;
+  }
+  if (m->ngeom > 255 || m->max_efc > 255 || m->npair > 256) {
+    why = "geom ids / row addresses are packed in bytes"; return DMB_ERR_MODEL;
   }
   S.nq = m->nq; S.nv = m->nv; S.nu = m->nu; S.nbody = m->nbody; S.njnt = m->njnt; S.ngeom = m->ngeom;
   S.npair = m->npair; S.nM = m->nM; S.iterations = m->iterations; S.max_con = m->max_con; S.max_efc = m->max_efc;
@@ -998,6 +1055,8 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
   S.arrive_k = 0;
   S.cost_mode = 0;
   S.patience = 0;
+  S.spread = 1;
+  if (const char* sp = getenv("DMB_SPREAD")) S.spread = atoi(sp) != 0;
   if (const char* pt = getenv("DMB_PATIENCE")) S.patience = atoi(pt);
   if (const char* cm = getenv("DMB_COST_MODE")) S.cost_mode = atoi(cm);
   if (const char* ak = getenv("DMB_ARRIVE_K")) S.arrive_k = atoi(ak);
@@ -1077,18 +1136,26 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
   if (e == cudaSuccess) e = upload(mocap->ref_aux, naux, &h->d_aux);
   delete[] tmp;
   if (e != cudaSuccess) { std::string msg = cudaGetErrorString(e); dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, "dmb_create: " + msg); }
-  // launch geometry: as many env tiles per CTA as opt-in shared memory allows, one CTA per SM
+  // launch geometry: as many env tiles per CTA as opt-in shared memory allows (28 on B200), one CTA per SM
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, cuda_device);
   if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, cudaGetErrorString(e)); }
-  const size_t maxsmem = prop.sharedMemPerBlockOptin;
-  int W = (int)((maxsmem - MODEL_BYTES) / sizeof(EnvS));
-  if (W > 16) W = 16;
-  {  // the register file bounds the resident warps as well
+  const void* tile_kernels[] = {(const void*)k_step<false>, (const void*)k_step<true>, (const void*)k_reset,
+                                (const void*)k_forward_debug, (const void*)k_obs_dm};
+  size_t static_smem = 0;
+  int max_regs = 0;
+  for (auto fn : tile_kernels) {   // every kernel launched with the tile geometry bounds it
     cudaFuncAttributes fa;
-    e = cudaFuncGetAttributes(&fa, (const void*)k_step<true>);
+    e = cudaFuncGetAttributes(&fa, fn);
     if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, cudaGetErrorString(e)); }
-    const int regs = ((fa.numRegs + 7) / 8) * 8;
+    if (fa.sharedSizeBytes > static_smem) static_smem = fa.sharedSizeBytes;
+    if (fa.numRegs > max_regs) max_regs = fa.numRegs;
+  }
+  const size_t maxsmem = prop.sharedMemPerBlockOptin;
+  int W = maxsmem > MODEL_BYTES + static_smem ? (int)((maxsmem - MODEL_BYTES - static_smem) / sizeof(EnvS)) : 0;
+  if (W > DMB_MAXTHREADS / 32) W = DMB_MAXTHREADS / 32;   // __launch_bounds__ of the tile kernels
+  {  // the register file bounds the resident warps as well
+    const int regs = ((max_regs + 7) / 8) * 8;
     const int wreg = prop.regsPerMultiprocessor / (32 * (regs > 0 ? regs : 1));
     if (W > wreg) W = wreg;
   }
@@ -1108,10 +1175,12 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
   h->smem = (int)(MODEL_BYTES + (size_t)W * sizeof(EnvS));
   int need = (num_envs + W - 1) / W;
   h->grid = need < prop.multiProcessorCount ? need : prop.multiProcessorCount;
-  for (auto fn : {(const void*)k_step<false>, (const void*)k_step<true>, (const void*)k_reset, (const void*)k_forward_debug, (const void*)k_obs_dm}) {
+  for (auto fn : tile_kernels) {
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
     if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
   }
+  e = cudaMalloc((void**)&h->d_scratch, sizeof(float) * (size_t)gs::stride * (size_t)h->grid * (size_t)W);
+  if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, cudaGetErrorString(e)); }
   if (const char* tr = getenv("DMB_TRACE")) {
     if (atoi(tr) != 0) {
       e = cudaMalloc((void**)&h->d_trace, sizeof(long long) * 8 * (size_t)h->grid);
@@ -1137,7 +1206,7 @@ int32_t dmb_get_trace(dmb_handle_t h, int64_t* host_out, int32_t max_ctas) {
 int dmb_destroy(dmb_handle_t h) {
   if (!h) return DMB_ERR_ARG;
   cudaSetDevice(h->device);
-  cudaFree(h->d_counter); cudaFree(h->d_cost); cudaFree(h->d_order); cudaFree(h->dmodel); cudaFree(h->d_cfg); cudaFree(h->d_vel); cudaFree(h->d_aux); cudaFree(h->d_trace);
+  cudaFree(h->d_counter); cudaFree(h->d_cost); cudaFree(h->d_order); cudaFree(h->dmodel); cudaFree(h->d_cfg); cudaFree(h->d_vel); cudaFree(h->d_aux); cudaFree(h->d_trace); cudaFree(h->d_scratch);
   delete h;
   return DMB_OK;
 }
@@ -1146,7 +1215,7 @@ static bool state_ok(const dmb_state_t* st) {
   return st && st->qpos && st->qvel && st->warm && st->clip && st->idx_init && st->idx_curr && st->reset_count &&
          st->ep_len && st->ep_ret && st->flags;
 }
-static DevPtrs devptrs(dmb_handle_t h) { DevPtrs P; P.counter = h->d_counter; P.cost = h->d_cost; P.order = h->d_order; P.model = h->dmodel; P.mocap_cfg = h->d_cfg; P.mocap_vel = h->d_vel; P.ref_aux = h->d_aux; P.trace = h->d_trace; return P; }
+static DevPtrs devptrs(dmb_handle_t h) { DevPtrs P; P.counter = h->d_counter; P.cost = h->d_cost; P.order = h->d_order; P.model = h->dmodel; P.mocap_cfg = h->d_cfg; P.mocap_vel = h->d_vel; P.ref_aux = h->d_aux; P.trace = h->d_trace; P.gscratch = h->d_scratch; return P; }
 
 int dmb_reset(dmb_handle_t h, const dmb_state_t* st, const uint8_t* mask, int32_t mode, float* obs, void* stream) {
   if (!h) return DMB_ERR_ARG;

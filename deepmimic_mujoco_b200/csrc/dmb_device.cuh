@@ -114,27 +114,27 @@ __device__ DMB_KIN_FN void kinematics(const ModelS& M, EnvS& S, int lane) {
     }
   }
   if (lane == 0) {
-    S.u.a.xpos[0] = S.u.a.xpos[1] = S.u.a.xpos[2] = 0.f;
-    S.u.a.xquat[0] = 1.f; S.u.a.xquat[1] = S.u.a.xquat[2] = S.u.a.xquat[3] = 0.f;
-    S.u.a.xmat[0] = 1.f; S.u.a.xmat[1] = 0.f; S.u.a.xmat[2] = 0.f; S.u.a.xmat[3] = 0.f; S.u.a.xmat[4] = 1.f; S.u.a.xmat[5] = 0.f;
-    S.u.a.xmat[6] = 0.f; S.u.a.xmat[7] = 0.f; S.u.a.xmat[8] = 1.f;
-    S.u.a.xipos[0] = S.u.a.xipos[1] = S.u.a.xipos[2] = 0.f;
+    S.o.k.xpos[0] = S.o.k.xpos[1] = S.o.k.xpos[2] = 0.f;
+    S.o.k.xquat[0] = 1.f; S.o.k.xquat[1] = S.o.k.xquat[2] = S.o.k.xquat[3] = 0.f;
+    S.o.k.xmat[0] = 1.f; S.o.k.xmat[1] = 0.f; S.o.k.xmat[2] = 0.f; S.o.k.xmat[3] = 0.f; S.o.k.xmat[4] = 1.f; S.o.k.xmat[5] = 0.f;
+    S.o.k.xmat[6] = 0.f; S.o.k.xmat[7] = 0.f; S.o.k.xmat[8] = 1.f;
+    S.o.k.xipos[0] = S.o.k.xipos[1] = S.o.k.xipos[2] = 0.f;
   }
   if (act) {
     quat = qnormalize(quat);
-    st3(&S.u.a.xpos[3 * b], pos);
-    S.u.a.xquat[4 * b] = quat.w; S.u.a.xquat[4 * b + 1] = quat.x; S.u.a.xquat[4 * b + 2] = quat.y; S.u.a.xquat[4 * b + 3] = quat.z;
+    st3(&S.o.k.xpos[3 * b], pos);
+    S.o.k.xquat[4 * b] = quat.w; S.o.k.xquat[4 * b + 1] = quat.x; S.o.k.xquat[4 * b + 2] = quat.y; S.o.k.xquat[4 * b + 3] = quat.z;
     float m[9];
     quat2mat(m, quat);
 #pragma unroll
-    for (int k = 0; k < 9; k++) S.u.a.xmat[9 * b + k] = m[k];
-    st3(&S.u.a.xipos[3 * b], pos + mat_vec(m, ld3(M.body_ipos[b])));
+    for (int k = 0; k < 9; k++) S.o.k.xmat[9 * b + k] = m[k];
+    st3(&S.o.k.xipos[3 * b], pos + mat_vec(m, ld3(M.body_ipos[b])));
     // world hinge axes, last joint first: axis_k = R(q after hinge k) a_k, then q <- q * conj(hinge k)
     Q4 q = quat;
 #pragma unroll
     for (int k = JPB - 1; k >= 0; k--) {
       if (k < jnum && M.jnt_type[jadr + k] == DMB_JNT_HINGE) {
-        st3(&S.cdof[6 * M.jnt_dofadr[jadr + k]], qrotv(q, ax[k]));
+        st3(&S.o.k.cdof[6 * M.jnt_dofadr[jadr + k]], qrotv(q, ax[k]));
         if (k > 0) {
           Q4 qc; qc.w = cs[k]; qc.x = -sn[k] * ax[k].x; qc.y = -sn[k] * ax[k].y; qc.z = -sn[k] * ax[k].z;
           q = qmul(q, qc);
@@ -153,20 +153,20 @@ __device__ DMB_KIN_FN void com_pos(const ModelS& M, EnvS& S, int lane) {
   const int b = lane;
   const bool act = b >= 1 && b < M.nbody;
   float ms = act ? M.body_mass[b] : 0.f;
-  V3 xi = act ? ld3(&S.u.a.xipos[3 * b]) : v3(0.f, 0.f, 0.f);
+  V3 xi = act ? ld3(&S.o.k.xipos[3 * b]) : v3(0.f, 0.f, 0.f);
   float cx = warp_sum(ms * xi.x) * M.inv_total_mass;
   float cy = warp_sum(ms * xi.y) * M.inv_total_mass;
   float cz = warp_sum(ms * xi.z) * M.inv_total_mass;
   if (lane == 0) { S.com[0] = cx; S.com[1] = cy; S.com[2] = cz; }
   const V3 com = v3(cx, cy, cz);
   if (lane < M.nbody) {
-    float* ci = &S.u.a.cinert[10 * b];
+    float* ci = &S.o.k.cinert[10 * b];
     if (!act) {
 #pragma unroll
       for (int k = 0; k < 10; k++) ci[k] = 0.f;
     } else {
       const float* I = M.body_inertia[b];
-      const float* R = &S.u.a.xmat[9 * b];
+      const float* R = &S.o.k.xmat[9 * b];
       // W = R * Ib * R'
       float Ib[9] = {I[0], I[3], I[4], I[3], I[1], I[5], I[4], I[5], I[2]};
       float RI[9], W[9];
@@ -190,15 +190,15 @@ __device__ DMB_KIN_FN void com_pos(const ModelS& M, EnvS& S, int lane) {
   }
   for (int d = lane; d < M.nv; d += 32) {
     const int db = M.dof_bodyid[d];
-    const V3 off = com - ld3(&S.u.a.xpos[3 * db]);
-    float* cd = &S.cdof[6 * d];
+    const V3 off = com - ld3(&S.o.k.xpos[3 * db]);
+    float* cd = &S.o.k.cdof[6 * d];
     const int kind = M.dof_kind[d], k = M.dof_axisk[d];
     if (kind == DOF_FREE_TRANS) {
       cd[0] = cd[1] = cd[2] = 0.f;
       cd[3] = k == 0 ? 1.f : 0.f; cd[4] = k == 1 ? 1.f : 0.f; cd[5] = k == 2 ? 1.f : 0.f;
     } else {
       V3 ax;
-      if (kind == DOF_FREE_ROT) { ax = v3(S.u.a.xmat[9 * db + k], S.u.a.xmat[9 * db + 3 + k], S.u.a.xmat[9 * db + 6 + k]); st3(cd, ax); }
+      if (kind == DOF_FREE_ROT) { ax = v3(S.o.k.xmat[9 * db + k], S.o.k.xmat[9 * db + 3 + k], S.o.k.xmat[9 * db + 6 + k]); st3(cd, ax); }
       else ax = ld3(cd);  // written by kinematics()
       st3(cd + 3, cross(ax, off));
     }
@@ -231,7 +231,7 @@ __device__ DMB_PHASE_FN void crb_factor(const ModelS& M, EnvS& S, int lane, floa
   const int b = lane;
   if (lane < M.nbody) {
 #pragma unroll
-    for (int k = 0; k < 10; k++) S.u.a.crb[10 * b + k] = S.u.a.cinert[10 * b + k];
+    for (int k = 0; k < 10; k++) S.o.k.crb[10 * b + k] = S.o.k.cinert[10 * b + k];
   }
   __syncwarp();
   for (int lev = M.maxdepth - 1; lev >= 1; lev--) {
@@ -240,20 +240,20 @@ __device__ DMB_PHASE_FN void crb_factor(const ModelS& M, EnvS& S, int lane, floa
       if (nc > 0) {
         float acc[10];
 #pragma unroll
-        for (int k = 0; k < 10; k++) acc[k] = S.u.a.crb[10 * b + k];
+        for (int k = 0; k < 10; k++) acc[k] = S.o.k.crb[10 * b + k];
         for (int c = 0; c < nc; c++) {
           const int ch = M.body_child[b][c];
 #pragma unroll
-          for (int k = 0; k < 10; k++) acc[k] += S.u.a.crb[10 * ch + k];
+          for (int k = 0; k < 10; k++) acc[k] += S.o.k.crb[10 * ch + k];
         }
 #pragma unroll
-        for (int k = 0; k < 10; k++) S.u.a.crb[10 * b + k] = acc[k];
+        for (int k = 0; k < 10; k++) S.o.k.crb[10 * b + k] = acc[k];
       }
     }
     __syncwarp();
   }
   DMB_TICK(11);
-  for (int d = lane; d < M.nv; d += 32) mul_inert_vec(&S.u.a.buf6[6 * d], &S.u.a.crb[10 * M.dof_bodyid[d]], &S.cdof[6 * d]);
+  for (int d = lane; d < M.nv; d += 32) mul_inert_vec(&S.o.k.buf6[6 * d], &S.o.k.crb[10 * M.dof_bodyid[d]], &S.o.k.cdof[6 * d]);
   __syncwarp();
   constexpr int NR = NMX / 32;  // rounds of 32 inertia entries
   {
@@ -264,8 +264,8 @@ __device__ DMB_PHASE_FN void crb_factor(const ModelS& M, EnvS& S, int lane, floa
       val[r] = 0.f;
       if (e < M.nM) {
         const int i = M.M_i[e], j = M.M_j[e];
-        const float* a = &S.cdof[6 * j];
-        const float* bf = &S.u.a.buf6[6 * i];
+        const float* a = &S.o.k.cdof[6 * j];
+        const float* bf = &S.o.k.buf6[6 * i];
         float s = a[0] * bf[0] + a[1] * bf[1] + a[2] * bf[2] + a[3] * bf[3] + a[4] * bf[4] + a[5] * bf[5];
         if (i == j) s += M.dof_armature[i];
         val[r] = s;
@@ -296,20 +296,23 @@ __device__ DMB_PHASE_FN void crb_factor(const ModelS& M, EnvS& S, int lane, floa
     const float* rowk = &S.qLD[(meta >> 16) + 1];
     const int16_t* rb = M.anc_rowbase[k];
     const float piv = rowk[-1];
+    // (slots past the step's pair range read the pivot word instead of a stray address, so that no lane ever reads a
+    // word another lane writes in the same step)
+    const int pva = (int)(meta >> 16);
     if (npair <= 32) {
-      const int d0 = rb[tp[0]] + qmp0;
+      const int d0 = lane < npair ? rb[tp[0]] + qmp0 : pva;
       const float p0 = rowk[tp[0]], q0 = rowk[tq[0]], v0 = S.qLD[d0];
       const float inv = rcp(piv);
       if (lane < npair) S.qLD[d0] = fmaf(-(p0 * inv), q0, v0);
     } else if (npair <= 64) {
-      const int d0 = rb[tp[0]] + qmp0, d1 = rb[tp[1]] + qmp1;
+      const int d0 = rb[tp[0]] + qmp0, d1 = lane + 32 < npair ? rb[tp[1]] + qmp1 : pva;
       const float p0 = rowk[tp[0]], q0 = rowk[tq[0]], v0 = S.qLD[d0];
       const float p1 = rowk[tp[1]], q1 = rowk[tq[1]], v1 = S.qLD[d1];
       const float inv = rcp(piv);
       S.qLD[d0] = fmaf(-(p0 * inv), q0, v0);
       if (lane + 32 < npair) S.qLD[d1] = fmaf(-(p1 * inv), q1, v1);
     } else {
-      const int d0 = rb[tp[0]] + qmp0, d1 = rb[tp[1]] + qmp1, d2 = rb[tp[2]] + qmp2;
+      const int d0 = rb[tp[0]] + qmp0, d1 = rb[tp[1]] + qmp1, d2 = lane + 64 < npair ? rb[tp[2]] + qmp2 : pva;
       const float p0 = rowk[tp[0]], q0 = rowk[tq[0]], v0 = S.qLD[d0];
       const float p1 = rowk[tp[1]], q1 = rowk[tq[1]], v1 = S.qLD[d1];
       const float p2 = rowk[tp[2]], q2 = rowk[tq[2]], v2 = S.qLD[d2];
@@ -347,7 +350,7 @@ __device__ DMB_PHASE_FN void crb_factor(const ModelS& M, EnvS& S, int lane, floa
 
 // ------------------------------------------------------------------------------------------
 // mj_comVel + mj_rne(flg_acc=0) + passive + actuation: leaves the smooth generalised force
-// qfrc_smooth = passive - bias + actuator in S.vec0.
+// qfrc_smooth = passive - bias + actuator in S.x_dv.
 // ------------------------------------------------------------------------------------------
 // Inclusive sums of a spatial 6-vector along the dof ancestor chains, dof d on lane d & 31 (x: d < 32,
 // xh: d >= 32), by pointer jumping: 4 rounds cover chains of up to 16 dofs.
@@ -367,7 +370,7 @@ __device__ __forceinline__ void chain_scan6(const ModelS& M, int lane, int nv, c
     }
   }
 }
-__device__ DMB_PHASE_FN void smooth_forces(const ModelS& M, EnvS& S, int lane, float* dbg_bias) {
+__device__ DMB_PHASE_FN void smooth_forces(const ModelS& M, EnvS& S, int lane, float* dbgrow) {
   const int nv = M.nv;
   const bool has_lo = lane < nv, has_hi = lane + 32 < nv;
   const int dl = has_lo ? lane : 0, dh = has_hi ? lane + 32 : 0;
@@ -377,7 +380,7 @@ __device__ DMB_PHASE_FN void smooth_forces(const ModelS& M, EnvS& S, int lane, f
   const float qvl = has_lo ? S.qvel[dl] : 0.f, qvh = has_hi ? S.qvel[dh] : 0.f;
   float cl[6], ch[6], V[6], Vh[6];
 #pragma unroll
-  for (int k = 0; k < 6; k++) { cl[k] = S.cdof[6 * dl + k]; ch[k] = S.cdof[6 * dh + k]; V[k] = cl[k] * qvl; Vh[k] = ch[k] * qvh; }
+  for (int k = 0; k < 6; k++) { cl[k] = S.o.k.cdof[6 * dl + k]; ch[k] = S.o.k.cdof[6 * dh + k]; V[k] = cl[k] * qvl; Vh[k] = ch[k] * qvh; }
   chain_scan6(M, lane, nv, jmp, V, Vh);
   // cdof_dot[d] = crossMotion(velocity seen by dof d, cdof[d]); A = chain sum of cdof_dot * qvel
   const int sl = has_lo ? M.dof_vsrc[dl] : -1, sh = has_hi ? M.dof_vsrc[dh] : -1;
@@ -394,17 +397,17 @@ __device__ DMB_PHASE_FN void smooth_forces(const ModelS& M, EnvS& S, int lane, f
 #pragma unroll
   for (int k = 0; k < 6; k++) { A[k] = sl >= 0 ? A[k] * qvl : 0.f; Ah[k] = sh >= 0 ? Ah[k] * qvh : 0.f; }
   chain_scan6(M, lane, nv, jmp, A, Ah);
-  // hand the sums of each body's last dof to the body lanes (velocity -> S.cvel, acceleration -> scratch)
-  float* acc = S.u.a.cdofd;
-  if (lane < 6) S.cvel[lane] = 0.f;
+  // hand the sums of each body's last dof to the body lanes (velocity -> S.o.k.cvel, acceleration -> scratch)
+  float* acc = S.o.k.acc;
+  if (lane < 6) S.o.k.cvel[lane] = 0.f;
   const int bl = has_lo ? M.dof_lastof[dl] : -1, bh = has_hi ? M.dof_lastof[dh] : -1;
   if (bl >= 0) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) { S.cvel[6 * bl + k] = V[k]; acc[6 * bl + k] = A[k]; }
+    for (int k = 0; k < 6; k++) { S.o.k.cvel[6 * bl + k] = V[k]; acc[6 * bl + k] = A[k]; }
   }
   if (bh >= 0) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) { S.cvel[6 * bh + k] = Vh[k]; acc[6 * bh + k] = Ah[k]; }
+    for (int k = 0; k < 6; k++) { S.o.k.cvel[6 * bh + k] = Vh[k]; acc[6 * bh + k] = Ah[k]; }
   }
   __syncwarp();
   // body forces  f = I a + v x* (I v)  with a = -gravity + chain acceleration
@@ -414,16 +417,16 @@ __device__ DMB_PHASE_FN void smooth_forces(const ModelS& M, EnvS& S, int lane, f
     if (b > 0) {
       float v[6], a[6], t1[6], t2[6];
 #pragma unroll
-      for (int k = 0; k < 6; k++) { v[k] = S.cvel[6 * b + k]; a[k] = acc[6 * b + k]; }
+      for (int k = 0; k < 6; k++) { v[k] = S.o.k.cvel[6 * b + k]; a[k] = acc[6 * b + k]; }
       a[3] -= M.gravity[0]; a[4] -= M.gravity[1]; a[5] -= M.gravity[2];
-      mul_inert_vec(f, &S.u.a.cinert[10 * b], a);
-      mul_inert_vec(t1, &S.u.a.cinert[10 * b], v);
+      mul_inert_vec(f, &S.o.k.cinert[10 * b], a);
+      mul_inert_vec(t1, &S.o.k.cinert[10 * b], v);
       cross_force(t2, v, t1);
 #pragma unroll
       for (int k = 0; k < 6; k++) f[k] += t2[k];
     }
 #pragma unroll
-    for (int k = 0; k < 6; k++) S.u.a.cfrc[6 * b + k] = f[k];
+    for (int k = 0; k < 6; k++) S.o.k.cfrc[6 * b + k] = f[k];
   }
   __syncwarp();
   for (int lev = M.maxdepth - 1; lev >= 1; lev--) {
@@ -433,24 +436,25 @@ __device__ DMB_PHASE_FN void smooth_forces(const ModelS& M, EnvS& S, int lane, f
       if (nc > 0) {
         float acc[6];
 #pragma unroll
-        for (int k = 0; k < 6; k++) acc[k] = S.u.a.cfrc[6 * b + k];
+        for (int k = 0; k < 6; k++) acc[k] = S.o.k.cfrc[6 * b + k];
         for (int c = 0; c < nc; c++) {
           const int ch = M.body_child[b][c];
 #pragma unroll
-          for (int k = 0; k < 6; k++) acc[k] += S.u.a.cfrc[6 * ch + k];
+          for (int k = 0; k < 6; k++) acc[k] += S.o.k.cfrc[6 * ch + k];
         }
 #pragma unroll
-        for (int k = 0; k < 6; k++) S.u.a.cfrc[6 * b + k] = acc[k];
+        for (int k = 0; k < 6; k++) S.o.k.cfrc[6 * b + k] = acc[k];
       }
     }
     __syncwarp();
   }
   for (int d = lane; d < M.nv; d += 32) {
-    const float* cd = &S.cdof[6 * d];
-    const float* cf = &S.u.a.cfrc[6 * M.dof_bodyid[d]];
+    const float* cd = &S.o.k.cdof[6 * d];
+    const float* cf = &S.o.k.cfrc[6 * M.dof_bodyid[d]];
     const float bias = cd[0] * cf[0] + cd[1] * cf[1] + cd[2] * cf[2] + cd[3] * cf[3] + cd[4] * cf[4] + cd[5] * cf[5];
-    if (dbg_bias) dbg_bias[d] = bias;
-    S.vec0[d] = -M.dof_damping[d] * S.qvel[d] - bias + S.ctrlf[d];
+    const float fs = -M.dof_damping[d] * S.qvel[d] - bias + S.ctrlf[d];
+    if (dbgrow) { dbgrow[dbg::qfrc_bias + d] = bias; dbgrow[dbg::qfrc_smooth + d] = fs; }
+    S.x_dv[d] = fs;   // qfrc_smooth (x_dv is scratch inside a forward evaluation)
   }
   __syncwarp();
 }
@@ -459,17 +463,17 @@ __device__ DMB_PHASE_FN void smooth_forces(const ModelS& M, EnvS& S, int lane, f
 __device__ __forceinline__ void geom_poses(const ModelS& M, EnvS& S, int lane) {
   if (lane < M.ngeom) {
     const int g = lane, gb = M.geom_bodyid[g];
-    st3(&S.u.b.gpos[3 * g], ld3(&S.u.b.xpos[3 * gb]) + mat_vec(&S.u.b.xmat[9 * gb], ld3(M.geom_pos[g])));
+    st3(&S.o.c.gpos[3 * g], ld3(&S.o.c.xpos[3 * gb]) + mat_vec(&S.o.c.xmat[9 * gb], ld3(M.geom_pos[g])));
     if (M.geom_identq[g]) {
 #pragma unroll
-      for (int k = 0; k < 9; k++) S.u.b.gmat[9 * g + k] = S.u.b.xmat[9 * gb + k];
+      for (int k = 0; k < 9; k++) S.o.c.gmat[9 * g + k] = S.o.c.xmat[9 * gb + k];
     } else {
-      Q4 qb; qb.w = S.u.b.xquat[4 * gb]; qb.x = S.u.b.xquat[4 * gb + 1]; qb.y = S.u.b.xquat[4 * gb + 2]; qb.z = S.u.b.xquat[4 * gb + 3];
+      Q4 qb; qb.w = S.o.c.xquat[4 * gb]; qb.x = S.o.c.xquat[4 * gb + 1]; qb.y = S.o.c.xquat[4 * gb + 2]; qb.z = S.o.c.xquat[4 * gb + 3];
       Q4 qg; qg.w = M.geom_quat[g][0]; qg.x = M.geom_quat[g][1]; qg.y = M.geom_quat[g][2]; qg.z = M.geom_quat[g][3];
       float m[9];
       quat2mat(m, qmul(qb, qg));
 #pragma unroll
-      for (int k = 0; k < 9; k++) S.u.b.gmat[9 * g + k] = m[k];
+      for (int k = 0; k < 9; k++) S.o.c.gmat[9 * g + k] = m[k];
     }
   }
   __syncwarp();
@@ -675,7 +679,7 @@ __device__ __forceinline__ void make_frame(float* f, V3 n, V3 y) {
   }
   y = y - dot(n, y) * n;
   normalize(y);
-  st3(f, n); st3(f + 3, y); st3(f + 6, cross(n, y));
+  st3(f, n); st3(f + 3, y);   // the second tangent is cross(n, y), recomputed where needed
 }
 
 // ------------------------------------------------------------------------------------------
@@ -690,9 +694,9 @@ __device__ DMB_PHASE_FN void collision(const ModelS& M, EnvS& S, int lane) {
     bool keep = false;
     if (p < M.npair) {
       const int g1 = M.pair_g1[p], g2 = M.pair_g2[p];
-      const V3 dif = ld3(&S.u.b.gpos[3 * g2]) - ld3(&S.u.b.gpos[3 * g1]);
+      const V3 dif = ld3(&S.o.c.gpos[3 * g2]) - ld3(&S.o.c.gpos[3 * g1]);
       if (M.geom_type[g1] == DMB_GEOM_PLANE) {
-        const V3 nrm = v3(S.u.b.gmat[9 * g1 + 2], S.u.b.gmat[9 * g1 + 5], S.u.b.gmat[9 * g1 + 8]);
+        const V3 nrm = v3(S.o.c.gmat[9 * g1 + 2], S.o.c.gmat[9 * g1 + 5], S.o.c.gmat[9 * g1 + 8]);
         keep = !(dot(dif, nrm) > M.geom_rbound[g2] + margin);
       } else {
         const float bound = M.geom_rbound[g1] + M.geom_rbound[g2] + margin;
@@ -700,7 +704,7 @@ __device__ DMB_PHASE_FN void collision(const ModelS& M, EnvS& S, int lane) {
       }
     }
     const unsigned bal = __ballot_sync(DMB_FULL, keep);
-    if (keep) S.u.b.surv[nsurv + __popc(bal & ((1u << lane) - 1u))] = p;
+    if (keep) S.o.c.surv[nsurv + __popc(bal & ((1u << lane) - 1u))] = (unsigned char)p;
     nsurv += __popc(bal);
   }
   __syncwarp();
@@ -709,12 +713,12 @@ __device__ DMB_PHASE_FN void collision(const ModelS& M, EnvS& S, int lane) {
     RawCon rc[4];
     int n = 0, g1 = 0, g2 = 0;
     if (base + lane < nsurv) {
-      const int p = S.u.b.surv[base + lane];
+      const int p = S.o.c.surv[base + lane];
       g1 = M.pair_g1[p]; g2 = M.pair_g2[p];
       const int t1 = M.geom_type[g1], t2 = M.geom_type[g2];
-      const V3 pos1 = ld3(&S.u.b.gpos[3 * g1]), pos2 = ld3(&S.u.b.gpos[3 * g2]);
-      const float* mat1 = &S.u.b.gmat[9 * g1];
-      const float* mat2 = &S.u.b.gmat[9 * g2];
+      const V3 pos1 = ld3(&S.o.c.gpos[3 * g1]), pos2 = ld3(&S.o.c.gpos[3 * g2]);
+      const float* mat1 = &S.o.c.gmat[9 * g1];
+      const float* mat2 = &S.o.c.gmat[9 * g2];
       const V3 s1 = ld3(M.geom_size[g1]), s2 = ld3(M.geom_size[g2]);
       if (t1 == DMB_GEOM_PLANE) {
         const V3 nrm = v3(mat1[2], mat1[5], mat1[8]);
@@ -761,12 +765,11 @@ __device__ DMB_PHASE_FN void collision(const ModelS& M, EnvS& S, int lane) {
     for (int i = 0; i < n; i++) {
       const int ci = off + i;
       if (ci < M.max_con) {
-        S.c_dist[ci] = rc[i].dist;
-        st3(&S.c_pos[3 * ci], rc[i].pos);
-        make_frame(&S.c_frame[9 * ci], rc[i].n, rc[i].y);
-        S.c_g1[ci] = g1; S.c_g2[ci] = g2;
+        S.o.c.c_dist[ci] = rc[i].dist;
+        st3(&S.o.c.c_pos[3 * ci], rc[i].pos);
+        make_frame(&S.o.c.c_frame[6 * ci], rc[i].n, rc[i].y);
         const int cd1 = M.geom_condim[g1], cd2 = M.geom_condim[g2];
-        S.c_dim[ci] = cd1 > cd2 ? cd1 : cd2;
+        S.c_meta[ci] = g1 | (g2 << 8) | ((cd1 > cd2 ? cd1 : cd2) << 16);   // first row (bits 24..31) set by count_rows
         S.c_mu[ci] = fmaxf(M.geom_mu[g1], M.geom_mu[g2]);
       }
     }
@@ -779,37 +782,47 @@ __device__ DMB_PHASE_FN void collision(const ModelS& M, EnvS& S, int lane) {
 
 // ------------------------------------------------------------------------------------------
 // mj_makeConstraint + mj_makeImpedance + mj_referenceConstraint, producing
-//   Y rows 0..nefc-1 = J rows (lane = dof), row nefc = qfrc_smooth,
-//   per-row pos / margin / R / aref (lane = row).
+//   Y rows 0..nefc-1 = J rows (lane = dof), per-row R / aref / dof support (lane = row).
 // Limit rows come first (joint order, lower then upper), then contacts in contact order:
 // 1 frictionless row (condim 1) or 4 pyramid edges (condim 3).
+// Row storage: the tile's PhaseR for up to RF rows, else (OVF) the warp's global scratch slot G.
 // ------------------------------------------------------------------------------------------
-__device__ DMB_PHASE_FN void make_constraint(const ModelS& M, EnvS& S, int lane) {
-  int* e_src = S.e_src;
-  // ---- joint limits: lane = joint
+template <bool OVF> struct RowView {
+  float *Y, *e_R, *e_aref, *e_b, *e_f, *AR;
+  unsigned long long* rowmask;
+  int* e_src;
+  __device__ __forceinline__ RowView(EnvS& S, float* G) {
+    if (OVF) {
+      Y = G + gs::Y; e_R = G + gs::e_R; e_aref = G + gs::e_aref; e_b = G + gs::e_b; e_f = G + gs::e_f; AR = G + gs::AR;
+      rowmask = reinterpret_cast<unsigned long long*>(G + gs::rowmask); e_src = reinterpret_cast<int*>(G + gs::e_src);
+    } else {
+      Y = S.o.r.Y; e_R = S.o.r.e_R; e_aref = S.o.r.e_aref; e_b = S.o.r.e_b; e_f = S.o.r.e_f; AR = S.o.r.AR;
+      rowmask = S.o.r.rowmask; e_src = S.e_src;
+    }
+  }
+};
+// limit row source: -(2 * (1 + joint) + side), side 0 = lower (J = +1), 1 = upper (J = -1)
+__device__ __forceinline__ int lim_joint(int src) { return ((-src) >> 1) - 1; }
+__device__ __forceinline__ int lim_side(int src) { return (-src) & 1; }
+
+// Row bookkeeping: active limits (lane = joint), contact row addresses (lane = contact), capacity check.
+// Writes e_src and the first-row field of c_meta; returns nefc.
+__device__ DMB_PHASE_FN int count_rows(const ModelS& M, EnvS& S, int lane, float* G) {
   int cnt = 0;
-  float dlo = 0.f, dhi = 0.f;
-  int dofj = 0;
+  bool lo = false, hi = false;
   if (lane < M.njnt && M.jnt_limited[lane] && M.jnt_type[lane] == DMB_JNT_HINGE) {
     const float q = S.qpos[M.jnt_qposadr[lane]];
-    dofj = M.jnt_dofadr[lane];
-    dlo = q - M.jnt_range[lane][0];
-    dhi = M.jnt_range[lane][1] - q;
-    cnt = (dlo < 0.f) + (dhi < 0.f);
+    lo = q - M.jnt_range[lane][0] < 0.f;
+    hi = M.jnt_range[lane][1] - q < 0.f;
+    cnt = (int)lo + (int)hi;
   }
   const int incl = warp_incl_scan(cnt, lane);
   const int nlimit = __shfl_sync(DMB_FULL, incl, 31);
-  {
-    int r = incl - cnt;
-    if (dlo < 0.f && cnt) { S.e_pos[r] = dlo; S.e_margin[r] = 0.f; e_src[r] = -(1 + dofj) * 2; r++; }      // J = +1
-    if (dhi < 0.f && cnt) { S.e_pos[r] = dhi; S.e_margin[r] = 0.f; e_src[r] = -(1 + dofj) * 2 - 1; }       // J = -1
-  }
-  // ---- contact row addresses: lane = contact
   int ncon = S.ncon;
   int nrow = 0;
-  if (lane < ncon) nrow = S.c_dim[lane] == 1 ? 1 : 4;
+  if (lane < ncon) nrow = cm_dim(S.c_meta[lane]) == 1 ? 1 : 4;
   const int cincl = warp_incl_scan(nrow, lane);
-  int adr = nlimit + cincl - nrow;
+  const int adr = nlimit + cincl - nrow;
   const bool fits = lane < ncon && adr + nrow <= M.max_efc;
   const unsigned fitbal = __ballot_sync(DMB_FULL, fits);
   // contacts are dropped from the first one that does not fit (oracle: make_constraint)
@@ -820,81 +833,100 @@ __device__ DMB_PHASE_FN void make_constraint(const ModelS& M, EnvS& S, int lane)
     if (lane == 0) { S.flags |= 2; S.ncon = ncon; }
   }
   int nefc = nlimit;
-  if (ncon > 0) {
-    const int lastadr = __shfl_sync(DMB_FULL, adr + nrow, ncon - 1);
-    nefc = lastadr;
+  if (ncon > 0) nefc = __shfl_sync(DMB_FULL, adr + nrow, ncon - 1);
+  int* e_src = nefc > RF ? reinterpret_cast<int*>(G + gs::e_src) : S.e_src;
+  {
+    int r = incl - cnt;
+    if (lo) e_src[r++] = -(2 * (1 + lane));
+    if (hi) e_src[r] = -(2 * (1 + lane) + 1);
   }
   if (lane < ncon) {
-    S.c_adr[lane] = adr;
-    for (int k = 0; k < nrow; k++) { e_src[adr + k] = lane * 4 + k; S.e_pos[adr + k] = S.c_dist[lane]; S.e_margin[adr + k] = M.margin; }
+    S.c_meta[lane] = (S.c_meta[lane] & 0xffffff) | (adr << 24);
+    for (int k = 0; k < nrow; k++) e_src[adr + k] = lane * 4 + k;
   }
   if (lane == 0) { S.nefc = nefc; S.nlimit = nlimit; }
   __syncwarp();
-  // ---- J rows into Y: lane = dof
+  return nefc;
+}
+
+template <bool OVF>
+__device__ DMB_PHASE_FN void build_rows(const ModelS& M, EnvS& S, int lane, float* G, float* dbgrow) {
+  const RowView<OVF> V(S, G);
+  const int nefc = S.nefc, nlimit = S.nlimit, ncon = S.ncon;
+  // ---- J rows into Y: lane = dof.  Y lies in front of cdof / the contact geometry, which are read here.
   const V3 com = ld3(S.com);
   for (int d = lane; d < M.nv; d += 32) {
     for (int r = 0; r < nlimit; r++) {
-      const int src = -e_src[r];          // 2*(1+dof) or 2*(1+dof)+1
-      const int dof = (src >> 1) - 1;
-      S.u.Y[r * YS + d] = (dof == d) ? ((src & 1) ? -1.f : 1.f) : 0.f;
+      const int src = V.e_src[r];
+      V.Y[r * YS + d] = (M.jnt_dofadr[lim_joint(src)] == d) ? (lim_side(src) ? -1.f : 1.f) : 0.f;
     }
-    const V3 ca = ld3(&S.cdof[6 * d]), cl = ld3(&S.cdof[6 * d + 3]);
+    const V3 ca = ld3(&S.o.c.cdof[6 * d]), cl = ld3(&S.o.c.cdof[6 * d + 3]);
     for (int c = 0; c < ncon; c++) {
-      const int b1 = M.geom_bodyid[S.c_g1[c]], b2 = M.geom_bodyid[S.c_g2[c]];
+      const int cm = S.c_meta[c];
+      const int b1 = M.geom_bodyid[cm_g1(cm)], b2 = M.geom_bodyid[cm_g2(cm)];
       const int in2 = (int)((M.body_dofmask[b2] >> d) & 1ull), in1 = (int)((M.body_dofmask[b1] >> d) & 1ull);
       const float sg = (float)(in2 - in1);
-      const int a = S.c_adr[c];
-      const float* fr = &S.c_frame[9 * c];
-      if (S.c_dim[c] == 1) {
+      const int a = cm_adr(cm);
+      const float* fr = &S.o.c.c_frame[6 * c];
+      if (cm_dim(cm) == 1) {
         float jn = 0.f;
-        if (sg != 0.f) { const V3 p = cl + cross(ca, ld3(&S.c_pos[3 * c]) - com); jn = sg * dot(ld3(fr), p); }
-        S.u.Y[a * YS + d] = jn;
+        if (sg != 0.f) { const V3 p = cl + cross(ca, ld3(&S.o.c.c_pos[3 * c]) - com); jn = sg * dot(ld3(fr), p); }
+        V.Y[a * YS + d] = jn;
       } else {
         float jn = 0.f, j1 = 0.f, j2 = 0.f;
         if (sg != 0.f) {
-          const V3 p = cl + cross(ca, ld3(&S.c_pos[3 * c]) - com);
-          jn = sg * dot(ld3(fr), p); j1 = sg * dot(ld3(fr + 3), p); j2 = sg * dot(ld3(fr + 6), p);
+          const V3 p = cl + cross(ca, ld3(&S.o.c.c_pos[3 * c]) - com);
+          const V3 n = ld3(fr), t1 = ld3(fr + 3);
+          jn = sg * dot(n, p); j1 = sg * dot(t1, p); j2 = sg * dot(cross(n, t1), p);
         }
         // base rows of the contact frame; half_solve_rows() solves these three together and then
         // expands them to the four pyramid edges  n +- mu t1, n +- mu t2
-        S.u.Y[a * YS + d] = jn;
-        S.u.Y[(a + 1) * YS + d] = j1;
-        S.u.Y[(a + 2) * YS + d] = j2;
+        V.Y[a * YS + d] = jn;
+        V.Y[(a + 1) * YS + d] = j1;
+        V.Y[(a + 2) * YS + d] = j2;
       }
     }
   }
-  // ---- per-row impedance, R, aref: lane = row
+  __syncwarp();   // cdof is dead from here on: the row scalars below overwrite it
+  // ---- per-row impedance, R, aref: lane = row.  Values are computed for all rows of a round first, then stored
+  // (the stores land on cdof, which no lane reads any more, but cvel / the contact geometry are still read)
   for (int r = lane; r < nefc; r += 32) {
-    const int src = e_src[r];
-    float dA, vel, mu = 0.f;
+    const int src = V.e_src[r];
+    float dA, vel, mu = 0.f, pos, mg;
+    unsigned long long mask;
     bool pyramid = false;
     if (src < 0) {
-      const int s2 = -src, dof = (s2 >> 1) - 1;
+      const int j = lim_joint(src), dof = M.jnt_dofadr[j];
+      const float q = S.qpos[M.jnt_qposadr[j]];
+      pos = lim_side(src) ? M.jnt_range[j][1] - q : q - M.jnt_range[j][0];
+      mg = 0.f;
       dA = M.dof_invw[dof];
-      vel = (s2 & 1) ? -S.qvel[dof] : S.qvel[dof];
-      S.rowmask[r] = M.dof_ancmask[dof] | (1ull << dof);
+      vel = lim_side(src) ? -S.qvel[dof] : S.qvel[dof];
+      mask = M.dof_ancmask[dof] | (1ull << dof);
     } else {
       const int c = src >> 2, k = src & 3;
-      const int b1 = M.geom_bodyid[S.c_g1[c]], b2 = M.geom_bodyid[S.c_g2[c]];
-      S.rowmask[r] = M.body_dofmask[b1] | M.body_dofmask[b2];
+      const int cm = S.c_meta[c];
+      const int b1 = M.geom_bodyid[cm_g1(cm)], b2 = M.geom_bodyid[cm_g2(cm)];
+      mask = M.body_dofmask[b1] | M.body_dofmask[b2];
+      pos = S.o.c.c_dist[c]; mg = M.margin;
       const float tran = M.body_invw[b1] + M.body_invw[b2];
-      const V3 off = ld3(&S.c_pos[3 * c]) - com;
-      const V3 v2 = ld3(&S.cvel[6 * b2 + 3]) + cross(ld3(&S.cvel[6 * b2]), off);
-      const V3 v1 = ld3(&S.cvel[6 * b1 + 3]) + cross(ld3(&S.cvel[6 * b1]), off);
+      const V3 off = ld3(&S.o.c.c_pos[3 * c]) - com;
+      const V3 v2 = ld3(&S.o.c.cvel[6 * b2 + 3]) + cross(ld3(&S.o.c.cvel[6 * b2]), off);
+      const V3 v1 = ld3(&S.o.c.cvel[6 * b1 + 3]) + cross(ld3(&S.o.c.cvel[6 * b1]), off);
       const V3 vr = v2 - v1;
-      const float* fr = &S.c_frame[9 * c];
-      const float vn = dot(ld3(fr), vr);
-      if (S.c_dim[c] == 1) { dA = tran; vel = vn; }
+      const float* fr = &S.o.c.c_frame[6 * c];
+      const V3 n = ld3(fr), t1 = ld3(fr + 3);
+      const float vn = dot(n, vr);
+      if (cm_dim(cm) == 1) { dA = tran; vel = vn; }
       else {
         pyramid = true;
         mu = S.c_mu[c];
-        const float vt = dot(ld3(fr + 3 * (1 + (k >> 1))), vr);
+        const float vt = dot((k >> 1) ? cross(n, t1) : t1, vr);
         vel = vn + ((k & 1) ? -mu : mu) * vt;
         dA = tran + mu * mu * tran;
       }
     }
     // getimpedance (solimp sigmoid)
-    const float pos = S.e_pos[r], mg = S.e_margin[r];
     float dmin = clampf(M.solimp[0], 0.0001f, 0.9999f), dmax = clampf(M.solimp[1], 0.0001f, 0.9999f);
     const float width = M.solimp[2], mid = clampf(M.solimp[3], 0.0001f, 0.9999f), power = fmaxf(M.solimp[4], 1.f);
     float imp;
@@ -913,8 +945,10 @@ __device__ DMB_PHASE_FN void make_constraint(const ModelS& M, EnvS& S, int lane)
     }
     float R = fmaxf((1.f - imp) * dA / imp, DMB_MINVAL);
     if (pyramid) R = 2.f * mu * mu * R;
-    S.e_R[r] = R;
-    S.e_aref[r] = -M.imp_b * vel - M.imp_k * imp * (pos - mg);
+    V.e_R[r] = R;
+    V.e_aref[r] = -M.imp_b * vel - M.imp_k * imp * (pos - mg);
+    V.rowmask[r] = mask;
+    if (dbgrow) dbgrow[dbg::efc_pos + r] = pos;
   }
   __syncwarp();
 }
@@ -992,7 +1026,9 @@ __device__ void mul_L_sqrtD(const ModelS& M, EnvS& S, int lane, const float* x, 
 // are eliminated together (factor entries and index work shared) and then expanded to the four
 // edge rows  n +- mu t1,  n +- mu t2  (the elimination is linear).
 // ------------------------------------------------------------------------------------------
-__device__ DMB_PHASE_FN void half_solve_rows(const ModelS& M, EnvS& S, int lane, int r_begin, int r_end) {
+template <bool OVF>
+__device__ DMB_PHASE_FN void half_solve_rows(const ModelS& M, EnvS& S, int lane, int r_begin, int r_end, float* G) {
+  const RowView<OVF> V(S, G);
   const bool has_lo = lane < M.nv, has_hi = lane + 32 < M.nv;
   const float dlo = has_lo ? S.dsq[lane] : 0.f, dhi = has_hi ? S.dsq[lane + 32] : 0.f;
   const unsigned nd_lo = has_lo ? (unsigned)M.dof_ndesc[lane] : 0u, nd_hi = has_hi ? (unsigned)M.dof_ndesc[lane + 32] : 0u;
@@ -1001,9 +1037,9 @@ __device__ DMB_PHASE_FN void half_solve_rows(const ModelS& M, EnvS& S, int lane,
   const int16_t* Lend = M.dof_Lend;
   int r = r_begin;   // r_begin must be the first row of a group (a limit row, a frictionless row or a pyramid)
   while (r < r_end) {
-    const int src = S.e_src[r];
-    const bool pyr = src >= 0 && S.c_dim[src >> 2] == 3;
-    float* y = &S.u.Y[r * YS];
+    const int src = V.e_src[r];
+    const bool pyr = src >= 0 && cm_dim(S.c_meta[src >> 2]) == 3;
+    float* y = &V.Y[r * YS];
     float a_lo = has_lo ? y[lane] : 0.f, a_hi = has_hi ? y[lane + 32] : 0.f;
     float b_lo = 0.f, b_hi = 0.f, c_lo = 0.f, c_hi = 0.f;
     if (pyr) {
@@ -1011,7 +1047,7 @@ __device__ DMB_PHASE_FN void half_solve_rows(const ModelS& M, EnvS& S, int lane,
       if (has_hi) { b_hi = y[YS + lane + 32]; c_hi = y[2 * YS + lane + 32]; }
     }
     // support dofs, deepest first: ids >= 32 (they can feed both halves), then ids < 32 (only the low half)
-    const unsigned long long sup64 = S.rowmask[r];
+    const unsigned long long sup64 = V.rowmask[r];
     unsigned sup_hi = (unsigned)(sup64 >> 32), sup = (unsigned)sup64 & ~1u;   // dof 0 has no ancestors
     while (sup_hi) {
       const int ih = 31 - __clz(sup_hi);
@@ -1074,7 +1110,9 @@ __device__ __forceinline__ int tri(int r) { return (r * (r + 1)) >> 1; }
 // Gram matrix AR = Y Y' + diag(R) (packed lower triangle) and b = Y y_s - aref.
 // lane = matrix entry: the nefc(nefc+1)/2 pairs (+ nefc entries for b) are dealt out 32 at a time;
 // each lane runs the sparse dot product over the intersection of the two row supports.
-__device__ DMB_PHASE_FN void gram(const ModelS& M, EnvS& S, int lane, int nefc, int t_begin, int t_end) {
+template <bool OVF>
+__device__ DMB_PHASE_FN void gram(const ModelS& M, EnvS& S, int lane, int nefc, int t_begin, int t_end, float* G) {
+  const RowView<OVF> V(S, G);
   const int npair = tri(nefc), ntask = min(npair + nefc, t_end);
   for (int t = t_begin + lane; t < ntask; t += 32) {
     // one loop for both kinds of task (a lane with a matrix entry and a lane with an entry of b would otherwise
@@ -1087,13 +1125,13 @@ __device__ DMB_PHASE_FN void gram(const ModelS& M, EnvS& S, int lane, int nefc, 
       if (tri(r + 1) <= t) r++;
       if (tri(r) > t) r--;
       c = t - tri(r);
-      z = &S.u.Y[c * YS];
-      mk = S.rowmask[r] & S.rowmask[c];
+      z = &V.Y[c * YS];
+      mk = V.rowmask[r] & V.rowmask[c];
     } else {
       r = t - npair;
-      mk = S.rowmask[r];
+      mk = V.rowmask[r];
     }
-    const float* yr = &S.u.Y[r * YS];
+    const float* yr = &V.Y[r * YS];
     float acc = 0.f;
     unsigned lo = (unsigned)mk, hi = (unsigned)(mk >> 32);
     while (hi) {  // dofs >= 32
@@ -1106,21 +1144,22 @@ __device__ DMB_PHASE_FN void gram(const ModelS& M, EnvS& S, int lane, int nefc, 
       lo ^= 1u << k;
       acc = fmaf(yr[k], z[k], acc);
     }
-    if (t < npair) S.AR[t] = (c == r) ? acc + S.e_R[r] : acc;
-    else S.e_b[r] = acc - S.e_aref[r];
+    if (t < npair) V.AR[t] = (c == r) ? acc + V.e_R[r] : acc;
+    else V.e_b[r] = acc - V.e_aref[r];
   }
   __syncwarp();
 }
 
-// PGS sweeps over rows [0, nefc): residuals res = AR f + b live in registers (lane = row, and
-// row + 32 when HI); a row update broadcasts its force increment and every lane applies one
-// column of AR.  All rows are scalar with force >= 0 (limits, frictionless normals, pyramid edges).
+// PGS sweeps over rows [0, nefc) with AR in memory (only used by stages with more than RF rows, whose rows live in
+// the global scratch slot): residuals res = AR f + b live in registers (lane = row, and row + 32 when HI); a row
+// update broadcasts its force increment and every lane applies one column of AR.  All rows are scalar with
+// force >= 0 (limits, frictionless normals, pyramid edges).
 template <bool HI>
-__device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, int nefc, float& f0, float& f1,
-                                          float& res0, float& res1) {
+__device__ __noinline__ int pgs_sweeps(const ModelS& M, const float* AR, int lane, int nefc, float& f0, float& f1,
+                                       float& res0, float& res1) {
   const int r0 = lane, r1 = lane + 32;
   const bool a0 = r0 < nefc, a1 = HI && r1 < nefc;
-  const float d0 = a0 ? S.AR[tri(r0) + r0] : 1.f, d1 = a1 ? S.AR[tri(r1) + r1] : 1.f;
+  const float d0 = a0 ? AR[tri(r0) + r0] : 1.f, d1 = a1 ? AR[tri(r1) + r1] : 1.f;
   const float inv0 = 1.0f / d0, inv1 = 1.0f / d1;
   const int t0 = tri(r0), t1 = tri(r1);
   const int nlo = HI ? 32 : nefc;
@@ -1129,20 +1168,18 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
     // the owner of a row remembers its increment and the residual it was computed from; the
     // cost decrease  -(0.5 delta^2 AR_ii + delta res_i)  is summed once per sweep
     float dm0 = 0.f, rm0 = 0.f, dm1 = 0.f, rm1 = 0.f;
-    // branch-free row updates; the AR column of row i+1 is loaded while row i is in flight, so the
-    // serial chain per row is FFMA -> FMNMX -> FADD -> SHFL -> FFMA.  Column i of the packed
-    // triangle for lane-row r is AR[tri(r) + i] (i <= r) or AR[tri(i) + r] (i > r): the index moves
-    // by 1 while i < r and by i + 1 afterwards.  Loads are unpredicated (indices past the last row
-    // stay inside the tile; lanes without a row never own an update).
+    // Column i of the packed triangle for lane-row r is AR[tri(r) + i] (i <= r) or AR[tri(i) + r] (i > r): the
+    // index moves by 1 while i < r and by i + 1 afterwards.  Loads are unpredicated (indices past the last row
+    // are clamped into the triangle; lanes without a row never own an update).
     int idx0 = t0, idx1 = t1;
-    float acol0 = S.AR[idx0];
-    float acol1 = HI ? S.AR[a1 ? idx1 : 0] : 0.f;
+    float acol0 = AR[idx0 < NTRI ? idx0 : 0];
+    float acol1 = HI ? AR[a1 ? idx1 : 0] : 0.f;
 #pragma unroll 2
     for (int i = 0; i < nlo; i++) {
       idx0 += (i < r0) ? 1 : i + 1;
-      const float an0 = S.AR[idx0];
+      const float an0 = AR[idx0 < NTRI ? idx0 : 0];
       float an1 = 0.f;
-      if (HI) { idx1 += (i < r1) ? 1 : i + 1; an1 = S.AR[a1 ? idx1 : 0]; }
+      if (HI) { idx1 += (i < r1) ? 1 : i + 1; an1 = AR[(a1 && idx1 < NTRI) ? idx1 : 0]; }
       const float fnew = fmaxf(0.f, f0 - res0 * inv0);
       const float mine = fnew - f0;
       const float delta = __shfl_sync(DMB_FULL, mine, i);
@@ -1155,8 +1192,8 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
       for (int i = 32; i < nefc; i++) {
         idx0 += i + 1;                                          // i >= 32 > r0
         idx1 += (i < r1) ? 1 : i + 1;
-        const float an0 = S.AR[idx0 < NTRI ? idx0 : 0];
-        const float an1 = S.AR[(a1 && idx1 < NTRI) ? idx1 : 0];
+        const float an0 = AR[idx0 < NTRI ? idx0 : 0];
+        const float an1 = AR[(a1 && idx1 < NTRI) ? idx1 : 0];
         const float fnew = fmaxf(0.f, f1 - res1 * inv1);
         const float mine = fnew - f1;
         const float delta = __shfl_sync(DMB_FULL, mine, i - 32);
@@ -1175,30 +1212,28 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, EnvS& S, int lane, in
   return iter;
 }
 
-// nefc <= 32 (every env of the benchmark rollout): this lane's column of AR (= its row, AR is
-// symmetric) is held in 32 registers, loaded once per solve; a sweep is then a fully unrolled chain of
-// row updates with no shared-memory access and no index arithmetic.  The increment is computed as
-// max(-f, -res/AR_ii) (= max(0, f - res/AR_ii) - f without the extra dependent subtraction), so the
-// serial chain per row is FMUL -> FMNMX -> SHFL -> FFMA.
-__device__ __forceinline__ float acol_diag(const EnvS& S, int t0, int r0) { return S.AR[t0 + r0]; }
-__device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, EnvS& S, int lane, int nefc, float& f0, float& res0) {
+// nefc <= RF (all but a handful of the benchmark's stage evaluations): this lane's column of AR (= its row, AR is
+// symmetric) is held in RF registers, loaded once per solve; a sweep is then a fully unrolled chain of
+// row updates with no shared-memory access and no index arithmetic.  Rows are kept scaled by -1/AR_ii
+// (sres = -res / AR_ii, scaled column acol * -1/AR_ii), so the increment is max(-f, sres) and the serial chain per
+// row is FMNMX -> SHFL -> FFMA.  The column is fetched in chunks of 8 rows behind a uniform branch (most envs have
+// fewer than 8 rows); lanes without a row keep a zero column.
+__device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, const float* AR, int lane, int nefc, float& f0, float& res0) {
+  static_assert(RF % 8 == 0 && RF <= 32, "column chunks of 8 rows");
   const int r0 = lane, t0 = tri(r0);
   const bool a0 = r0 < nefc;
-  // Rows are kept scaled by -1/AR_ii (sres = -res / AR_ii, scaled column acol * -1/AR_ii), so the increment is
-  // max(-f, sres) and the serial chain per row is FMNMX -> SHFL -> FFMA.  The column is fetched in chunks of 8
-  // rows behind a uniform branch (most envs have fewer than 8 rows); lanes without a row keep a zero column.
-  const float d0 = a0 ? acol_diag(S, t0, r0) : 1.f;
+  const float d0 = a0 ? AR[t0 + r0] : 1.f;
   const float ninv0 = -rcp(d0);
-  float acol[32];
+  float acol[RF];
 #pragma unroll
-  for (int i = 0; i < 32; i++) acol[i] = 0.f;
+  for (int i = 0; i < RF; i++) acol[i] = 0.f;
 #pragma unroll
-  for (int c = 0; c < 4; c++) {
+  for (int c = 0; c < RF / 8; c++) {
     if (8 * c < nefc) {
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         const int i = 8 * c + j;
-        if (a0 && i < nefc) acol[i] = S.AR[i <= r0 ? t0 + i : tri(i) + r0] * ninv0;
+        if (a0 && i < nefc) acol[i] = AR[i <= r0 ? t0 + i : tri(i) + r0] * ninv0;
       }
     }
   }
@@ -1209,7 +1244,7 @@ __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, EnvS& S, int lane
     // AR symmetric): exact like the per-row sum MuJoCo accumulates, without any per-row bookkeeping.
     const float fs = f0, ss = sres;
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) {
+    for (int i = 0; i < RF; i += 2) {
       if (i >= nefc) break;   // rows are taken in pairs; a row past nefc has no owner and a zero column
       {
         const float mine = fmaxf(-f0, sres);
@@ -1234,41 +1269,47 @@ __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, EnvS& S, int lane
 
 // ------------------------------------------------------------------------------------------
 // mj_fwdConstraint: warmstart + PGS on the dual, then qacc = L^-1 D^-1/2 (y_s + Y' f).
+// S.qacc holds qacc_warmstart on entry and the new acceleration on exit.
 // ------------------------------------------------------------------------------------------
-__device__ DMB_PHASE_FN void solve_constraints(const ModelS& M, EnvS& S, int lane, int nefc) {
+template <bool OVF>
+__device__ DMB_PHASE_FN void solve_constraints(const ModelS& M, EnvS& S, int lane, int nefc, float* G) {
+  const RowView<OVF> V(S, G);
   int iter = 0;
   if (nefc > 0) {
     const int r0 = lane, r1 = lane + 32;
-    const bool a0 = r0 < nefc, a1 = r1 < nefc;
+    const bool a0 = r0 < nefc, a1 = OVF && r1 < nefc;
     // warmstart forces from qacc_warmstart: jar = J qacc_w - aref = Y (D^1/2 L qacc_w) - aref
-    mul_L_sqrtD(M, S, lane, S.warm, S.vec1);
+    float* w = S.x_dv;   // scratch (x_dv is dead inside a forward evaluation)
+    mul_L_sqrtD(M, S, lane, S.qacc, w);
     float jar0 = 0.f, jar1 = 0.f;
-    if (a0) { const float* y = &S.u.Y[r0 * YS]; for (int k = 0; k < M.nv; k++) jar0 += y[k] * S.vec1[k]; jar0 -= S.e_aref[r0]; }
-    if (a1) { const float* y = &S.u.Y[r1 * YS]; for (int k = 0; k < M.nv; k++) jar1 += y[k] * S.vec1[k]; jar1 -= S.e_aref[r1]; }
-    float f0 = (a0 && jar0 < 0.f) ? -jar0 / S.e_R[r0] : 0.f;
-    float f1 = (a1 && jar1 < 0.f) ? -jar1 / S.e_R[r1] : 0.f;
-    if (a0) S.e_f[r0] = f0;
-    if (a1) S.e_f[r1] = f1;
+    if (a0) { const float* y = &V.Y[r0 * YS]; for (int k = 0; k < M.nv; k++) jar0 += y[k] * w[k]; jar0 -= V.e_aref[r0]; }
+    if (a1) { const float* y = &V.Y[r1 * YS]; for (int k = 0; k < M.nv; k++) jar1 += y[k] * w[k]; jar1 -= V.e_aref[r1]; }
+    float f0 = (a0 && jar0 < 0.f) ? -jar0 / V.e_R[r0] : 0.f;
+    float f1 = (a1 && jar1 < 0.f) ? -jar1 / V.e_R[r1] : 0.f;
+    if (a0) V.e_f[r0] = f0;
+    if (a1) V.e_f[r1] = f1;
     __syncwarp();
     // res = AR f + b ; dual cost = sum f (0.5 (res - b) + b); a positive cost falls back to f = 0
-    const float b0 = a0 ? S.e_b[r0] : 0.f, b1 = a1 ? S.e_b[r1] : 0.f;
+    const float b0 = a0 ? V.e_b[r0] : 0.f, b1 = a1 ? V.e_b[r1] : 0.f;
     float res0 = b0, res1 = b1;
     for (int s = 0; s < nefc; s++) {
-      const float fs = S.e_f[s];
+      const float fs = V.e_f[s];
       if (fs != 0.f) {
-        if (a0) res0 += S.AR[r0 >= s ? tri(r0) + s : tri(s) + r0] * fs;
-        if (a1) res1 += S.AR[r1 >= s ? tri(r1) + s : tri(s) + r1] * fs;
+        if (a0) res0 += V.AR[r0 >= s ? tri(r0) + s : tri(s) + r0] * fs;
+        if (a1) res1 += V.AR[r1 >= s ? tri(r1) + s : tri(s) + r1] * fs;
       }
     }
     float cost = f0 * 0.5f * (res0 + b0) + f1 * 0.5f * (res1 + b1);
     cost = warp_sum(cost);
     if (cost > 0.f) { f0 = 0.f; f1 = 0.f; res0 = b0; res1 = b1; }
     DMB_TICK(14);
-    iter = nefc > 32 ? pgs_sweeps<true>(M, S, lane, nefc, f0, f1, res0, res1)
-                     : pgs_sweeps_reg(M, S, lane, nefc, f0, res0);
+    if (OVF) iter = nefc > 32 ? pgs_sweeps<true>(M, V.AR, lane, nefc, f0, f1, res0, res1)
+                              : pgs_sweeps<false>(M, V.AR, lane, nefc, f0, f1, res0, res1);
+    else iter = pgs_sweeps_reg(M, V.AR, lane, nefc, f0, res0);
     DMB_TICK(15);
-    if (a0) S.e_f[r0] = f0;
-    if (a1) S.e_f[r1] = f1;
+    __syncwarp();
+    if (a0) V.e_f[r0] = f0;
+    if (a1) V.e_f[r1] = f1;
     __syncwarp();
   }
   if (lane == 0) {
@@ -1281,17 +1322,17 @@ __device__ DMB_PHASE_FN void solve_constraints(const ModelS& M, EnvS& S, int lan
   // t = y_s + sum_r Y_r f_r  (lane = dof), then qacc = L^-1 D^-1/2 t in registers
   float tlo = lane < M.nv ? S.ys[lane] : 0.f, thi = lane + 32 < M.nv ? S.ys[lane + 32] : 0.f;
   for (int r = 0; r < nefc; r++) {
-    const float fr = S.e_f[r];
+    const float fr = V.e_f[r];
     if (fr != 0.f) {
-      if (lane < M.nv) tlo += S.u.Y[r * YS + lane] * fr;
-      if (lane + 32 < M.nv) thi += S.u.Y[r * YS + lane + 32] * fr;
+      if (lane < M.nv) tlo += V.Y[r * YS + lane] * fr;
+      if (lane + 32 < M.nv) thi += V.Y[r * YS + lane + 32] * fr;
     }
   }
   if (lane < M.nv) tlo *= S.dsq[lane];
   if (lane + 32 < M.nv) thi *= S.dsq[lane + 32];
   reg_solve_L(M, S, lane, tlo, thi);
-  if (lane < M.nv) { S.qacc[lane] = tlo; S.warm[lane] = tlo; }
-  if (lane + 32 < M.nv) { S.qacc[lane + 32] = thi; S.warm[lane + 32] = thi; }
+  if (lane < M.nv) S.qacc[lane] = tlo;
+  if (lane + 32 < M.nv) S.qacc[lane + 32] = thi;
   __syncwarp();
 }
 
@@ -1332,8 +1373,9 @@ __device__ __forceinline__ void patient_barrier(int* cnt, int W, int patience, i
 
 template <bool LOCKSTEP>
 __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, float* dbgrow, bool active, int bar_id,
-                                         int bar_n, int* arrive, EnvS* tiles, int* share_cnt) {
+                                         int bar_n, int* arrive, EnvS* tiles, int* share_cnt, float* gcta) {
 #define DMB_PHASE_SYNC(bit) do { if (LOCKSTEP && (M.sync_mask & (bit))) { if (M.arrive_k > 0) arrival_barrier(arrive, bar_n >> 5, M.arrive_k, lane); else if (M.patience > 0) patient_barrier(arrive, bar_n >> 5, M.patience, lane); else group_barrier(bar_id, bar_n); } } while (0)
+  float* const G = gcta + (size_t)(threadIdx.x >> 5) * gs::stride;   // this warp's scratch slot (stages with > RF rows)
   DMB_TICK(0);
   DMB_PHASE_SYNC(1);
   DMB_TICK(1);
@@ -1342,8 +1384,8 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
     DMB_TICK(16);
     com_pos(M, S, lane);
     if (dbgrow) {
-      for (int i = lane; i < M.nbody * 3; i += 32) { dbgrow[dbg::xpos + i] = S.u.a.xpos[i]; dbgrow[dbg::xipos + i] = S.u.a.xipos[i]; }
-      for (int i = lane; i < M.nbody * 4; i += 32) dbgrow[dbg::xquat + i] = S.u.a.xquat[i];
+      for (int i = lane; i < M.nbody * 3; i += 32) { dbgrow[dbg::xpos + i] = S.o.k.xpos[i]; dbgrow[dbg::xipos + i] = S.o.k.xipos[i]; }
+      for (int i = lane; i < M.nbody * 4; i += 32) dbgrow[dbg::xquat + i] = S.o.k.xquat[i];
     }
   }
   DMB_TICK(2);
@@ -1352,10 +1394,10 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
   DMB_TICK(3);
   DMB_PHASE_SYNC(4);
   if (active) {
-    smooth_forces(M, S, lane, dbgrow ? dbgrow + dbg::qfrc_bias : nullptr);
+    smooth_forces(M, S, lane, dbgrow);
     DMB_TICK(17);
     // y_s = D^-1/2 L^-T qfrc_smooth (registers)
-    float lo = lane < M.nv ? S.vec0[lane] : 0.f, hi = lane + 32 < M.nv ? S.vec0[lane + 32] : 0.f;
+    float lo = lane < M.nv ? S.x_dv[lane] : 0.f, hi = lane + 32 < M.nv ? S.x_dv[lane + 32] : 0.f;
     reg_solve_LT(M, S, lane, lo, hi);
     if (lane < M.nv) S.ys[lane] = lo * S.dsq[lane];
     if (lane + 32 < M.nv) S.ys[lane + 32] = hi * S.dsq[lane + 32];
@@ -1370,8 +1412,22 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
   DMB_PHASE_SYNC(16);
   int nefc = 0;
   if (active) {
-    make_constraint(M, S, lane);
-    nefc = S.nefc;
+    nefc = count_rows(M, S, lane, G);
+    if (dbgrow) {   // contact geometry and cvel are overwritten by the row data below
+      for (int i = lane; i < M.nbody * 6; i += 32) dbgrow[dbg::cvel + i] = S.o.c.cvel[i];
+      for (int c = lane; c < S.ncon; c += 32) {
+        float* cr = dbgrow + dbg::contact + 16 * c;
+        const float* fr = &S.o.c.c_frame[6 * c];
+        const V3 t2 = cross(ld3(fr), ld3(fr + 3));
+        cr[0] = S.o.c.c_dist[c];
+        for (int k = 0; k < 3; k++) cr[1 + k] = S.o.c.c_pos[3 * c + k];
+        for (int k = 0; k < 6; k++) cr[4 + k] = fr[k];
+        cr[10] = t2.x; cr[11] = t2.y; cr[12] = t2.z;
+        cr[13] = (float)cm_g1(S.c_meta[c]); cr[14] = (float)cm_g2(S.c_meta[c]); cr[15] = (float)cm_dim(S.c_meta[c]);
+      }
+      __syncwarp();
+    }
+    if (nefc > RF) build_rows<true>(M, S, lane, G, dbgrow); else build_rows<false>(M, S, lane, G, dbgrow);
   }
   DMB_TICK(6);
 #if DMB_SHARE
@@ -1396,8 +1452,9 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
         const int g = t - (w > 0 ? __shfl_sync(DMB_FULL, incl, w - 1) : 0);
         const int nlw = __shfl_sync(DMB_FULL, nl, w);
         EnvS& T = tiles[w];
-        const int row = g < nlw ? g : T.c_adr[g - nlw];
-        half_solve_rows(M, T, lane, row, row + 1);
+        const int row = g < nlw ? g : cm_adr(T.c_meta[g - nlw]);
+        if (T.nefc > RF) half_solve_rows<true>(M, T, lane, row, row + 1, gcta + (size_t)w * gs::stride);
+        else half_solve_rows<false>(M, T, lane, row, row + 1, nullptr);
       }
     }
     group_barrier(bar_id, bar_n);                                   // B: every Y row is half-solved
@@ -1415,7 +1472,8 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
         const int w = __popc(__ballot_sync(DMB_FULL, incl <= t));
         const int c = t - (w > 0 ? __shfl_sync(DMB_FULL, incl, w - 1) : 0);
         const int new_ = __shfl_sync(DMB_FULL, ne, w);
-        gram(M, tiles[w], lane, new_, 32 * c, 32 * c + 32);
+        if (new_ > RF) gram<true>(M, tiles[w], lane, new_, 32 * c, 32 * c + 32, gcta + (size_t)w * gs::stride);
+        else gram<false>(M, tiles[w], lane, new_, 32 * c, 32 * c + 32, nullptr);
       }
     }
     group_barrier(bar_id, bar_n);                                   // C: every AR / b entry is in place
@@ -1425,9 +1483,14 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
   {
     DMB_PHASE_SYNC(32);
     if (active && nefc > 0) {
-      half_solve_rows(M, S, lane, 0, nefc);
-      DMB_TICK(7);
-      gram(M, S, lane, nefc, 0, 1 << 30);
+      if (nefc > RF) {
+        half_solve_rows<true>(M, S, lane, 0, nefc, G);
+        gram<true>(M, S, lane, nefc, 0, 1 << 30, G);
+      } else {
+        half_solve_rows<false>(M, S, lane, 0, nefc, nullptr);
+        DMB_TICK(7);
+        gram<false>(M, S, lane, nefc, 0, 1 << 30, nullptr);
+      }
     }
   }
   DMB_TICK(8);
@@ -1437,12 +1500,14 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
     reg_solve_L(M, S, lane, lo, hi);
     if (lane < M.nv) dbgrow[dbg::qacc_smooth + lane] = lo;
     if (lane + 32 < M.nv) dbgrow[dbg::qacc_smooth + lane + 32] = hi;
-    for (int d = lane; d < M.nv; d += 32) dbgrow[dbg::qfrc_smooth + d] = S.vec0[d];
     for (int e = lane; e < M.nM; e += 32) dbgrow[dbg::qLD + e] = S.qLD[e];
+    const RowView<true> Vg(S, G);
+    const RowView<false> Vt(S, G);
     for (int r = lane; r < nefc; r += 32) {
-      dbgrow[dbg::efc_pos + r] = S.e_pos[r]; dbgrow[dbg::efc_R + r] = S.e_R[r];
-      dbgrow[dbg::efc_aref + r] = S.e_aref[r]; dbgrow[dbg::efc_b + r] = S.e_b[r];
-      dbgrow[dbg::efc_AR_diag + r] = S.AR[tri(r) + r];
+      const bool ov = nefc > RF;
+      dbgrow[dbg::efc_R + r] = ov ? Vg.e_R[r] : Vt.e_R[r];
+      dbgrow[dbg::efc_aref + r] = ov ? Vg.e_aref[r] : Vt.e_aref[r]; dbgrow[dbg::efc_b + r] = ov ? Vg.e_b[r] : Vt.e_b[r];
+      dbgrow[dbg::efc_AR_diag + r] = ov ? Vg.AR[tri(r) + r] : Vt.AR[tri(r) + r];
     }
     __syncwarp();
   }
@@ -1451,7 +1516,14 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
 #endif
   DMB_PHASE_SYNC(64);
   DMB_TICK(9);
-  if (active) solve_constraints(M, S, lane, nefc);
+  if (active) {
+    if (nefc > RF) solve_constraints<true>(M, S, lane, nefc, G); else solve_constraints<false>(M, S, lane, nefc, G);
+    if (dbgrow) {
+      const RowView<true> Vg(S, G);
+      const RowView<false> Vt(S, G);
+      for (int r = lane; r < nefc; r += 32) dbgrow[dbg::efc_force + r] = nefc > RF ? Vg.e_f[r] : Vt.e_f[r];
+    }
+  }
   DMB_TICK(10);
 #undef DMB_PHASE_SYNC
   return active ? S.com[2] : 0.f;

@@ -5,6 +5,7 @@
 // because most of its tables are indexed per lane (body / dof / geom ids), which the
 // constant cache would serialise.
 #pragma once
+#include <cstddef>
 #include <cstdint>
 
 #include "../../include/dmb.h"
@@ -14,7 +15,7 @@ namespace dmb {
 constexpr int NB = DMB_MAX_BODY;  // 16
 constexpr int NJ = DMB_MAX_JNT;   // 32
 constexpr int NVC = 36;           // dof capacity of the kernel (nv <= 36; humanoid: 34)
-constexpr int NQC = 40;
+constexpr int NQC = 36;           // qpos capacity (nq <= 36; humanoid: 35)
 constexpr int NG = DMB_MAX_GEOM;  // 16
 constexpr int NP = DMB_MAX_PAIR;  // 128
 constexpr int NU = DMB_MAX_U;     // 32
@@ -56,7 +57,7 @@ struct ModelS {
   uint8_t dof_ancr[NVC][MAXANC];        // ancestor of d at depth r (root side first)
   int8_t dof_ndesc[NVC];
   int16_t dof_Lend[NVC];
-  int maxanc, pad_a0;
+  int maxanc, spread;                   // spread: deal the sorted env list round robin over the CTAs when one round suffices
   uint32_t ldl_meta[NVC];               // L'DL step k: chain length | pair count << 8 | row address << 16
   // chain prefix sums by pointer jumping: dof_jump[s][d] = the 2^s-th ancestor of dof d (-1: none);
   // dof_vsrc[d] = dof whose inclusive chain sum is the velocity seen by cdof_dot[d] (mj_comVel; -1: zero);
@@ -91,46 +92,86 @@ struct ModelS {
   int clip_start[DMB_MAX_CLIP], clip_len[DMB_MAX_CLIP];
 };
 
-// Per-env tile (fp32).  Arrays that are dead by the time the constraint stage starts share
-// storage with the Delassus matrix through the union `u` ("shared-memory tile"):
-//   phase A  kinematics / inertia / RNE temporaries
-//   phase B  geom poses + broad-phase survivor list (xpos/xmat stay where phase A put them)
-//   then     the half-solved constraint Jacobian Y (the Delassus matrix AR has its own storage)
-// Y rows have an odd stride so that lane=row accesses hit 32 different banks.
-struct PhaseA {
-  float xpos[NB * 3], xquat[NB * 4], xmat[NB * 9], xipos[NB * 3];
-  float cinert[NB * 10], crb[NB * 10];
-  float cdofd[NVC * 6], buf6[NVC * 6], cfrc[NB * 6];
+// Per-env tile (fp32), 7.9 KB: 28 tiles + the model tables fill the 227 KB of one SM, so that all 4096 envs of
+// the benchmark batch are resident at once (148 SMs x 28 warps).  `Fixed` lives for the whole env step; the overlay
+// `o` is time-shared by the phases of one forward evaluation ("shared-memory tile"):
+//   PhaseK  kinematics / inertia / RNE temporaries, cdof, cvel
+//   PhaseC  geom poses + broad-phase survivors + contact geometry (xpos/xquat/xmat/cdof/cvel stay where PhaseK put them)
+//   PhaseR  the half-solved constraint Jacobian Y, per-row scalars and the packed Delassus matrix AR for up to
+//           RF rows.  Y is written while cdof / contact geometry are still read (they lie behind it); the row
+//           scalars and AR are written after those are dead.
+// Envs with more than RF rows in a stage (rare: < 0.1 % of the benchmark's stage evaluations) keep Y / rows / AR in
+// a per-warp scratch slot in global memory instead (same code, template parameter OVF).
+#ifndef DMB_RF
+#define DMB_RF 24
+#endif
+constexpr int RF = DMB_RF;        // rows held in the tile
+constexpr int NTRI_F = RF * (RF + 1) / 2;
+
+struct PhaseK {
+  float xpos[NB * 3], xquat[NB * 4], xmat[NB * 9], xipos[NB * 3];   // [0, 304)
+  float cinert[NB * 10], crb[NB * 10];                              // [304, 624)
+  union {                                                            // [624, 840)
+    float buf6[NVC * 6];                                             //   crb * cdof (M entries); cdof * qvel (features)
+    struct { float acc[NB * 6], cfrc[NB * 6]; };                     //   RNE body accelerations / forces
+  };
+  float cdof[NVC * 6], cvel[NB * 6];                                 // [840, 1152)
 };
-struct PhaseB {
-  float xpos[NB * 3], xquat[NB * 4], xmat[NB * 9];
-  float gpos[NG * 3], gmat[NG * 9];
-  int surv[NP];
+struct PhaseC {
+  float xpos[NB * 3], xquat[NB * 4], xmat[NB * 9];                   // as PhaseK
+  float gpos[NG * 3], gmat[NG * 9];                                  // [256, 448)
+  unsigned char surv[NP];                                            // [448, 480) broad-phase survivors (pair ids)
+  float pad[360];
+  float cdof[NVC * 6], cvel[NB * 6];                                 // as PhaseK
+  float c_dist[MAXC], c_pos[MAXC * 3], c_frame[MAXC * 6];            // [1152, 1312) contact frame: normal, tangent 1
 };
-union PhaseU {
-  PhaseA a;
-  PhaseB b;
-  float Y[MAXROW * YS];  // half-solved constraint Jacobian, written after the collision stage
+struct PhaseR {
+  float Y[RF * YS];                                                  // [0, 840)
+  float e_R[RF], e_aref[RF], e_b[RF], e_f[RF];                       // [840, 936)
+  unsigned long long rowmask[RF];                                    // [936, 984) dof support of each half-solved row
+  float AR[NTRI_F];                                                  // [984, 1284) packed lower triangle of J M^-1 J' + R
 };
+union Overlay {
+  PhaseK k;
+  PhaseC c;
+  PhaseR r;
+};
+static_assert(offsetof(PhaseC, cdof) == offsetof(PhaseK, cdof), "cdof must not move between phases");
+static_assert(offsetof(PhaseC, xmat) == offsetof(PhaseK, xmat), "xmat must not move between phases");
+static_assert(offsetof(PhaseR, e_R) >= offsetof(PhaseK, cdof), "row scalars may only overwrite cdof / cvel");
+static_assert(sizeof(float) * RF * YS <= offsetof(PhaseK, cdof), "Y is written while cdof is read");
+static_assert(offsetof(PhaseR, AR) % 4 == 0 && offsetof(PhaseR, rowmask) % 8 == 0, "alignment");
 
 struct EnvS {
-  float qpos[NQC], qvel[NQC], ctrlf[NQC], warm[NQC], qacc[NQC];
-  float x_q0[NQC], x_dv[NQC];          // RK4: X0 positions, stage velocity increment
-  float vec0[NQC], vec1[NQC], ys[NQC];  // qfrc_smooth / scratch / y_s = D^-1/2 L^-T qfrc_smooth
+  float qpos[NQC], qvel[NVC], ctrlf[NVC];
+  float qacc[NVC];                     // also qacc_warmstart: mj_forward leaves warmstart = qacc
+  float x_q0[NQC], x_dv[NVC];          // RK4: X0 positions, stage velocity; x_dv doubles as scratch inside forward_eval
+  float qLD[NMX], dsq[NVC], ys[NVC];   // sparse factor, D^-1/2, y_s = D^-1/2 L^-T qfrc_smooth
   float com[4];
-  float cdof[NVC * 6], cvel[NB * 6];
-  float qLD[NMX], dsq[NVC];
-  // contacts
-  float c_dist[MAXC], c_pos[MAXC * 3], c_frame[MAXC * 9], c_mu[MAXC];
-  int c_g1[MAXC], c_g2[MAXC], c_dim[MAXC], c_adr[MAXC];
-  // constraint rows
-  float e_pos[MAXROW], e_margin[MAXROW], e_R[MAXROW], e_aref[MAXROW], e_b[MAXROW], e_f[MAXROW];
-  int e_src[MAXROW];  // row source: >=0 contact*4+edge, <0 joint limit (see make_constraint)
   int ncon, nefc, nlimit, flags, iter, cost, pad0, pad1;
-  unsigned long long rowmask[MAXROW];  // dof support of each half-solved row
-  float AR[NTRI];                      // packed lower triangle of J M^-1 J' + R
-  PhaseU u;
+  int c_meta[MAXC];                    // geom1 | geom2 << 8 | condim << 16 | first row << 24
+  float c_mu[MAXC];
+  int e_src[RF];                       // row source: >=0 contact*4+edge, <0 joint limit (see make_constraint)
+  Overlay o;
 };
+__device__ __forceinline__ int cm_g1(int m) { return m & 0xff; }
+__device__ __forceinline__ int cm_g2(int m) { return (m >> 8) & 0xff; }
+__device__ __forceinline__ int cm_dim(int m) { return (m >> 16) & 0xff; }
+__device__ __forceinline__ int cm_adr(int m) { return (m >> 24) & 0xff; }
+
+// Global scratch slot of one warp for a stage with more than RF rows (floats)
+namespace gs {
+constexpr int Y = 0;                          // MAXROW * YS
+constexpr int e_R = Y + MAXROW * YS;
+constexpr int e_aref = e_R + MAXROW;
+constexpr int e_b = e_aref + MAXROW;
+constexpr int e_f = e_b + MAXROW;
+constexpr int rowmask = e_f + MAXROW;         // MAXROW x u64 (8-byte aligned: all offsets are even)
+constexpr int AR = rowmask + 2 * MAXROW;      // NTRI
+constexpr int e_src = AR + NTRI;              // MAXROW ints
+constexpr int stride = ((e_src + MAXROW + 31) / 32) * 32;
+static_assert(rowmask % 2 == 0, "u64 alignment");
+}  // namespace gs
 
 // Debug row layout (floats) for dmb_forward_debug
 namespace dbg {

@@ -30,7 +30,15 @@ def mixed_clip_ids(start: int, end: int, nclip: int) -> torch.Tensor:
 
 
 class RecordGather:
-    """All-gather of the per-step record into a pre-allocated [N_global, width] buffer."""
+    """All-gather of the per-step record into pre-allocated [N_global, width] buffers.
+
+    ``g(local)`` is the blocking form (gather on the current stream, used by the CPU/gloo tests and simple callers).
+    ``launch(local)`` / ``wait()`` is the overlapped form used by the rollout loops: the collective runs on a side
+    stream, gated by an event recorded after the step kernel, and writes the gathered record of step t into
+    ``out_buffers[t % 2]`` while the compute stream already runs step t + 1 (the env step never waits for the
+    slowest rank's previous kernel; SURVEY.md section 5 "Distributed communication backend").  ``wait()`` makes the
+    current stream wait for the oldest outstanding gather and returns its buffer.
+    """
 
     def __init__(self, local_rec: torch.Tensor, num_envs_global: int, group=None):
         self.group = group
@@ -39,21 +47,63 @@ class RecordGather:
         self.local = local_rec
         width = local_rec.shape[1]
         self.equal = num_envs_global % self.world == 0
-        self.out = torch.empty(num_envs_global, width, dtype=local_rec.dtype, device=local_rec.device)
+        kw = dict(dtype=local_rec.dtype, device=local_rec.device)
+        self.out_buffers = [torch.empty(num_envs_global, width, **kw) for _ in range(2)]
+        self.out = self.out_buffers[0]
         if not self.equal:  # ragged shards: pad every rank to the largest shard, gather, then compact
             self.sizes = [shard_range(num_envs_global, self.world, r) for r in range(self.world)]
             self.maxn = max(e - s for s, e in self.sizes)
-            self.pad = torch.zeros(self.maxn, width, dtype=local_rec.dtype, device=local_rec.device)
-            self.buf = torch.empty(self.world * self.maxn, width, dtype=local_rec.dtype, device=local_rec.device)
+            self.pad = torch.zeros(self.maxn, width, **kw)
+            self.buf = torch.empty(self.world * self.maxn, width, **kw)
+        self.cuda = local_rec.is_cuda
+        self.side = torch.cuda.Stream(device=local_rec.device) if self.cuda else None
+        self._pending = []      # (event, buffer) of launched gathers, oldest first
+        self._t = 0
 
-    def __call__(self) -> torch.Tensor:
+    def _gather(self, out: torch.Tensor, local: torch.Tensor) -> None:
         if self.world == 1:
-            self.out.copy_(self.local)
+            out.copy_(local)
         elif self.equal:
-            dist.all_gather_into_tensor(self.out, self.local, group=self.group)
+            dist.all_gather_into_tensor(out, local, group=self.group)
         else:
-            self.pad[: self.local.shape[0]].copy_(self.local)
+            self.pad[: local.shape[0]].copy_(local)
             dist.all_gather_into_tensor(self.buf, self.pad, group=self.group)
             for r, (s, e) in enumerate(self.sizes):
-                self.out[s:e].copy_(self.buf[r * self.maxn: r * self.maxn + (e - s)])
+                out[s:e].copy_(self.buf[r * self.maxn: r * self.maxn + (e - s)])
+
+    def __call__(self, local: torch.Tensor = None) -> torch.Tensor:
+        self._gather(self.out, self.local if local is None else local)
         return self.out
+
+    def launch(self, local: torch.Tensor = None) -> None:
+        """Start gathering ``local`` (default: the tensor given at construction) without blocking the current
+        stream.  At most two gathers may be outstanding (double buffer): call ``wait()`` before a third."""
+        local = self.local if local is None else local
+        if len(self._pending) >= 2:
+            raise RuntimeError("RecordGather: two gathers already outstanding; call wait() first")
+        out = self.out_buffers[self._t & 1]
+        self._t += 1
+        if not self.cuda:
+            self._gather(out, local)
+            self._pending.append((None, out))
+            return
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(local.device))      # after the step kernel that wrote `local`
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            self._gather(out, local)
+            done = torch.cuda.Event()
+            done.record(self.side)
+        self._pending.append((done, out))
+
+    def wait(self) -> torch.Tensor:
+        """Make the current stream wait for the oldest outstanding gather; returns its [N_global, width] buffer."""
+        done, out = self._pending.pop(0)
+        if done is not None:
+            torch.cuda.current_stream(out.device).wait_event(done)
+        self.out = out
+        return out
+
+    def drain(self) -> None:
+        while self._pending:
+            self.wait()

@@ -80,6 +80,10 @@ class BatchedSim:
         self.qpos = torch.zeros(N, _lib.QSTRIDE, dtype=f32, device=d)
         self.qvel = torch.zeros(N, _lib.VSTRIDE, dtype=f32, device=d)
         self.warm = torch.zeros(N, _lib.VSTRIDE, dtype=f32, device=d)
+        if clip_ids is not None:
+            ci = torch.as_tensor(clip_ids)
+            if ci.numel() != N or int(ci.min()) < 0 or int(ci.max()) >= len(self.mocap.names):
+                raise ValueError(f"clip_ids must hold {N} ids in [0, {len(self.mocap.names)}) (one per env)")
         self.clip = torch.zeros(N, dtype=i32, device=d) if clip_ids is None else clip_ids.to(d, i32).contiguous()
         self.idx_init = torch.zeros(N, dtype=i32, device=d)
         self.idx_curr = torch.zeros(N, dtype=i32, device=d)
@@ -90,7 +94,11 @@ class BatchedSim:
         self.obs = torch.zeros(N, self.obs_dim, dtype=f32, device=d)
         self.reward = torch.zeros(N, dtype=f32, device=d)
         self.done = torch.zeros(N, dtype=torch.uint8, device=d)
-        self.rec = torch.zeros(N, self.obs_dim + 2, dtype=f32, device=d)
+        # the packed (obs, reward, done) record is double-buffered: step t writes rec_buffers[t % 2], so that the
+        # all-gather of step t (dist.RecordGather, on its own stream) can overlap step t + 1
+        self.rec_buffers = [torch.zeros(N, self.obs_dim + 2, dtype=f32, device=d) for _ in range(2)]
+        self.rec_index = 0
+        self.rec = self.rec_buffers[0]    # the record of the latest step
         self.last_ret = torch.zeros(N, dtype=f32, device=d)
         self.last_len = torch.zeros(N, dtype=i32, device=d)
         self._st = _lib.DmbState(*[t.data_ptr() for t in (self.qpos, self.qvel, self.warm, self.clip, self.idx_init,
@@ -139,6 +147,9 @@ class BatchedSim:
         if action.device != self.device or action.dtype != torch.float32 or not action.is_contiguous() \
                 or tuple(action.shape) != (self.N, self.nu):
             raise ValueError("action must be a contiguous CUDA float32 tensor of shape [N, nu] on the sim's device")
+        self.rec_index ^= 1
+        self.rec = self.rec_buffers[self.rec_index]
+        self._out.rec = self.rec.data_ptr()
         with torch.cuda.device(self.device):
             _lib.check(self.L.dmb_step(self.handle, C.byref(self._st), C.c_void_p(action.data_ptr()),
                                        C.byref(self._out), self._stream()), self.handle, "dmb_step")

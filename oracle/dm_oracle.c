@@ -15,6 +15,7 @@
 #include "dm_oracle.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #define MINVAL 1e-15
@@ -1153,6 +1154,16 @@ static void get_reference(const dmb_model_t* m, const dmb_config_t* cfg, const d
   for (int i = 0; i < m->nq; i++) rq[i] = (double)(float)mc->data_config[f*m->nq + i];
   for (int i = 0; i < m->nv; i++) rv[i] = (double)(float)mc->data_vel[f*m->nv + i];
   if (aux) for (int i = 0; i < DMB_REF_AUX; i++) aux[i] = (double)(float)mc->ref_aux[f*DMB_REF_AUX + i];
+  if (cfg->reward_mode == 4) {
+    /* the integer frame counter wraps (dp_env_v3.py:101-102); the 5-term reward scores the absolute root
+     * position, so the reference root keeps moving: every completed pass over the clip adds the last frame's
+     * root xy (the root-offset accumulation of MocapDM.play, mocap_v2.py:168-182) */
+    const int len = mc->clip_len[e->clip];
+    const int cycle = (e->idx_init + e->ep_len)/len;
+    const size_t fl = (size_t)(mc->clip_start[e->clip] + len - 1);
+    rq[0] += (double)cycle*(double)(float)mc->data_config[fl*m->nq + 0];
+    rq[1] += (double)cycle*(double)(float)mc->data_config[fl*m->nq + 1];
+  }
 }
 
 static double reward_imitate(const dmb_model_t* m, const dmb_config_t* cfg, dmo_env_t* e, const double* rq,
@@ -1266,6 +1277,7 @@ int dmo_env_step(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_
   dmo_step(m, d);
   int bad = (d->flags & 4) != 0;
   double zc = d->com[2]; /* stale CoM of the last RK4 stage, as mjData.xipos is after mj_step */
+  e->zcom_last = zc;
   double rew = 1.0;
   const int len = mc->clip_len[e->clip];
   /* phase_mode 1: the reference is sampled at the post-step time for every reward mode */
@@ -1345,4 +1357,43 @@ long dmo_rollout(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_
     dmo_env_step(m, &c, mc, e, action, obs, &rew);
   }
   return nsteps;
+}
+
+/* One env step for a batch of independent envs, from explicit per-env inputs (the tests feed it the fp32 state
+ * of the CUDA path and compare the outputs): env i has global id first_env_id + i (Philox stream of its resets).
+ * Arrays are row-major [n][.] doubles / int32; qpos/qvel/warm and the bookkeeping arrays are updated in place.
+ * last_ret / last_len = return and length of the episode including this step (the Monitor record,
+ * bench/monitor.py:58-76, meaningful where done is set).  Test infrastructure only. */
+void dmo_batch_step(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, int n, uint64_t seed,
+                    uint32_t first_env_id, double* qpos, double* qvel, double* warm, const int32_t* clip,
+                    int32_t* idx_init, int32_t* idx_curr, int32_t* ep_len, double* ep_ret, int32_t* reset_count,
+                    const double* action, double* obs, int obs_stride, double* reward, int32_t* done,
+                    double* last_ret, int32_t* last_len, int32_t* flags, int32_t* nefc_last, double* zcom) {
+  dmo_env_t* e = (dmo_env_t*)malloc(sizeof(dmo_env_t));
+  double ob[2 + 13*DMB_MAX_PART + 2*DMB_MAX_DOF];
+  for (int i = 0; i < n; i++) {
+    dmo_env_init(m, cfg, mc, e, seed, first_env_id + (uint32_t)i, clip[i]);
+    memcpy(e->d.qpos, qpos + (size_t)i*m->nq, sizeof(double)*m->nq);
+    memcpy(e->d.qvel, qvel + (size_t)i*m->nv, sizeof(double)*m->nv);
+    memcpy(e->d.qacc_warmstart, warm + (size_t)i*m->nv, sizeof(double)*m->nv);
+    e->idx_init = idx_init[i]; e->idx_curr = idx_curr[i]; e->ep_len = ep_len[i]; e->ep_ret = ep_ret[i];
+    e->reset_count = (uint32_t)reset_count[i];
+    double rew = 0;
+    const double ret0 = e->ep_ret;
+    const int len0 = e->ep_len;
+    e->d.com[2] = 0;
+    done[i] = dmo_env_step(m, cfg, mc, e, action + (size_t)i*m->nu, ob, &rew);
+    reward[i] = rew;
+    last_ret[i] = ret0 + rew; last_len[i] = len0 + 1;
+    if (flags) flags[i] = e->d.flags;
+    if (nefc_last) nefc_last[i] = e->d.nefc;
+    if (zcom) zcom[i] = e->zcom_last;
+    memcpy(obs + (size_t)i*obs_stride, ob, sizeof(double)*obs_stride);
+    memcpy(qpos + (size_t)i*m->nq, e->d.qpos, sizeof(double)*m->nq);
+    memcpy(qvel + (size_t)i*m->nv, e->d.qvel, sizeof(double)*m->nv);
+    memcpy(warm + (size_t)i*m->nv, e->d.qacc_warmstart, sizeof(double)*m->nv);
+    idx_init[i] = e->idx_init; idx_curr[i] = e->idx_curr; ep_len[i] = e->ep_len; ep_ret[i] = e->ep_ret;
+    reset_count[i] = (int32_t)e->reset_count;
+  }
+  free(e);
 }

@@ -67,6 +67,7 @@ typedef struct dmo_env {
   uint32_t env_id, reset_count;
   double ep_ret;
   double reward_terms[5];
+  double zcom_last;    /* CoM height the last dmo_env_step tested for termination */
 } dmo_env_t;
 
 int dmo_version(void);
@@ -108,6 +109,13 @@ void dmo_philox(uint64_t seed, uint32_t env_id, uint32_t reset_count, uint32_t b
  * returns number of env steps done. */
 long dmo_rollout(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, dmo_env_t* e,
                  long nsteps, uint64_t action_seed);
+
+/* one env step of n independent envs from explicit inputs (full-size parity tests); see dm_oracle.c */
+void dmo_batch_step(const dmb_model_t* m, const dmb_config_t* cfg, const dmb_mocap_t* mc, int n, uint64_t seed,
+                    uint32_t first_env_id, double* qpos, double* qvel, double* warm, const int32_t* clip,
+                    int32_t* idx_init, int32_t* idx_curr, int32_t* ep_len, double* ep_ret, int32_t* reset_count,
+                    const double* action, double* obs, int obs_stride, double* reward, int32_t* done,
+                    double* last_ret, int32_t* last_len, int32_t* flags, int32_t* nefc_last, double* zcom);
 
 #ifdef __cplusplus
 }

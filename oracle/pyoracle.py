@@ -56,7 +56,7 @@ class DmoData(C.Structure):
 class DmoEnv(C.Structure):
     _fields_ = [("d", DmoData), ("clip", i32), ("idx_init", i32), ("idx_curr", i32), ("ep_len", i32),
                 ("seed", C.c_uint64), ("env_id", C.c_uint32), ("reset_count", C.c_uint32),
-                ("ep_ret", f64), ("reward_terms", f64 * 5)]
+                ("ep_ret", f64), ("reward_terms", f64 * 5), ("zcom_last", f64)]
 
 
 def build(force: bool = False) -> str:
@@ -103,6 +103,10 @@ def lib():
         L.dmo_philox.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
         L.dmo_rollout.argtypes = [mp, cp, mcp, ep, C.c_long, C.c_uint64]
         L.dmo_rollout.restype = C.c_long
+        ip, fp = C.POINTER(i32), C.POINTER(f64)
+        L.dmo_batch_step.argtypes = [mp, cp, mcp, C.c_int, C.c_uint64, C.c_uint32, fp, fp, fp, ip, ip, ip, ip, fp, ip,
+                                     fp, fp, C.c_int, fp, ip, fp, ip, ip, ip, fp]
+        L.dmo_batch_step.restype = None
         _lib = L
     return _lib
 
@@ -153,3 +157,26 @@ class Oracle:
     @property
     def qvel(self):
         return self.d.arr("qvel")[: self.nv]
+
+
+def batch_step(model, cfg, mcs, seed, first_env_id, state: dict, action, obs_dim: int) -> dict:
+    """One oracle env step for a batch of envs from explicit inputs (dmo_batch_step).  ``state`` holds numpy arrays
+    qpos [n,nq], qvel [n,nv], warm [n,nv] (float64) and clip, idx_init, idx_curr, ep_len, reset_count (int32), ep_ret
+    (float64); it is NOT modified.  Returns the post-step arrays plus obs, reward, done, last_ret, last_len, flags,
+    nefc (of the last RK4 stage)."""
+    L = lib()
+    n = state["qpos"].shape[0]
+    f = lambda k: np.ascontiguousarray(state[k], dtype=np.float64).copy()
+    i = lambda k: np.ascontiguousarray(state[k], dtype=np.int32).copy()
+    out = dict(qpos=f("qpos"), qvel=f("qvel"), warm=f("warm"), clip=i("clip"), idx_init=i("idx_init"),
+               idx_curr=i("idx_curr"), ep_len=i("ep_len"), ep_ret=f("ep_ret"), reset_count=i("reset_count"))
+    act = np.ascontiguousarray(action, dtype=np.float64)
+    out.update(obs=np.zeros((n, obs_dim)), reward=np.zeros(n), done=np.zeros(n, np.int32), last_ret=np.zeros(n),
+               last_len=np.zeros(n, np.int32), flags=np.zeros(n, np.int32), nefc=np.zeros(n, np.int32), zcom=np.zeros(n))
+    ip = lambda a: a.ctypes.data_as(C.POINTER(i32))
+    L.dmo_batch_step(C.byref(model), C.byref(cfg), C.byref(mcs), n, C.c_uint64(seed), C.c_uint32(first_env_id),
+                     dptr(out["qpos"]), dptr(out["qvel"]), dptr(out["warm"]), ip(out["clip"]), ip(out["idx_init"]),
+                     ip(out["idx_curr"]), ip(out["ep_len"]), dptr(out["ep_ret"]), ip(out["reset_count"]), dptr(act),
+                     dptr(out["obs"]), obs_dim, dptr(out["reward"]), ip(out["done"]), dptr(out["last_ret"]),
+                     ip(out["last_len"]), ip(out["flags"]), ip(out["nefc"]), dptr(out["zcom"]))
+    return out

@@ -94,3 +94,13 @@ def rollout_states(rng, n, steps_range=(5, 40)):
             o.step()
         qs.append(o.qpos.copy()); vs.append(o.qvel.copy()); ws.append(o.d.arr("qacc_warmstart")[: mt.nv].copy())
     return f32(np.array(qs)), f32(np.array(vs)), f32(np.array(ws))
+
+
+# ---- measured-error bookkeeping: the parity tests record the worst error they saw per quantity; conftest.py writes
+# the table to gpurun_out/parity_measured.json at the end of a GPU session (evidence for DESIGN.md section 2)
+MEASURED = {}
+
+
+def record(label, key, value):
+    d = MEASURED.setdefault(label, {})
+    d[key] = max(float(value), d.get(key, 0.0))

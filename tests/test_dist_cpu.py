@@ -32,7 +32,14 @@ def _worker(rank, world, port, n_global, q):
     g = RecordGather(local, n_global)
     out = g()
     expect = torch.arange(n_global, dtype=torch.float32)[:, None] * torch.ones(1, 58) + torch.arange(58) * 1e-3
-    q.put((rank, bool(torch.equal(out, expect))))
+    ok = bool(torch.equal(out, expect))
+    # overlapped form (double buffer): two launches may be outstanding, results come back oldest first
+    g.launch(local); g.launch(local * 2)
+    with pytest.raises(RuntimeError):
+        g.launch(local)
+    a = g.wait().clone(); b = g.wait()
+    ok = ok and bool(torch.equal(a, expect)) and bool(torch.equal(b, expect * 2)) and a.data_ptr() != b.data_ptr()
+    q.put((rank, ok))
     dist.barrier()
     dist.destroy_process_group()
 

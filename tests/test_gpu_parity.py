@@ -1,8 +1,9 @@
 """CUDA path vs the float64 oracle, through the C-ABI (run on the B200 box: pytest -m gpu).
 
 Tolerances: single step from identical fp32-representable inputs,
-|dqpos| <= 1e-4, |dqvel| / max(1,|qvel|) <= 1e-4 (contact-rich: 2e-4), reward <= 1e-5 abs,
-FK quantities <= 1e-5, `done` exact away from the threshold.  PARITY UNPINNED against MuJoCo
+|dqpos| <= 1e-4, |dqvel| / max(1,|qvel|) <= 1e-4, reward <= 1e-5 abs,
+FK quantities <= 1e-5, `done` exact away from the threshold.  Measured on B200 (profiles/r2_parity_measured.json):
+|dqpos| <= 1.4e-7, rel |dqvel| <= 4.4e-6, reward <= 5e-7 on every case of this file.  PARITY UNPINNED against MuJoCo
 itself (no binary, no golden vectors) -- the oracle is the restatement being matched.
 """
 import ctypes as C
@@ -34,7 +35,13 @@ def oracle_forward(o, mt, q, v, c, w):
     return o.d
 
 
-def compare_forward(ctx, q, v, ctrl, warm=None, tol_scale=1.0):
+# Envs whose contact normal is ill-conditioned in fp32 (deep sphere/capsule-vs-foot-box penetration: the normal is
+# (c - clamp(c)) / |c - clamp(c)| with |.| ~ 1e-4): rows, forces and qacc are compared with the bound scaled by this factor.
+# Measured worst case (profiles/r2_parity_measured.json): 2.5 x the normal bound on aref / b, 2 x on qacc.
+LOOSE_SCALE = 5.0
+
+
+def compare_forward(ctx, q, v, ctrl, warm=None, tol_scale=1.0, label="forward"):
     sim, o, mt, po = ctx
     n = q.shape[0]
     warm = np.zeros((n, mt.nv)) if warm is None else warm
@@ -44,6 +51,7 @@ def compare_forward(ctx, q, v, ctrl, warm=None, tol_scale=1.0):
         d = oracle_forward(o, mt, q[i], v[i], ctrl[i], warm[i])
         assert d.ncon == g["ncon"][i] and d.nefc == g["nefc"][i], (i, d.ncon, g["ncon"][i], d.nefc, g["nefc"][i])
         nb, nv, ne = mt.nbody, mt.nv, d.nefc
+        env_scale = 1.0
         assert np.abs(d.arr("xpos")[:nb] - g["xpos"][i]).max() < 1e-5
         assert np.abs(d.arr("xquat")[:nb] - g["xquat"][i]).max() < 1e-5
         assert np.abs(d.arr("xipos")[:nb] - g["xipos"][i]).max() < 1e-5
@@ -67,8 +75,11 @@ def compare_forward(ctx, q, v, ctrl, warm=None, tol_scale=1.0):
             if (~loose).any():
                 assert np.abs(oc[~loose][:, cols] - gc[~loose][:, cols]).max() < 2e-5
             if loose.any():
+                # measured: <= 2e-3 on the normal (profiles/r2_parity_measured.json); the rows / forces / qacc that
+                # inherit this normal are still compared below, with the bound scaled by the same factor
                 assert np.abs(oc[loose][:, cols] - gc[loose][:, cols]).max() < 5e-3
-                continue   # downstream rows inherit the ill-conditioned normal
+                common.record(label, "loose_contact_normal", np.abs(oc[loose][:, cols] - gc[loose][:, cols]).max())
+                env_scale = LOOSE_SCALE
             fr = oc[:, 15] > 1
             if fr.any():
                 assert np.abs(oc[fr, 7:13] - gc[fr, 7:13]).max() < 1e-4
@@ -77,14 +88,20 @@ def compare_forward(ctx, q, v, ctrl, warm=None, tol_scale=1.0):
             # shows up as ~5e-4 absolute
             for k, rel, ab in (("efc_pos", 1e-5, 0.0), ("efc_R", 1e-4, 0.0), ("efc_aref", 1e-4, 1e-3), ("efc_b", 1e-4, 1e-3)):
                 a = d.arr(k)[:ne]
-                assert np.abs(a - g[k][i][:ne]).max() < ab + rel * tol_scale * max(1.0, np.abs(a).max()), (k, i)
+                err = np.abs(a - g[k][i][:ne]).max()
+                common.record(label + ("/loose" if env_scale > 1 else ""), k + "_over_bound", err / (ab + rel * max(1.0, np.abs(a).max())))
+                assert err < (ab + rel * max(1.0, np.abs(a).max())) * tol_scale * env_scale, (k, i)
             f = d.arr("efc_force")[:ne]
-            assert np.abs(f - g["efc_force"][i][:ne]).max() < 1e-3 * tol_scale * max(1.0, np.abs(f).max())
+            err = np.abs(f - g["efc_force"][i][:ne]).max() / max(1.0, np.abs(f).max())
+            common.record(label + ("/loose" if env_scale > 1 else ""), "efc_force_rel", err)
+            assert err < 1e-3 * tol_scale * env_scale, i
         qa = d.arr("qacc")[:nv]
-        assert np.abs(qa - g["qacc"][i]).max() < 2e-4 * tol_scale * max(1.0, np.abs(qa).max())
+        err = np.abs(qa - g["qacc"][i]).max() / max(1.0, np.abs(qa).max())
+        common.record(label + ("/loose" if env_scale > 1 else ""), "qacc_rel", err)
+        assert err < 2e-4 * tol_scale * env_scale, i
 
 
-def compare_step(ctx, q, v, ctrl, warm=None, vtol=1e-4):
+def compare_step(ctx, q, v, ctrl, warm=None, vtol=1e-4, label="step"):
     sim, o, mt, po = ctx
     n = q.shape[0]
     warm = np.zeros((n, mt.nv)) if warm is None else warm
@@ -96,6 +113,8 @@ def compare_step(ctx, q, v, ctrl, warm=None, vtol=1e-4):
     for i in range(n):
         o.set_state(q[i], v[i], ctrl[i], warm[i])
         o.step()
+        common.record(label, "qpos_abs", np.abs(o.qpos - gq[i]).max())
+        common.record(label, "qvel_rel", (np.abs(o.qvel - gv[i]) / np.maximum(1.0, np.abs(o.qvel))).max())
         assert np.abs(o.qpos - gq[i]).max() < 1e-4
         assert (np.abs(o.qvel - gv[i]) / np.maximum(1.0, np.abs(o.qvel))).max() < vtol
         zc = o.d.arr("com")[2]
@@ -108,19 +127,19 @@ def compare_step(ctx, q, v, ctrl, warm=None, vtol=1e-4):
 def test_forward_airborne(ctx):
     rng = np.random.default_rng(0)
     q, v = common.airborne_states(rng, N)
-    compare_forward(ctx, q, v, common.f32(rng.uniform(-0.6, 0.6, (N, 28))))
+    compare_forward(ctx, q, v, common.f32(rng.uniform(-0.6, 0.6, (N, 28))), label="forward_airborne")
 
 
 def test_forward_standing_contacts(ctx):
     rng = np.random.default_rng(1)
     q, v = common.standing_states(rng, N)
-    compare_forward(ctx, q, v, common.f32(rng.uniform(-0.6, 0.6, (N, 28))))
+    compare_forward(ctx, q, v, common.f32(rng.uniform(-0.6, 0.6, (N, 28))), label="forward_standing")
 
 
 def test_forward_rollout_states_with_warmstart(ctx):
     rng = np.random.default_rng(2)
     q, v, w = common.rollout_states(rng, N)
-    compare_forward(ctx, q, v, common.f32(rng.uniform(-0.6, 0.6, (N, 28))), w, tol_scale=2.0)
+    compare_forward(ctx, q, v, common.f32(rng.uniform(-0.6, 0.6, (N, 28))), w, label="forward_rollout_warm")
 
 
 @pytest.mark.parametrize("clip", ["walk", "spinkick", "dance_b"])
@@ -129,21 +148,21 @@ def test_step_from_mocap_frames(ctx, clip):
     c = common.clip(clip)
     idx = rng.integers(0, len(c), size=N)
     q, v = common.mocap_states(clip, idx)
-    compare_step(ctx, q, v, common.f32(rng.uniform(-0.5, 0.5, (N, 28))))
+    compare_step(ctx, q, v, common.f32(rng.uniform(-0.5, 0.5, (N, 28))), label="step_mocap_" + clip)
 
 
 def test_step_standing_and_rollout(ctx):
     rng = np.random.default_rng(4)
     q, v = common.standing_states(rng, N)
-    compare_step(ctx, q, v, common.f32(rng.uniform(-0.7, 0.7, (N, 28))))
+    compare_step(ctx, q, v, common.f32(rng.uniform(-0.7, 0.7, (N, 28))), label="step_standing")
     q, v, w = common.rollout_states(rng, N)
-    compare_step(ctx, q, v, common.f32(rng.normal(size=(N, 28))), w, vtol=2e-4)
+    compare_step(ctx, q, v, common.f32(rng.normal(size=(N, 28))), w, label="step_rollout")
 
 
 def test_step_airborne_self_contacts(ctx):
     rng = np.random.default_rng(5)
     q, v = common.airborne_states(rng, N, frac=0.35)
-    compare_step(ctx, q, v, common.f32(rng.uniform(-0.5, 0.5, (N, 28))), vtol=3e-4)
+    compare_step(ctx, q, v, common.f32(rng.uniform(-0.5, 0.5, (N, 28))), label="step_airborne_selfcontact")
 
 
 def _env_pair(po, reward_mode, ctrl_mode, motions=("walk",), n=32, seed=5, auto_reset=1, reset_mode=0, term_mode=0,
@@ -209,7 +228,8 @@ def test_env_step_rewards_pd_and_reset(ctx, reward_mode, ctrl_mode, term_mode, p
             a = np.ascontiguousarray(act[i])
             od = L.dmo_env_step(C.byref(m), C.byref(cfg), C.byref(mcs), C.byref(e), po.dptr(a), po.dptr(obs_o), C.byref(rew_o))
             zc = e.d.com[2] if not od else None
-            assert abs(rew_o.value - rew[i]) < 2e-5, (t, i, rew_o.value, rew[i])
+            common.record(f"env_step_r{reward_mode}", "reward_abs", abs(rew_o.value - rew[i]))
+            assert abs(rew_o.value - rew[i]) < 1e-5, (t, i, rew_o.value, rew[i])
             assert bool(od) == bool(done[i]), (t, i)
             ndone += int(od)
             assert e.idx_curr == int(sim.idx_curr[i]) and e.idx_init == int(sim.idx_init[i])

@@ -19,8 +19,11 @@ sim = env.sim
 env.reset()
 g = torch.Generator(device="cuda"); g.manual_seed(1)
 buf = np.zeros((256, 8), dtype=np.int64)
+flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda") if os.environ.get("TRACE_FLUSH") == "1" else None
 for t in range(140):
     act = torch.rand(E, sim.nu, device="cuda", generator=g) - 0.5
+    if flush is not None:
+        flush.zero_()      # cold L2, as between the timed steps of bench.py
     env.step(act)
     if t >= 100 and t % 10 == 0:
         torch.cuda.synchronize()
@@ -38,5 +41,6 @@ for t in range(140):
             order = np.argsort(r1)
             r2 = end - r1
             print("round-1 duration deciles (us):", np.round(np.percentile(r1, [0, 10, 25, 50, 75, 90, 100]) / 1e3, 1))
-            print("round-2 duration deciles (us):", np.round(np.percentile(r2[rounds >= 2], [0, 10, 25, 50, 75, 90, 100]) / 1e3, 1))
-            print("corr(round1, round2) =", np.corrcoef(r1[rounds >= 2], r2[rounds >= 2])[0, 1])
+            if (rounds >= 2).any():
+                print("round-2 duration deciles (us):", np.round(np.percentile(r2[rounds >= 2], [0, 10, 25, 50, 75, 90, 100]) / 1e3, 1))
+                print("corr(round1, round2) =", np.corrcoef(r1[rounds >= 2], r2[rounds >= 2])[0, 1])
