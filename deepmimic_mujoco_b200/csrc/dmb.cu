@@ -53,7 +53,7 @@ __device__ __forceinline__ void load_state(const ModelS& M, EnvS& S, const dmb_s
     float* dst = a == 0 ? S.qpos : (a == 1 ? S.qvel : S.qacc);
     reinterpret_cast<float4*>(dst)[w] = __ldg(reinterpret_cast<const float4*>(src + (size_t)env * NQC) + w);
   }
-  if (lane == 0) { S.flags = 0; S.cost = 0; }
+  if (lane == 0) { S.flags = 0; S.cost = 0; S.diag = 0; S.big = 0; }
   __syncwarp();
 }
 __device__ __forceinline__ void store_state(const ModelS& M, EnvS& S, const dmb_state_t& st, int env, int lane) {
@@ -314,7 +314,7 @@ __device__ __forceinline__ void integrate_pos(const ModelS& M, EnvS& S, int lane
 // the kernel is instruction-fetch bound).  Returns the CoM height of the last stage evaluation.
 template <bool LOCKSTEP>
 __device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bool active, int bar_id, int bar_n, int* arrive,
-                                          EnvS* tiles, int* share_cnt, float* gcta) {
+                                          EnvS* tiles, int* share_cnt, float* gcta, int warp, bool use_slot) {
   const float h = M.timestep;
   const int d0 = lane, d1 = lane + 32;
   const bool a0 = active && d0 < M.nv, a1 = active && d1 < M.nv;
@@ -333,7 +333,7 @@ __device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bo
       if (active) integrate_pos(M, S, lane, h);
       __syncwarp();
     }
-    zc = forward_eval<LOCKSTEP>(M, S, lane, nullptr, active, bar_id, bar_n, arrive + st, tiles, share_cnt, gcta);
+    zc = forward_eval<LOCKSTEP>(M, S, lane, nullptr, active, bar_id, bar_n, arrive + st, tiles, share_cnt, gcta, warp, use_slot);
     const float bw = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);
     if (a0) { sv0 += bw * S.qvel[d0]; sa0 += bw * S.qacc[d0]; }
     if (a1) { sv1 += bw * S.qvel[d1]; sa1 += bw * S.qacc[d1]; }
@@ -516,14 +516,21 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
   ModelS& M = *reinterpret_cast<ModelS*>(smem);
   EnvS* tiles = reinterpret_cast<EnvS*>(smem + MODEL_BYTES);
   stage_model(&M, P.model);
+  // (pinning warp / lane in registers with an opaque asm removes the S2R + shift + multiply-add re-derivations of the
+  // tile address -- 13 % of the instructions under the 72-register cap -- but costs 110 bytes of extra spills:
+  // measured 7.03 M vs 7.21 M env-steps/s without the pin)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
   EnvS& S = tiles[warp];
   const int od = M.obs_dim;
   __shared__ int s_base[8];
   __shared__ int s_arrive[4];
+  __shared__ int s_diag[4];
+  if (threadIdx.x < 4) s_diag[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_slot_owner = -1;
+  // (one shared slot per CTA lies behind the tiles: Y of a stage with more than RF rows, see count_rows)
 #if DMB_SHARE
-  __shared__ int s_share[2];   // task counters of the CTA-wide work sharing
-  if (threadIdx.x < 2) s_share[threadIdx.x] = 0;
+  __shared__ int s_share[16];   // task counters of the work sharing (two per lockstep group)
+  if (threadIdx.x < 16) s_share[threadIdx.x] = 0;
 #else
   int* const s_share = nullptr;
 #endif
@@ -576,8 +583,10 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
       bad = state_bad(M, S, lane);
       if (!bad) set_ctrl(M, S, action, env, lane);
     }
-    const float zc = rk4_step<LOCKSTEP>(M, S, lane, have && !bad, bar_id, bar_n, s_arrive, tiles,
-                                        (LOCKSTEP && M.ngroups == 1) ? s_share : nullptr, gcta);
+    // work sharing happens inside a lockstep group: its tiles, its scratch slots, its two task counters
+    const float zc = rk4_step<LOCKSTEP>(M, S, lane, have && !bad, bar_id, bar_n, s_arrive, tiles + grp * gsz,
+                                        LOCKSTEP ? s_share + 2 * grp : nullptr, gcta + (size_t)grp * gsz * gs::stride, gw,
+                                        LOCKSTEP && M.ngroups == 1);
     if (!have) { round++; continue; }
     if (!bad) bad = state_bad(M, S, lane);
     // reward (dp_env_v3.py:117 / 89-104).  Reference pose: phase_mode 0 = table row of the integer frame
@@ -680,7 +689,13 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
       if (lane < S.ncon) fall = M.geom_type[cm_g1(S.c_meta[lane])] == DMB_GEOM_PLANE && ((M.fall_body_mask >> M.geom_bodyid[cm_g2(S.c_meta[lane])]) & 1u);
       done = done || __any_sync(DMB_FULL, fall);
     }
-    const int flags = S.flags | (bad ? 4 : 0);
+    int flags = S.flags | (bad ? 4 : 0);
+    if (P.trace) {   // diagnostics in the upper bits: rows << 8 (6 bits) | PGS sweeps << 14 (8) | warp time in 2-us units << 22
+      long long tnow;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tnow));
+      const long long dt = (tnow - P.trace[blockIdx.x * 8]) / 2000;
+      flags |= (min(S.diag >> 16, 63) << 8) | (min(S.diag & 0xffff, 255) << 14) | ((int)min(dt, 1023LL) << 22);
+    }
     float ep_ret = st.ep_ret[env] + rew;
     if (lane == 0) {
       out.reward[env] = rew;
@@ -707,10 +722,24 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
     store_state(M, S, st, env, lane);
     __syncwarp();
     ++round;
-    if (P.trace && threadIdx.x == 0 && round < 8) {
+    if (P.trace && (warp | lane) == 0 && round < 6) {
       long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       P.trace[blockIdx.x * 8 + round] = t;
+    }
+    if (P.trace && lane == 0) {   // per-CTA diagnostics of the step: most PGS sweeps / rows of one env, scratch-path envs
+      atomicMax(&s_diag[0], S.diag & 0xffff);
+      atomicMax(&s_diag[1], S.diag >> 16);
+      if ((S.diag >> 16) > RF) atomicAdd(&s_diag[2], 1);
+    }
+  }
+  if (P.trace) {   // slot 6: the CTA's last warp is done; slot 7: diagnostics (sweeps | rows << 16 | scratch envs << 24)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      P.trace[blockIdx.x * 8 + 6] = t;
+      P.trace[blockIdx.x * 8 + 7] = (long long)s_diag[0] | ((long long)s_diag[1] << 16) | ((long long)s_diag[2] << 24);
     }
   }
 }
@@ -833,7 +862,7 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_forward_debug(DevPtrs P, 
     for (int i = lane; i < dbg::stride; i += 32) row[i] = 0.f;
     __syncwarp();
     const float zc = forward_eval<false>(M, S, lane, row, true, 0, 0, nullptr, nullptr, nullptr,
-                                         P.gscratch + (size_t)blockIdx.x * W * gs::stride);
+                                         P.gscratch + (size_t)blockIdx.x * W * gs::stride, warp, false);
     for (int i = lane; i < M.nv; i += 32) row[dbg::qacc + i] = S.qacc[i];
     if (lane == 0) {
       row[dbg::com] = S.com[0]; row[dbg::com + 1] = S.com[1]; row[dbg::com + 2] = S.com[2];
@@ -885,7 +914,7 @@ static int fail(dmb_handle_t h, int code, const std::string& msg) {
 
 static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mocap_t* mc, ModelS& S, std::string& why) {
   memset(&S, 0, sizeof(S));
-  if (m->nv > YS || m->nv > NVC || m->nq > NQC || m->nbody > NB || m->njnt > NJ || m->ngeom > NG || m->npair > NP || m->nu > NU ||
+  if (m->nv > YS || m->nv > NVT || m->nq > NQC - 1 || m->nM > NMT || m->nbody > NB || m->njnt > NJ || m->ngeom > NG || m->npair > NP || m->nu > NU ||
       m->nM > NMX || m->nv > 64) { why = "model exceeds kernel capacities"; return DMB_ERR_MODEL; }
   if (m->max_efc > MAXROW || m->max_con > MAXC || m->max_con > 32 || m->max_efc < m->njnt) {
     why = "max_efc must be <= 40 and >= njnt, max_con <= 16 (kernel capacities)"; return DMB_ERR_MODEL;
@@ -1152,7 +1181,8 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
     if (fa.numRegs > max_regs) max_regs = fa.numRegs;
   }
   const size_t maxsmem = prop.sharedMemPerBlockOptin;
-  int W = maxsmem > MODEL_BYTES + static_smem ? (int)((maxsmem - MODEL_BYTES - static_smem) / sizeof(EnvS)) : 0;
+  constexpr size_t SLOT_BYTES = sizeof(float) * gs::stride;   // the CTA's shared big-stage slot
+  int W = maxsmem > MODEL_BYTES + static_smem + SLOT_BYTES ? (int)((maxsmem - MODEL_BYTES - static_smem - SLOT_BYTES) / sizeof(EnvS)) : 0;
   if (W > DMB_MAXTHREADS / 32) W = DMB_MAXTHREADS / 32;   // __launch_bounds__ of the tile kernels
   {  // the register file bounds the resident warps as well
     const int regs = ((max_regs + 7) / 8) * 8;
@@ -1172,7 +1202,7 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
     if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, cudaGetErrorString(e)); }
   }
   h->envs_per_cta = W; h->block = 32 * W;
-  h->smem = (int)(MODEL_BYTES + (size_t)W * sizeof(EnvS));
+  h->smem = (int)(MODEL_BYTES + (size_t)W * sizeof(EnvS) + SLOT_BYTES);
   int need = (num_envs + W - 1) / W;
   h->grid = need < prop.multiProcessorCount ? need : prop.multiProcessorCount;
   for (auto fn : tile_kernels) {

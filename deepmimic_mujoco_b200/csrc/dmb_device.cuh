@@ -568,6 +568,17 @@ __device__ int raw_capsule_box(RawCon* c, float margin, V3 cpos, const float* cm
     knot[j + 1] = v;
   }
   float tlo, thi;
+  // the axis runs through the box: zero distance on the clipped stretch [tin, tout] (see oracle raw_capsule_box)
+  float tin = -h, tout = h;
+  for (int k = 0; k < 3; k++) {
+    if (fabsf(uu[k]) > 1e-12f) {
+      float ta = (-ss[k] - cc[k]) / uu[k], tb = (ss[k] - cc[k]) / uu[k];
+      if (ta > tb) { const float t = ta; ta = tb; tb = t; }
+      tin = fmaxf(tin, ta); tout = fminf(tout, tb);
+    } else if (fabsf(cc[k]) > ss[k]) { tin = h; tout = -h; }
+  }
+  if (tout - tin > 1e-6f * h) { tlo = tin; thi = tout; }
+  else {
   {
     float gprev = capbox_dfdt(cl, u, bs, knot[0]);
     if (gprev >= 0.f) tlo = knot[0];
@@ -592,7 +603,10 @@ __device__ int raw_capsule_box(RawCon* c, float margin, V3 cpos, const float* cm
       }
     }
   }
-  const float ts = (thi - tlo > 1e-6f * h) ? (fabsf(tlo) <= fabsf(thi) ? tlo : thi) : 0.5f * (tlo + thi);
+  }
+  // flat stretch (see oracle raw_capsule_box): the end nearer the capsule centre, moved 1e-3 of the stretch inwards
+  float ts = 0.5f * (tlo + thi);
+  if (thi - tlo > 1e-6f * h) ts = fabsf(tlo) <= fabsf(thi) ? tlo + 1e-3f * (thi - tlo) : thi - 1e-3f * (thi - tlo);
   int n = 0;
   n += raw_sphere_box(c[n], margin, cpos + ts * axis, r, bpos, bmat, bs);
   const float te = (h - ts >= ts + h) ? h : -h;
@@ -770,7 +784,6 @@ __device__ DMB_PHASE_FN void collision(const ModelS& M, EnvS& S, int lane) {
         make_frame(&S.o.c.c_frame[6 * ci], rc[i].n, rc[i].y);
         const int cd1 = M.geom_condim[g1], cd2 = M.geom_condim[g2];
         S.c_meta[ci] = g1 | (g2 << 8) | ((cd1 > cd2 ? cd1 : cd2) << 16);   // first row (bits 24..31) set by count_rows
-        S.c_mu[ci] = fmaxf(M.geom_mu[g1], M.geom_mu[g2]);
       }
     }
     ncon += total;
@@ -785,16 +798,18 @@ __device__ DMB_PHASE_FN void collision(const ModelS& M, EnvS& S, int lane) {
 //   Y rows 0..nefc-1 = J rows (lane = dof), per-row R / aref / dof support (lane = row).
 // Limit rows come first (joint order, lower then upper), then contacts in contact order:
 // 1 frictionless row (condim 1) or 4 pyramid edges (condim 3).
-// Row storage: the tile's PhaseR for up to RF rows, else (OVF) the warp's global scratch slot G.
+// Row storage: the tile's PhaseR for up to RF rows; else (OVF) Y in the warp's global scratch slot G and the
+// row scalars / AR in the tile's PhaseRbig.
 // ------------------------------------------------------------------------------------------
 template <bool OVF> struct RowView {
   float *Y, *e_R, *e_aref, *e_b, *e_f, *AR;
   unsigned long long* rowmask;
-  int* e_src;
+  signed char* e_src;
   __device__ __forceinline__ RowView(EnvS& S, float* G) {
     if (OVF) {
-      Y = G + gs::Y; e_R = G + gs::e_R; e_aref = G + gs::e_aref; e_b = G + gs::e_b; e_f = G + gs::e_f; AR = G + gs::AR;
-      rowmask = reinterpret_cast<unsigned long long*>(G + gs::rowmask); e_src = reinterpret_cast<int*>(G + gs::e_src);
+      Y = G + gs::Y; e_src = reinterpret_cast<signed char*>(G + gs::e_src);
+      e_R = S.o.rb.e_R; e_aref = S.o.rb.e_aref; e_b = S.o.rb.e_b; e_f = S.o.rb.e_f; AR = S.o.rb.AR;
+      rowmask = S.o.rb.rowmask;
     } else {
       Y = S.o.r.Y; e_R = S.o.r.e_R; e_aref = S.o.r.e_aref; e_b = S.o.r.e_b; e_f = S.o.r.e_f; AR = S.o.r.AR;
       rowmask = S.o.r.rowmask; e_src = S.e_src;
@@ -807,7 +822,10 @@ __device__ __forceinline__ int lim_side(int src) { return (-src) & 1; }
 
 // Row bookkeeping: active limits (lane = joint), contact row addresses (lane = contact), capacity check.
 // Writes e_src and the first-row field of c_meta; returns nefc.
-__device__ DMB_PHASE_FN int count_rows(const ModelS& M, EnvS& S, int lane, float* G) {
+// warp that holds the CTA's one shared slot for a stage with more than RF rows (-1: free); reset by k_step
+__shared__ int s_slot_owner;
+
+__device__ DMB_PHASE_FN int count_rows(const ModelS& M, EnvS& S, int lane, float* Gglobal, float* slot, int warp) {
   int cnt = 0;
   bool lo = false, hi = false;
   if (lane < M.njnt && M.jnt_limited[lane] && M.jnt_type[lane] == DMB_JNT_HINGE) {
@@ -834,17 +852,25 @@ __device__ DMB_PHASE_FN int count_rows(const ModelS& M, EnvS& S, int lane, float
   }
   int nefc = nlimit;
   if (ncon > 0) nefc = __shfl_sync(DMB_FULL, adr + nrow, ncon - 1);
-  int* e_src = nefc > RF ? reinterpret_cast<int*>(G + gs::e_src) : S.e_src;
+  // A stage with more than RF rows keeps Y (and e_src) outside the tile: in the CTA's one shared slot if it is free
+  // (claimed until this stage's solve is done), else in the warp's global scratch slot (slow, very rare).
+  int big = 0;
+  if (nefc > RF) {
+    if (lane == 0) big = (slot && atomicCAS(&s_slot_owner, -1, warp) == -1) ? 1 : 2;
+    big = __shfl_sync(DMB_FULL, big, 0);
+  }
+  float* const G = big == 1 ? slot : Gglobal;
+  signed char* e_src = big ? reinterpret_cast<signed char*>(G + gs::e_src) : S.e_src;
   {
     int r = incl - cnt;
-    if (lo) e_src[r++] = -(2 * (1 + lane));
-    if (hi) e_src[r] = -(2 * (1 + lane) + 1);
+    if (lo) e_src[r++] = (signed char)(-(2 * (1 + lane)));
+    if (hi) e_src[r] = (signed char)(-(2 * (1 + lane) + 1));
   }
   if (lane < ncon) {
     S.c_meta[lane] = (S.c_meta[lane] & 0xffffff) | (adr << 24);
-    for (int k = 0; k < nrow; k++) e_src[adr + k] = lane * 4 + k;
+    for (int k = 0; k < nrow; k++) e_src[adr + k] = (signed char)(lane * 4 + k);
   }
-  if (lane == 0) { S.nefc = nefc; S.nlimit = nlimit; }
+  if (lane == 0) { S.nefc = nefc; S.nlimit = nlimit; S.big = big; }
   __syncwarp();
   return nefc;
 }
@@ -920,7 +946,7 @@ __device__ DMB_PHASE_FN void build_rows(const ModelS& M, EnvS& S, int lane, floa
       if (cm_dim(cm) == 1) { dA = tran; vel = vn; }
       else {
         pyramid = true;
-        mu = S.c_mu[c];
+        mu = fmaxf(M.geom_mu[cm_g1(cm)], M.geom_mu[cm_g2(cm)]);
         const float vt = dot((k >> 1) ? cross(n, t1) : t1, vr);
         vel = vn + ((k & 1) ? -mu : mu) * vt;
         dA = tran + mu * mu * tran;
@@ -1088,7 +1114,8 @@ __device__ DMB_PHASE_FN void half_solve_rows(const ModelS& M, EnvS& S, int lane,
     }
     a_lo *= dlo; a_hi *= dhi;
     if (pyr) {
-      const float mu = S.c_mu[src >> 2];
+      const int cmm = S.c_meta[src >> 2];
+      const float mu = fmaxf(M.geom_mu[cm_g1(cmm)], M.geom_mu[cm_g2(cmm)]);
       b_lo *= mu * dlo; b_hi *= mu * dhi; c_lo *= mu * dlo; c_hi *= mu * dhi;
       if (has_lo) { y[lane] = a_lo + b_lo; y[YS + lane] = a_lo - b_lo; y[2 * YS + lane] = a_lo + c_lo; y[3 * YS + lane] = a_lo - c_lo; }
       if (has_hi) {
@@ -1154,9 +1181,11 @@ __device__ DMB_PHASE_FN void gram(const ModelS& M, EnvS& S, int lane, int nefc, 
 // the global scratch slot): residuals res = AR f + b live in registers (lane = row, and row + 32 when HI); a row
 // update broadcasts its force increment and every lane applies one column of AR.  All rows are scalar with
 // force >= 0 (limits, frictionless normals, pyramid edges).
+// (inlined into its two call sites in solve_constraints<true>: as an out-of-line function its four reference
+// parameters lived in local memory and every row update paid several L1/L2 round trips -- 125 cycles per row)
 template <bool HI>
-__device__ __noinline__ int pgs_sweeps(const ModelS& M, const float* AR, int lane, int nefc, float& f0, float& f1,
-                                       float& res0, float& res1) {
+__device__ __forceinline__ int pgs_sweeps(const ModelS& M, const float* AR, int lane, int nefc, float& f0, float& f1,
+                                          float& res0, float& res1) {
   const int r0 = lane, r1 = lane + 32;
   const bool a0 = r0 < nefc, a1 = HI && r1 < nefc;
   const float d0 = a0 ? AR[tri(r0) + r0] : 1.f, d1 = a1 ? AR[tri(r1) + r1] : 1.f;
@@ -1314,6 +1343,7 @@ __device__ DMB_PHASE_FN void solve_constraints(const ModelS& M, EnvS& S, int lan
   }
   if (lane == 0) {
     S.iter = iter;
+    S.diag = ((S.diag & 0xffff) + iter) | (max(S.diag >> 16, nefc) << 16);
     // scheduler key (see k_order): modes 0-2 accumulate over the RK stages, 3-4 keep the last stage only
     if (M.cost_mode == 3) S.cost = 4 * nefc * iter;
     else if (M.cost_mode == 4) S.cost = 4 * nefc * (8 + iter);
@@ -1373,9 +1403,12 @@ __device__ __forceinline__ void patient_barrier(int* cnt, int W, int patience, i
 
 template <bool LOCKSTEP>
 __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, float* dbgrow, bool active, int bar_id,
-                                         int bar_n, int* arrive, EnvS* tiles, int* share_cnt, float* gcta) {
+                                         int bar_n, int* arrive, EnvS* tiles, int* share_cnt, float* gcta, int warp,
+                                         bool use_slot) {
+  // the CTA's shared slot lies behind its last tile (k_step); only the single-group lockstep kernel has one
+  float* const slot = use_slot ? reinterpret_cast<float*>(tiles + (bar_n >> 5)) : nullptr;
 #define DMB_PHASE_SYNC(bit) do { if (LOCKSTEP && (M.sync_mask & (bit))) { if (M.arrive_k > 0) arrival_barrier(arrive, bar_n >> 5, M.arrive_k, lane); else if (M.patience > 0) patient_barrier(arrive, bar_n >> 5, M.patience, lane); else group_barrier(bar_id, bar_n); } } while (0)
-  float* const G = gcta + (size_t)(threadIdx.x >> 5) * gs::stride;   // this warp's scratch slot (stages with > RF rows)
+  float* G = gcta + (size_t)warp * gs::stride;   // where Y lives in a stage with > RF rows (set by count_rows)
   DMB_TICK(0);
   DMB_PHASE_SYNC(1);
   DMB_TICK(1);
@@ -1412,7 +1445,8 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
   DMB_PHASE_SYNC(16);
   int nefc = 0;
   if (active) {
-    nefc = count_rows(M, S, lane, G);
+    nefc = count_rows(M, S, lane, G, slot, warp);
+    if (S.big == 1) G = slot;
     if (dbgrow) {   // contact geometry and cvel are overwritten by the row data below
       for (int i = lane; i < M.nbody * 6; i += 32) dbgrow[dbg::cvel + i] = S.o.c.cvel[i];
       for (int c = lane; c < S.ncon; c += 32) {
@@ -1453,12 +1487,12 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
         const int nlw = __shfl_sync(DMB_FULL, nl, w);
         EnvS& T = tiles[w];
         const int row = g < nlw ? g : cm_adr(T.c_meta[g - nlw]);
-        if (T.nefc > RF) half_solve_rows<true>(M, T, lane, row, row + 1, gcta + (size_t)w * gs::stride);
+        if (T.nefc > RF) half_solve_rows<true>(M, T, lane, row, row + 1, T.big == 1 ? slot : gcta + (size_t)w * gs::stride);
         else half_solve_rows<false>(M, T, lane, row, row + 1, nullptr);
       }
     }
     group_barrier(bar_id, bar_n);                                   // B: every Y row is half-solved
-    if (threadIdx.x == 0) share_cnt[0] = 0;
+    if ((warp | lane) == 0) share_cnt[0] = 0;
     {
       int nt = 0, ne = 0;
       if (lane < W) { ne = tiles[lane].nefc; nt = (tri(ne) + ne + 31) >> 5; }
@@ -1472,12 +1506,12 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
         const int w = __popc(__ballot_sync(DMB_FULL, incl <= t));
         const int c = t - (w > 0 ? __shfl_sync(DMB_FULL, incl, w - 1) : 0);
         const int new_ = __shfl_sync(DMB_FULL, ne, w);
-        if (new_ > RF) gram<true>(M, tiles[w], lane, new_, 32 * c, 32 * c + 32, gcta + (size_t)w * gs::stride);
+        if (new_ > RF) gram<true>(M, tiles[w], lane, new_, 32 * c, 32 * c + 32, tiles[w].big == 1 ? slot : gcta + (size_t)w * gs::stride);
         else gram<false>(M, tiles[w], lane, new_, 32 * c, 32 * c + 32, nullptr);
       }
     }
     group_barrier(bar_id, bar_n);                                   // C: every AR / b entry is in place
-    if (threadIdx.x == 0) share_cnt[1] = 0;
+    if ((warp | lane) == 0) share_cnt[1] = 0;
   } else
 #endif
   {
@@ -1518,6 +1552,10 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
   DMB_TICK(9);
   if (active) {
     if (nefc > RF) solve_constraints<true>(M, S, lane, nefc, G); else solve_constraints<false>(M, S, lane, nefc, G);
+    if (nefc > RF && S.big == 1 && !dbgrow) {   // hand the CTA's shared slot back
+      __syncwarp();
+      if (lane == 0) atomicExch(&s_slot_owner, -1);
+    }
     if (dbgrow) {
       const RowView<true> Vg(S, G);
       const RowView<false> Vt(S, G);

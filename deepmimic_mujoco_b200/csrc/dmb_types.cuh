@@ -20,6 +20,8 @@ constexpr int NG = DMB_MAX_GEOM;  // 16
 constexpr int NP = DMB_MAX_PAIR;  // 128
 constexpr int NU = DMB_MAX_U;     // 32
 constexpr int NMX = DMB_MAX_M;    // 320
+constexpr int NMT = 312;          // sparse-inertia capacity of the tile (nM <= 312; humanoid: 310)
+constexpr int NVT = 34;           // dof capacity of the tile arrays that need no 16-byte alignment
 constexpr int MAXANC = 12;        // longest dof ancestor chain (humanoid: 12)
 constexpr int MAXROW = 40;        // constraint-row capacity of the kernel (max_efc <= 40)
 constexpr int MAXC = 16;          // contact capacity per env (max_con <= 16)
@@ -100,8 +102,8 @@ struct ModelS {
 //   PhaseR  the half-solved constraint Jacobian Y, per-row scalars and the packed Delassus matrix AR for up to
 //           RF rows.  Y is written while cdof / contact geometry are still read (they lie behind it); the row
 //           scalars and AR are written after those are dead.
-// Envs with more than RF rows in a stage (rare: < 0.1 % of the benchmark's stage evaluations) keep Y / rows / AR in
-// a per-warp scratch slot in global memory instead (same code, template parameter OVF).
+// Envs with more than RF rows in a stage (about 0.1 % of the benchmark's stage evaluations) keep Y in a per-warp
+// scratch slot in global memory and the row scalars / AR in PhaseRbig (same code, template parameter OVF).
 #ifndef DMB_RF
 #define DMB_RF 24
 #endif
@@ -131,11 +133,24 @@ struct PhaseR {
   unsigned long long rowmask[RF];                                    // [936, 984) dof support of each half-solved row
   float AR[NTRI_F];                                                  // [984, 1284) packed lower triangle of J M^-1 J' + R
 };
+// Stage with more than RF rows: the half-solved Jacobian Y (MAXROW x YS floats) does not fit the tile and lives in
+// the warp's global scratch slot; the latency-critical row scalars and the Delassus matrix (PGS reads a column per
+// row update) stay in shared memory, in the part of the overlay that Y leaves free.
+struct PhaseRbig {
+  float e_R[MAXROW], e_aref[MAXROW], e_b[MAXROW], e_f[MAXROW];      // [0, 160)
+  unsigned long long rowmask[MAXROW];                                // [160, 240)
+  float AR[NTRI];                                                    // [240, 1060): over cdof, written after J is built
+};
 union Overlay {
   PhaseK k;
   PhaseC c;
   PhaseR r;
+  PhaseRbig rb;
 };
+static_assert(offsetof(PhaseRbig, AR) <= offsetof(PhaseK, cdof),
+              "the big-row scalars are written by the row stage, which still reads cvel and the contact geometry (AR is "
+              "written later, by the Gram stage, and may lie over them)");
+static_assert(offsetof(PhaseRbig, rowmask) % 8 == 0, "alignment");
 static_assert(offsetof(PhaseC, cdof) == offsetof(PhaseK, cdof), "cdof must not move between phases");
 static_assert(offsetof(PhaseC, xmat) == offsetof(PhaseK, xmat), "xmat must not move between phases");
 static_assert(offsetof(PhaseR, e_R) >= offsetof(PhaseK, cdof), "row scalars may only overwrite cdof / cvel");
@@ -145,15 +160,17 @@ static_assert(offsetof(PhaseR, AR) % 4 == 0 && offsetof(PhaseR, rowmask) % 8 == 
 struct EnvS {
   float qpos[NQC], qvel[NVC], ctrlf[NVC];
   float qacc[NVC];                     // also qacc_warmstart: mj_forward leaves warmstart = qacc
-  float x_q0[NQC], x_dv[NVC];          // RK4: X0 positions, stage velocity; x_dv doubles as scratch inside forward_eval
-  float qLD[NMX], dsq[NVC], ys[NVC];   // sparse factor, D^-1/2, y_s = D^-1/2 L^-T qfrc_smooth
-  float com[4];
-  int ncon, nefc, nlimit, flags, iter, cost, pad0, pad1;
+  float x_q0[NQC - 1], x_dv[NVC];      // RK4: X0 positions (nq <= 35), stage velocity; x_dv doubles as scratch inside forward_eval
+  float qLD[NMT], dsq[NVT], ys[NVT];   // sparse factor, D^-1/2, y_s = D^-1/2 L^-T qfrc_smooth
+  float com[3];
+  int diag;                            // diagnostics: PGS sweeps summed over the RK stages | largest row count << 16
+  int ncon, nefc, nlimit, flags, iter, cost;
+  int big;                             // stage with > RF rows: 1 = Y in the CTA's shared slot, 2 = in global scratch
   int c_meta[MAXC];                    // geom1 | geom2 << 8 | condim << 16 | first row << 24
-  float c_mu[MAXC];
-  int e_src[RF];                       // row source: >=0 contact*4+edge, <0 joint limit (see make_constraint)
+  signed char e_src[RF];               // row source: >=0 contact*4+edge, <0 joint limit (see count_rows)
   Overlay o;
 };
+static_assert(sizeof(EnvS) % 16 == 0, "tiles start on 16-byte boundaries (float4 state rows)");
 __device__ __forceinline__ int cm_g1(int m) { return m & 0xff; }
 __device__ __forceinline__ int cm_g2(int m) { return (m >> 8) & 0xff; }
 __device__ __forceinline__ int cm_dim(int m) { return (m >> 16) & 0xff; }
@@ -162,15 +179,8 @@ __device__ __forceinline__ int cm_adr(int m) { return (m >> 24) & 0xff; }
 // Global scratch slot of one warp for a stage with more than RF rows (floats)
 namespace gs {
 constexpr int Y = 0;                          // MAXROW * YS
-constexpr int e_R = Y + MAXROW * YS;
-constexpr int e_aref = e_R + MAXROW;
-constexpr int e_b = e_aref + MAXROW;
-constexpr int e_f = e_b + MAXROW;
-constexpr int rowmask = e_f + MAXROW;         // MAXROW x u64 (8-byte aligned: all offsets are even)
-constexpr int AR = rowmask + 2 * MAXROW;      // NTRI
-constexpr int e_src = AR + NTRI;              // MAXROW ints
-constexpr int stride = ((e_src + MAXROW + 31) / 32) * 32;
-static_assert(rowmask % 2 == 0, "u64 alignment");
+constexpr int e_src = Y + MAXROW * YS;        // MAXROW bytes (10 words)
+constexpr int stride = ((e_src + MAXROW / 4 + 3) / 4) * 4;
 }  // namespace gs
 
 // Debug row layout (floats) for dmb_forward_debug

@@ -14,7 +14,6 @@
 """
 from __future__ import annotations
 
-import types
 from typing import Optional, Sequence
 
 import numpy as np
@@ -117,6 +116,64 @@ class DPVecEnv:
         self.sim.close()
 
 
+class _StateView(np.ndarray):
+    """``env.sim.data.qpos`` / ``qvel``: a float64 host copy of one state row whose item assignment writes
+    through to the device tensor, so the mujoco-py idiom ``sim.data.qpos[:] = x`` (dp_env_v3.py:192-197 style
+    scripts) changes the simulation state instead of a temporary."""
+
+    def __new__(cls, values, push):
+        obj = np.asarray(values, dtype=np.float64).view(cls)
+        obj._push = push
+        return obj
+
+    def __array_finalize__(self, obj):
+        self._push = getattr(obj, "_push", None)
+
+    def __setitem__(self, key, value):
+        super().__setitem__(key, value)
+        root = self
+        while isinstance(root.base, _StateView):     # a slice of the view writes through as well
+            root = root.base
+        if root._push is not None:
+            root._push(np.asarray(root))
+
+
+class _SimData:
+    """``env.sim.data`` (the mjData fields the reference's scripts touch)."""
+
+    def __init__(self, env):
+        self._env = env
+
+    @property
+    def qpos(self):
+        s = self._env._sim
+        def push(a):
+            s.qpos[0, : s.nq] = torch.as_tensor(a, dtype=torch.float32, device=s.device)
+        return _StateView(s.qpos[0, : s.nq].double().cpu().numpy(), push)
+
+    @property
+    def qvel(self):
+        s = self._env._sim
+        def push(a):
+            s.qvel[0, : s.nv] = torch.as_tensor(a, dtype=torch.float32, device=s.device)
+        return _StateView(s.qvel[0, : s.nv].double().cpu().numpy(), push)
+
+    @property
+    def ctrl(self):
+        return self._env._act[0].double().cpu().numpy()
+
+
+class _SimView:
+    """``env.sim``: ``data`` plus ``forward()`` (mj_forward at the current state) as mujoco-py's MjSim."""
+
+    def __init__(self, env):
+        self.data = _SimData(env)
+        self._env = env
+
+    def forward(self):
+        self._env._forward(self._env._act)
+
+
 class _MocapView:
     """``env.mocap`` as poked by the reference scripts (dp_env_v3.py:192-197, env_torque_test.py)."""
 
@@ -158,12 +215,11 @@ class DPEnv(_EnvBase):
                                  (t.nu,), np.float32)
         self.np_random = np.random.RandomState(seed)
         self._act = torch.zeros(1, t.nu, dtype=torch.float32, device=self._sim.device)
-        self._needs_reset = False
         # gym MujocoEnv.__init__ side effect: one probe step with a random action
         ob, _, done, _ = self.step(self.action_space.sample())
         assert not done
         self.observation_space = _Box(-np.inf, np.inf, (ob.size,), np.float64)
-        self.sim = types.SimpleNamespace(data=self)  # env.sim.data.qpos / qvel
+        self.sim = _SimView(self)  # env.sim.data.qpos / qvel (write-through), env.sim.forward()
 
     # --- gym.Env ------------------------------------------------------------------------
     @property
@@ -216,7 +272,6 @@ class DPEnv(_EnvBase):
         ob = self._sim.reset(mode=0)[0].double().cpu().numpy()   # reset_model(): mocap RSI
         self._act.zero_()                                         # sim.reset() clears data.ctrl
         self._forward(self._act)
-        self._needs_reset = False
         return ob
 
     def reset_model(self):

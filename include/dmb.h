@@ -62,7 +62,8 @@ typedef struct dmb_state {
   uint32_t* reset_count; /* [N] Philox counter: number of resets so far */
   int32_t* ep_len;       /* [N] steps in the current episode */
   float* ep_ret;         /* [N] return of the current episode */
-  int32_t* flags;        /* [N] bit0 contact overflow, bit1 row overflow, bit2 non-finite state */
+  int32_t* flags;        /* [N] bit0 contact overflow, bit1 row overflow, bit2 non-finite state (bits 8.. carry
+                          * per-env diagnostics when DMB_TRACE=1, see dmb_get_trace) */
 } dmb_state_t;
 
 /* Outputs of one step (caller-owned device buffers). `rec` is optional: the packed
@@ -125,8 +126,10 @@ int32_t dmb_debug_offset(const char* name);
 int dmb_launch_info(dmb_handle_t h, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* envs_per_cta);
 
 /* Diagnostics (DMB_TRACE=1 in the environment at create time): per-CTA timeline of the last dmb_step,
- * host int64 [grid][8] = globaltimer ns at kernel start and after each scheduler round; returns the number
- * of CTAs written (0 when tracing is off).  Synchronises the device. */
+ * host int64 [grid][8]: [0] globaltimer ns at kernel start, [1..5] when warp 0 finished its 1st..5th scheduler
+ * round, [6] when the CTA's last warp was done, [7] most PGS sweeps of one env (summed over the RK stages) |
+ * largest row count << 16 | envs that used the global scratch rows << 24; returns the number of CTAs written
+ * (0 when tracing is off).  Synchronises the device. */
 int32_t dmb_get_trace(dmb_handle_t h, int64_t* host_out, int32_t max_ctas);
 
 const char* dmb_last_error(dmb_handle_t h);

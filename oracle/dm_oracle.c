@@ -384,6 +384,20 @@ static int raw_capsule_box(rawcon_t* c, double margin, const double* cpos, const
     knot[j + 1] = v;
   }
   double tlo, thi;
+  /* Does the axis run through the box?  Clip the segment against the three slabs (Liang-Barsky): inside the box
+   * the distance is zero on the whole stretch [tin, tout], and looking for roots of its derivative there means
+   * testing the sign of rounding noise (found by the full-size parity test: fp32 and fp64 disagreed). */
+  double tin = -h, tout = h;
+  for (int k = 0; k < 3; k++) {
+    if (fabs(u[k]) > 1e-12) {
+      double ta = (-bsize[k] - cl[k]) / u[k], tb = (bsize[k] - cl[k]) / u[k];
+      if (ta > tb) { double t = ta; ta = tb; tb = t; }
+      if (ta > tin) tin = ta;
+      if (tb < tout) tout = tb;
+    } else if (fabs(cl[k]) > bsize[k]) { tin = h; tout = -h; }
+  }
+  if (tout - tin > 1e-6*h) { tlo = tin; thi = tout; }
+  else {
   { /* leftmost root */
     double gprev = capbox_dfdt(cl, u, bsize, knot[0]);
     if (gprev >= 0) tlo = knot[0];
@@ -408,9 +422,14 @@ static int raw_capsule_box(rawcon_t* c, double margin, const double* cpos, const
       }
     }
   }
-  /* a flat stretch of the derivative (axis inside the box, or sliding parallel to a face): take
-   * the end nearer the capsule centre -- a midpoint would sit equidistant from opposite faces */
-  double ts = (thi - tlo > 1e-6*h) ? (fabs(tlo) <= fabs(thi) ? tlo : thi) : 0.5*(tlo + thi);
+  }
+  /* a flat stretch of the derivative (the axis runs through the box, or slides parallel to a face): the closest
+   * point is not unique.  Take the end nearer the capsule centre (the middle would sit equidistant from the two
+   * faces a capsule pierces), moved into the stretch by 1e-3 of its length: the end itself lies exactly ON the box
+   * surface, where the sphere-box normal is a 0/0 limit that fp32 and fp64 resolve differently (found by the
+   * full-size parity test on spinkick: knee capsule through the other foot's box). */
+  double ts = 0.5*(tlo + thi);
+  if (thi - tlo > 1e-6*h) ts = fabs(tlo) <= fabs(thi) ? tlo + 1e-3*(thi - tlo) : thi - 1e-3*(thi - tlo);
   int n = 0;
   double sp[3];
   for (int k = 0; k < 3; k++) sp[k] = cpos[k] + ts*axis[k];

@@ -73,6 +73,18 @@ def check_step(sim, po, mcs, seed, st, act, obs, rew, done, label, frac_loose=2e
           f"|dqpos| max {eq.max():.2e} | rel |dqvel| p50 {np.median(ev):.1e} p99 {np.quantile(ev, 0.99):.1e} "
           f"p99.9 {np.quantile(ev, 0.999):.1e} max {ev.max():.2e} | beyond 1e-4: {int(loose.sum())} envs | "
           f"|dreward| max {er.max():.1e}")
+    if loose.any():   # keep the outliers for offline analysis with the oracle (tools/analyze_outliers.py)
+        import os
+        idx = np.nonzero(alive)[0][loose]
+        try:
+            os.makedirs(os.path.join(common.ROOT, "gpurun_out"), exist_ok=True)
+            np.savez(os.path.join(common.ROOT, "gpurun_out", "parity_outliers_" + label.replace(" ", "_").replace("=", "") + ".npz"),
+                     idx=idx, qpos=st["qpos"][idx], qvel=st["qvel"][idx], warm=st["warm"][idx],
+                     action=act.double().cpu().numpy()[idx], gpu_qpos=gq[idx], gpu_qvel=gv[idx],
+                     ora_qpos=out["qpos"][idx], ora_qvel=out["qvel"][idx], nefc=out["nefc"][idx],
+                     **{k: st[k][idx] for k in STATE_KEYS})
+        except OSError:
+            pass
     common.record(label.split(" ")[0], "qvel_rel_p999", np.quantile(ev, 0.999))
     common.record(label.split(" ")[0], "qvel_rel_max_excluding_threshold_flips", ev[~loose].max())
     common.record(label.split(" ")[0], "threshold_flip_envs_per_step", loose.sum())

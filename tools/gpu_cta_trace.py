@@ -30,13 +30,20 @@ for t in range(140):
         n = sim.L.dmb_get_trace(sim.handle, buf.ctypes.data_as(C.c_void_p), 256)
         tr = buf[:n].astype(np.float64)
         t0 = tr[:, 0].min()
-        rounds = (tr[:, 1:] > 0).sum(axis=1)
-        end = tr[:, 1:].max(axis=1) - t0
+        rounds = (tr[:, 1:6] > 0).sum(axis=1)
+        end = tr[:, 6] - t0                      # the CTA's last warp
+        diag = buf[:n, 7]
+        sweeps, rows, nscr = diag & 0xffff, (diag >> 16) & 0xff, diag >> 24
         r1 = tr[:, 1] - t0
         start = tr[:, 0] - t0
         print(f"step {t}: kernel {end.max()/1e3:7.1f} us | CTA end mean {end.mean()/1e3:7.1f} min {end.min()/1e3:7.1f} max {end.max()/1e3:7.1f} "
               f"| idle tail {100*(1-end.mean()/end.max()):4.1f}% | round-1 end mean {r1.mean()/1e3:6.1f} min {r1.min()/1e3:6.1f} max {r1.max()/1e3:6.1f} "
               f"| rounds/CTA {np.bincount(rounds)} | start spread {start.max()/1e3:5.1f} us")
+        slow = np.argsort(end)[-5:][::-1]
+        print("   slowest CTAs (us, most sweeps of one env, most rows, scratch envs):",
+              [(round(end[i] / 1e3, 1), int(sweeps[i]), int(rows[i]), int(nscr[i])) for i in slow],
+              f"| corr(end, sweeps) {np.corrcoef(end, sweeps)[0, 1]:.2f} corr(end, rows) {np.corrcoef(end, rows)[0, 1]:.2f}",
+              f"| CTAs with a scratch env: {int((nscr > 0).sum())}, their mean end {end[nscr > 0].mean() / 1e3 if (nscr > 0).any() else 0:.1f} us")
         if t == 130:
             order = np.argsort(r1)
             r2 = end - r1

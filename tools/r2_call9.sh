@@ -1,0 +1,18 @@
+#!/bin/bash
+set -u
+O=gpurun_out
+rm -f $O/parity_outliers_*.npz
+python -m pytest tests -m gpu -q > $O/r2c9_pytest.log 2>&1
+tail -3 $O/r2c9_pytest.log; grep "n=16384" $O/r2c9_pytest.log | cut -c1-250
+DMB_TRACE=1 python tools/gpu_slow_step_probe.py 4096 110 > $O/r2c9_slow_probe.txt 2>&1
+python - <<'PY'
+import re, statistics as st
+sp=[float(m.group(1)) for m in re.finditer(r"span\s+([0-9.]+) us", open("gpurun_out/r2c9_slow_probe.txt").read())]
+print("spans: n", len(sp), "mean", round(st.mean(sp),1), "median", round(st.median(sp),1), "min", min(sp), "max", max(sp))
+PY
+grep "> 32: [1-9]" $O/r2c9_slow_probe.txt | head -3 | cut -c1-250
+python bench.py --no-cpu-baseline > $O/r2c9_bench_1gpu.json 2>/dev/null; cut -c1-250 $O/r2c9_bench_1gpu.json
+for kn in "DMB_GROUPS=2" "DMB_GROUPS=4" "DMB_SYNC_MASK=0x01" "DMB_SPREAD=0"; do
+  echo "== $kn"; env $kn python bench.py --steps 100 --warmup 20 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'])"
+done
+for c in 3 4 5; do python bench.py --config $c --steps 100 --warmup 10 --no-cpu-baseline > $O/r2c9_bench_config$c.json 2>/dev/null; cut -c60-200 $O/r2c9_bench_config$c.json; done
