@@ -897,6 +897,9 @@ struct dmb_handle_s {
   int nu = 0, obs_dim = 0;
   int lockstep = 1;
   int no_sort = 0;
+  int sort_period = 1;      // single-round schedule: re-sort the env list every sort_period steps
+  long long nstep = 0;
+  long long nlaunch = 0;    // kernels launched through this handle so far
   std::string err;
 };
 
@@ -1191,6 +1194,8 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
   }
   if (const char* lenv = getenv("DMB_LOCKSTEP")) h->lockstep = atoi(lenv) != 0;
   if (const char* ns = getenv("DMB_NO_SORT")) h->no_sort = atoi(ns) != 0;
+  h->sort_period = 8;
+  if (const char* sp = getenv("DMB_SORT_PERIOD")) { int p = atoi(sp); if (p >= 1) h->sort_period = p; }
   if (const char* wenv = getenv("DMB_ENVS_PER_CTA")) { int w = atoi(wenv); if (w >= 1 && w < W) W = w; }
   if (W < 1) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, "not enough shared memory for one env tile"); }
   {  // lockstep groups: DMB_GROUPS (default 1); must divide the warps of a CTA
@@ -1260,7 +1265,16 @@ int dmb_step(dmb_handle_t h, const dmb_state_t* st, const float* action, const d
   if (!h) return DMB_ERR_ARG;
   if (!state_ok(st) || !action || !out || !out->obs || !out->reward || !out->done) return fail(h, DMB_ERR_ARG, "dmb_step: bad argument");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  k_order<<<1, 1024, 0, (cudaStream_t)stream>>>(h->d_cost, h->d_order, h->d_counter, h->num_envs, h->no_sort);
+  // Scheduler sort.  With dynamic pulling (more envs than resident warps) it runs every step: it also rewinds the
+  // pull counter.  When one round holds every env the sorted list only balances the CTAs' mix of heavy and light
+  // envs, which changes slowly: it is refreshed every sort_period steps (the sort costs 10 us + a launch gap).
+  const bool single_round = h->lockstep && h->hmodel.spread && h->num_envs <= h->grid * h->envs_per_cta;
+  if (!single_round || h->nstep % h->sort_period == 0) {
+    k_order<<<1, 1024, 0, (cudaStream_t)stream>>>(h->d_cost, h->d_order, h->d_counter, h->num_envs, h->no_sort);
+    h->nlaunch++;
+  }
+  h->nstep++;
+  h->nlaunch++;
   if (h->lockstep) k_step<true><<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
   else k_step<false><<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
   CUDA_TRY(h, cudaGetLastError());
@@ -1307,6 +1321,8 @@ int dmb_mocap_sample(dmb_handle_t h, const int32_t* clip, const double* frame_co
 }
 
 int32_t dmb_obs_dim(dmb_handle_t h) { return h ? h->obs_dim : DMB_ERR_ARG; }
+
+int64_t dmb_kernel_launches(dmb_handle_t h) { return h ? h->nlaunch : DMB_ERR_ARG; }
 
 #if DMB_PHASE_TIMERS
 /* diagnostic builds only (-DDMB_PHASE_TIMERS=1): read and clear the per-phase cycle counters */

@@ -1241,23 +1241,24 @@ __device__ __forceinline__ int pgs_sweeps(const ModelS& M, const float* AR, int 
   return iter;
 }
 
-// nefc <= RF (all but a handful of the benchmark's stage evaluations): this lane's column of AR (= its row, AR is
+// nefc <= NR (NR = RF = 24 in the tile path, 32 for big stages): this lane's column of AR (= its row, AR is
 // symmetric) is held in RF registers, loaded once per solve; a sweep is then a fully unrolled chain of
 // row updates with no shared-memory access and no index arithmetic.  Rows are kept scaled by -1/AR_ii
 // (sres = -res / AR_ii, scaled column acol * -1/AR_ii), so the increment is max(-f, sres) and the serial chain per
 // row is FMNMX -> SHFL -> FFMA.  The column is fetched in chunks of 8 rows behind a uniform branch (most envs have
 // fewer than 8 rows); lanes without a row keep a zero column.
+template <int NR>
 __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, const float* AR, int lane, int nefc, float& f0, float& res0) {
-  static_assert(RF % 8 == 0 && RF <= 32, "column chunks of 8 rows");
+  static_assert(NR % 8 == 0 && NR <= 32, "column chunks of 8 rows");
   const int r0 = lane, t0 = tri(r0);
   const bool a0 = r0 < nefc;
   const float d0 = a0 ? AR[t0 + r0] : 1.f;
   const float ninv0 = -rcp(d0);
-  float acol[RF];
+  float acol[NR];
 #pragma unroll
-  for (int i = 0; i < RF; i++) acol[i] = 0.f;
+  for (int i = 0; i < NR; i++) acol[i] = 0.f;
 #pragma unroll
-  for (int c = 0; c < RF / 8; c++) {
+  for (int c = 0; c < NR / 8; c++) {
     if (8 * c < nefc) {
 #pragma unroll
       for (int j = 0; j < 8; j++) {
@@ -1273,7 +1274,7 @@ __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, const float* AR, 
     // AR symmetric): exact like the per-row sum MuJoCo accumulates, without any per-row bookkeeping.
     const float fs = f0, ss = sres;
 #pragma unroll
-    for (int i = 0; i < RF; i += 2) {
+    for (int i = 0; i < NR; i += 2) {
       if (i >= nefc) break;   // rows are taken in pairs; a row past nefc has no owner and a zero column
       {
         const float mine = fmaxf(-f0, sres);
@@ -1332,9 +1333,10 @@ __device__ DMB_PHASE_FN void solve_constraints(const ModelS& M, EnvS& S, int lan
     cost = warp_sum(cost);
     if (cost > 0.f) { f0 = 0.f; f1 = 0.f; res0 = b0; res1 = b1; }
     DMB_TICK(14);
+    // up to 32 rows: one row per lane, its column of AR in registers; more: a second row on lanes 0..7, AR in the tile
     if (OVF) iter = nefc > 32 ? pgs_sweeps<true>(M, V.AR, lane, nefc, f0, f1, res0, res1)
-                              : pgs_sweeps<false>(M, V.AR, lane, nefc, f0, f1, res0, res1);
-    else iter = pgs_sweeps_reg(M, V.AR, lane, nefc, f0, res0);
+                              : pgs_sweeps_reg<32>(M, V.AR, lane, nefc, f0, res0);
+    else iter = pgs_sweeps_reg<RF>(M, V.AR, lane, nefc, f0, res0);
     DMB_TICK(15);
     __syncwarp();
     if (a0) V.e_f[r0] = f0;
@@ -1472,6 +1474,7 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
     const int W = bar_n >> 5;
     if (!active && lane == 0) { S.nefc = 0; S.nlimit = 0; S.ncon = 0; }
     group_barrier(bar_id, bar_n);                                   // A: the rows of every tile are assembled
+    DMB_TICK(18);
     {
       int ng = 0, nl = 0;
       if (lane < W) { nl = tiles[lane].nlimit; ng = tiles[lane].nefc > 0 ? nl + tiles[lane].ncon : 0; }
@@ -1491,7 +1494,9 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
         else half_solve_rows<false>(M, T, lane, row, row + 1, nullptr);
       }
     }
+    DMB_TICK(19);
     group_barrier(bar_id, bar_n);                                   // B: every Y row is half-solved
+    DMB_TICK(20);
     if ((warp | lane) == 0) share_cnt[0] = 0;
     {
       int nt = 0, ne = 0;
@@ -1510,6 +1515,7 @@ __device__ DMB_PHASE_FN float forward_eval(const ModelS& M, EnvS& S, int lane, f
         else gram<false>(M, tiles[w], lane, new_, 32 * c, 32 * c + 32, nullptr);
       }
     }
+    DMB_TICK(21);
     group_barrier(bar_id, bar_n);                                   // C: every AR / b entry is in place
     if ((warp | lane) == 0) share_cnt[1] = 0;
   } else

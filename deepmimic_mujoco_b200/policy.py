@@ -64,6 +64,10 @@ class MlpPolicy:
         if not torch.cuda.is_available():
             raise _lib.DmbError("MlpPolicy.act runs on the GPU only")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if obs_dim > 64 or hid > 128 or act_dim > 32:
+            raise ValueError(f"MlpPolicy: the fused inference kernel (include/dmb_policy.h) keeps both networks' weights in "
+                             f"shared memory and supports obs_dim <= 64, hid <= 128, act_dim <= 32; got obs_dim={obs_dim}, "
+                             f"hid={hid}, act_dim={act_dim} (the 197-d DeepMimic state of obs_mode=1 does not fit)")
         self.obs_dim, self.act_dim, self.hid = obs_dim, act_dim, hid
         g = torch.Generator(device=self.device); g.manual_seed(seed)
         z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)

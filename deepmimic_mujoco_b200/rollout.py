@@ -49,7 +49,12 @@ class SegmentGenerator:
         return self
 
     def __next__(self) -> Dict[str, torch.Tensor]:
-        ep_rets, ep_lens = [], []
+        # finished-episode records are kept per step on the device and compacted once per segment: a boolean-mask
+        # gather inside the loop would force a host sync every env step
+        N, d = self.env.num_envs, self.ob.device
+        done_hist = torch.empty(self.T, N, dtype=torch.bool, device=d)
+        ret_hist = torch.empty(self.T, N, device=d)
+        len_hist = torch.empty(self.T, N, dtype=torch.int32, device=d)
         for t in range(self.T):
             self.ob[t].copy_(self.cur_ob)
             self.new[t].copy_(self.cur_new)
@@ -57,13 +62,13 @@ class SegmentGenerator:
             obs, rew, done, info = self.env.step(self.ac[t])
             self.rew[t].copy_(rew)
             self.cur_ob.copy_(obs)
-            self.cur_new.copy_(done.float())
-            d = done.bool()
-            ep_rets.append(info["episode_return"][d].clone())
-            ep_lens.append(info["episode_length"][d].clone())
-        nextvpred = torch.empty(self.env.num_envs, device=self.ob.device)
-        tmp_ac = torch.empty(self.env.num_envs, self.env.sim.nu, device=self.ob.device)
+            self.cur_new.copy_(done)
+            done_hist[t].copy_(done)
+            ret_hist[t].copy_(info["episode_return"])
+            len_hist[t].copy_(info["episode_length"])
+        nextvpred = torch.empty(N, device=d)
+        tmp_ac = torch.empty(N, self.env.sim.nu, device=d)
         self.pi.act(self.stochastic, self.cur_ob, out_ac=tmp_ac, out_vpred=nextvpred)
         nextvpred = nextvpred * (1.0 - self.cur_new)   # trpo.py:56
         return {"ob": self.ob, "ac": self.ac, "rew": self.rew, "vpred": self.vpred, "new": self.new,
-                "nextvpred": nextvpred, "ep_rets": torch.cat(ep_rets), "ep_lens": torch.cat(ep_lens)}
+                "nextvpred": nextvpred, "ep_rets": ret_hist[done_hist], "ep_lens": len_hist[done_hist]}

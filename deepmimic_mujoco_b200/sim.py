@@ -129,6 +129,10 @@ class BatchedSim:
         self.L.dmb_launch_info(self.handle, C.byref(g), C.byref(b), C.byref(s), C.byref(w))
         return dict(grid=g.value, block=b.value, smem_bytes=s.value, envs_per_cta=w.value)
 
+    def kernel_launches(self) -> int:
+        """Kernels launched by ``step`` so far (the scheduler sort + the fused step kernel)."""
+        return int(self.L.dmb_kernel_launches(self.handle))
+
     # ------------------------------------------------------------------------------------
     def reset(self, mask: Optional[torch.Tensor] = None, mode: int = -1) -> torch.Tensor:
         """(Re)initialise envs (all, or where mask != 0); returns the observation tensor [N,56]."""

@@ -81,19 +81,21 @@ def flat_grad(y: torch.Tensor, xs: List[torch.Tensor], create_graph: bool = Fals
 
 def cg(f_Ax: Callable[[torch.Tensor], torch.Tensor], b: torch.Tensor, cg_iters: int = 10,
        residual_tol: float = 1e-10) -> torch.Tensor:
-    """Conjugate gradient, cg.py:2-34 (Demmel p. 312)."""
+    """Conjugate gradient, cg.py:2-34 (Demmel p. 312).  The early exit of cg.py:31-32 (``rdotr < residual_tol``)
+    is applied as a device-side mask instead of a Python ``break``: once the residual is below the tolerance the
+    iterate stops changing, and no iteration waits for a device-to-host copy of ``rdotr``."""
     p, r, x = b.clone(), b.clone(), torch.zeros_like(b)
     rdotr = r.dot(r)
+    live = (rdotr >= residual_tol).to(b.dtype)
     for _ in range(cg_iters):
         z = f_Ax(p)
-        v = rdotr / p.dot(z)
+        v = live * rdotr / torch.where(live > 0, p.dot(z), torch.ones_like(rdotr))
         x += v * p
         r -= v * z
         newrdotr = r.dot(r)
-        p = r + (newrdotr / rdotr) * p
+        p = torch.where(live > 0, r + (newrdotr / torch.where(live > 0, rdotr, torch.ones_like(rdotr))) * p, p)
         rdotr = newrdotr
-        if float(rdotr) < residual_tol:
-            break
+        live = live * (rdotr >= residual_tol).to(b.dtype)
     return x
 
 

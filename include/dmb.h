@@ -122,6 +122,9 @@ int32_t dmb_debug_stride(void);
  *        efc_pos efc_R efc_aref efc_b efc_force efc_AR_diag qacc z_com cvel */
 int32_t dmb_debug_offset(const char* name);
 
+/* kernels launched by dmb_step through this handle so far (bench.py reports the count of its timed region) */
+int64_t dmb_kernel_launches(dmb_handle_t h);
+
 /* launch geometry chosen at create time (for DESIGN.md / bench reporting) */
 int dmb_launch_info(dmb_handle_t h, int32_t* grid, int32_t* block, int32_t* smem_bytes, int32_t* envs_per_cta);
 

@@ -30,10 +30,12 @@ torch.cuda.synchronize()
 sim.L.dmb_phase_cycles(buf.ctypes.data_as(C.c_void_p))
 names = {1: "wait @stage barrier", 16: "kinematics", 2: "comPos", 11: "crb: composite inertias", 12: "crb: M entries",
          13: "factor: L'DL elimination", 3: "factor: scaling", 17: "smooth forces (RNE)", 4: "LT solve of qfrc_smooth",
-         5: "geom poses + collision", 6: "make_constraint", 7: "half solve", 8: "gram", 9: "wait @solve barrier",
+         5: "geom poses + collision", 6: "count rows + J rows + row scalars", 7: "half solve (unshared path)",
+         18: "wait @barrier A (rows assembled)", 19: "half-solve tasks (shared)", 20: "wait @barrier B", 21: "Gram tasks (shared)",
+         8: "wait @barrier C", 9: "wait @solve barrier",
          14: "solve: warmstart + residual", 15: "solve: PGS sweeps", 10: "solve: Y'f + L solve"}
 per = buf.astype(np.float64) / (T * E * 4)
-order = [1, 16, 2, 11, 12, 13, 3, 17, 4, 5, 6, 7, 8, 9, 14, 15, 10]
+order = [1, 16, 2, 11, 12, 13, 3, 17, 4, 5, 6, 7, 18, 19, 20, 21, 8, 9, 14, 15, 10]
 tot = sum(per[i] for i in order)
 print(f"cycles per stage and warp: {tot:9.0f}  ({tot*4/1.965e3:7.1f} us per env-step at 1.965 GHz)")
 for i in order:

@@ -35,7 +35,7 @@ for it in range(a.iters):
     st = learner.update(seg)
     steps += a.envs * a.horizon * world
     if rank == 0:
-        n = max(1, len(seg["ep_lens"]))
+        n = len(seg["ep_lens"])
         print(f"iter {it:3d} steps {steps:9d}  rew/step {seg['rew'].mean().item():.4f}  EpLenMean {seg['ep_lens'].float().mean().item() if n else 0:.1f} "
               f"EpRewMean {seg['ep_rets'].mean().item() if n else 0:.2f}  kl {st['meankl']:.4f} surr {st['surrgain']:.4f} "
               f"step {st['stepsize']:.3f} vferr {st['vferr']:.3f}  {steps/(time.time()-t0)/1e3:.0f}k steps/s", flush=True)
