@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--term-mode", type=int, default=0, help="1 = add the DeepMimic fall-contact termination rule")
     ap.add_argument("--sync-gather", action="store_true", help="all-gather on the compute stream (no overlap)")
+    ap.add_argument("--gather-depth", type=int, default=4, help="outstanding all-gathers (record buffers) in the overlapped form")
     ap.add_argument("--reward-mode", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
@@ -343,25 +344,27 @@ def run_ours(a):
     nclip = len(a.motions)
     clip_ids = mixed_clip_ids(first, first + E, nclip) if nclip > 1 else None   # clip = global env index % nclip
     env = DPVecEnv(E, motions=tuple(a.motions), device=dev, seed=a.seed, first_env_id=first, reward_mode=a.reward_mode,
-                   auto_reset=True, clip_ids=clip_ids, term_mode=a.term_mode)
+                   auto_reset=True, clip_ids=clip_ids, term_mode=a.term_mode, rec_depth=max(2, a.gather_depth))
     sim = env.sim
     env.reset()
-    gather = RecordGather(sim.rec, n_global) if world > 1 else None
+    D = max(2, a.gather_depth)
+    gather = RecordGather(sim.rec, n_global, depth=D) if world > 1 else None
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
     pool = torch.rand(16, E, sim.nu, device=dev, generator=g) - 0.5          # U(-0.5, 0.5) actions
     flush = None if a.no_flush else torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
     K, W = a.steps, max(a.warmup, 3)
 
     # One step = the fused env-step kernel + (N > 1) the NCCL all-gather of its [E, 58] record.  The gather of step
-    # t runs on a side stream and overlaps step t + 1 (double-buffered record): the compute stream joins it right
-    # after the kernel of step t + 1, so every gather lies inside some step's timed interval.
+    # t runs on a side stream and overlaps the following steps (D record buffers): the compute stream joins it right
+    # after the kernel of step t + D - 1, so every gather lies inside some step's timed interval (the last D - 1
+    # are drained and timed after the loop).
     def one_step(i):
         env.step(pool[i % 16])
         if gather is not None:
             if a.sync_gather:
                 gather(sim.rec)
             else:
-                if i > 0:
+                if i >= D - 1:
                     gather.wait()
                 gather.launch(sim.rec)
 
@@ -391,8 +394,8 @@ def run_ours(a):
             if a.sync_gather:
                 gather(sim.rec)
             else:
-                if i > 0:
-                    gather.wait()          # gather of step i-1, launched before this step's flush
+                if i >= D - 1:
+                    gather.wait()          # gather of step i-D+1, launched D-1 steps ago
                 gather.launch(sim.rec)
         ev1[i].record()
     if gather is not None:
@@ -481,7 +484,7 @@ def run_ours(a):
                            "parallelism": f"env-shard x{world}",
                            "collective": (f"nccl all_gather [N,{rec_w}] f32 per step, "
                                           + ("on the compute stream" if a.sync_gather else
-                                             "side stream, overlapped with the next step (double-buffered record)"))
+                                             f"side stream, overlapped with the following steps ({D} record buffers)"))
                                          if world > 1 else "none",
                            "l2": "no flush" if a.no_flush else "L2 flushed between timed steps (192 MiB memset, untimed)",
                            "launch": sim.launch_info()},

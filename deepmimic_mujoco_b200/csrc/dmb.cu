@@ -313,7 +313,7 @@ __device__ __forceinline__ void integrate_pos(const ModelS& M, EnvS& S, int lane
 // registers (dof d on lane d & 31).  forward_eval has a single call site (code size matters:
 // the kernel is instruction-fetch bound).  Returns the CoM height of the last stage evaluation.
 template <bool LOCKSTEP>
-__device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bool active, int bar_id, int bar_n, int* arrive,
+__device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bool active, int bar_id, int bar_n,
                                           EnvS* tiles, int* share_cnt, float* gcta, int warp, bool use_slot) {
   const float h = M.timestep;
   const int d0 = lane, d1 = lane + 32;
@@ -333,7 +333,7 @@ __device__ __forceinline__ float rk4_step(const ModelS& M, EnvS& S, int lane, bo
       if (active) integrate_pos(M, S, lane, h);
       __syncwarp();
     }
-    zc = forward_eval<LOCKSTEP>(M, S, lane, nullptr, active, bar_id, bar_n, arrive + st, tiles, share_cnt, gcta, warp, use_slot);
+    zc = forward_eval<LOCKSTEP>(M, S, lane, nullptr, active, bar_id, bar_n, tiles, share_cnt, gcta, warp, use_slot);
     const float bw = (st == 0 || st == 3) ? (1.f / 6.f) : (1.f / 3.f);
     if (a0) { sv0 += bw * S.qvel[d0]; sa0 += bw * S.qacc[d0]; }
     if (a1) { sv1 += bw * S.qvel[d1]; sa1 += bw * S.qacc[d1]; }
@@ -523,7 +523,6 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
   EnvS& S = tiles[warp];
   const int od = M.obs_dim;
   __shared__ int s_base[8];
-  __shared__ int s_arrive[4];
   __shared__ int s_diag[4];
   if (threadIdx.x < 4) s_diag[threadIdx.x] = 0;
   if (threadIdx.x == 0) s_slot_owner = -1;
@@ -556,14 +555,12 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
     int env = N;
     if (spread) {
       if (round > 0) break;
-      if (threadIdx.x < 4) s_arrive[threadIdx.x] = 0;
       if (threadIdx.x == 0) s_base[0] = 0;
       __syncthreads();
       const int idx = warp * (int)gridDim.x + (int)blockIdx.x;
       if (idx < N) env = P.order[idx];
     } else if (LOCKSTEP) {
       group_barrier(bar_id, bar_n);
-      if (threadIdx.x < 4) s_arrive[threadIdx.x] = 0;   // per-stage arrival counters (soft barrier)
       if (gw == 0 && lane == 0) s_base[grp] = atomicAdd(P.counter, gsz);
       group_barrier(bar_id, bar_n);
       const int idx = s_base[grp] + gw;
@@ -577,6 +574,7 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
     const bool have = env < N;
     if (LOCKSTEP) { if (s_base[grp] >= N) break; }
     else if (!have) break;
+    DMB_TICK(-1);
     bool bad = false;
     if (have) {
       load_state(M, S, st, env, lane);
@@ -584,10 +582,11 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
       if (!bad) set_ctrl(M, S, action, env, lane);
     }
     // work sharing happens inside a lockstep group: its tiles, its scratch slots, its two task counters
-    const float zc = rk4_step<LOCKSTEP>(M, S, lane, have && !bad, bar_id, bar_n, s_arrive, tiles + grp * gsz,
+    const float zc = rk4_step<LOCKSTEP>(M, S, lane, have && !bad, bar_id, bar_n, tiles + grp * gsz,
                                         LOCKSTEP ? s_share + 2 * grp : nullptr, gcta + (size_t)grp * gsz * gs::stride, gw,
                                         LOCKSTEP && M.ngroups == 1);
     if (!have) { round++; continue; }
+    DMB_TICK(22);
     if (!bad) bad = state_bad(M, S, lane);
     // reward (dp_env_v3.py:117 / 89-104).  Reference pose: phase_mode 0 = table row of the integer frame
     // counter; phase_mode 1 = interpolated at the post-step mocap time into S.x_q0 / S.x_dv (dead here)
@@ -675,6 +674,7 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
       }
       (void)k_ref;
     }
+    DMB_TICK(23);
     // frame counter: phase_mode 0 advances by one per step whenever a mocap reward is configured (also for a
     // non-finite state); phase_mode 1 reports the frame interval of the post-step reference time
     if (M.phase_mode == 1) {
@@ -721,6 +721,7 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
     emit_obs(M, S, clip, idx_init, idx_curr, ep_len, out.obs, out.rec, env, lane);
     store_state(M, S, st, env, lane);
     __syncwarp();
+    DMB_TICK(24);
     ++round;
     if (P.trace && (warp | lane) == 0 && round < 6) {
       long long t;
@@ -861,7 +862,7 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_forward_debug(DevPtrs P, 
     float* row = dbgout + (size_t)env * dbg::stride;
     for (int i = lane; i < dbg::stride; i += 32) row[i] = 0.f;
     __syncwarp();
-    const float zc = forward_eval<false>(M, S, lane, row, true, 0, 0, nullptr, nullptr, nullptr,
+    const float zc = forward_eval<false>(M, S, lane, row, true, 0, 0, nullptr, nullptr,
                                          P.gscratch + (size_t)blockIdx.x * W * gs::stride, warp, false);
     for (int i = lane; i < M.nv; i += 32) row[dbg::qacc + i] = S.qacc[i];
     if (lane == 0) {
@@ -1084,14 +1085,10 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
   if (c->ctrl_mode < 0 || c->ctrl_mode > 2) { why = "ctrl_mode must be 0, 1 or 2"; return DMB_ERR_ARG; }
   S.nclip = mc->nclip; S.nframe_total = mc->nframe_total;
   S.ngroups = 1;
-  S.arrive_k = 0;
   S.cost_mode = 0;
-  S.patience = 0;
   S.spread = 1;
   if (const char* sp = getenv("DMB_SPREAD")) S.spread = atoi(sp) != 0;
-  if (const char* pt = getenv("DMB_PATIENCE")) S.patience = atoi(pt);
   if (const char* cm = getenv("DMB_COST_MODE")) S.cost_mode = atoi(cm);
-  if (const char* ak = getenv("DMB_ARRIVE_K")) S.arrive_k = atoi(ak);
   S.sync_mask = 0x41;  // barriers at the start of every RK stage and before the constraint solve (sweep on B200)
   if (const char* sm = getenv("DMB_SYNC_MASK")) S.sync_mask = (int)strtol(sm, nullptr, 0);
   if (mc->nclip < 1 || mc->nclip > DMB_MAX_CLIP) { why = "need 1..16 motion clips"; return DMB_ERR_ARG; }

@@ -36,7 +36,7 @@ struct ModelS {
   int nq, nv, nu, nbody, njnt, ngeom, npair, nM;
   int iterations, max_con, max_efc, maxdepth;
   int nclip, nframe_total, nee, sync_mask;  // sync_mask: which lockstep phase barriers are active
-  int ngroups, arrive_k, cost_mode, patience;  // patience > 0: stage barrier gives up after that many cycles    // arrive_k > 0: stage barrier releases warps in arrival-order groups of k      // lockstep groups per CTA (each with its own named barrier)
+  int ngroups, cost_mode, pad_k0, pad_k1;   // ngroups: lockstep groups per CTA (each with its own named barrier)
   float timestep, tolerance, pgs_scale, margin;
   float gravity[3], inv_total_mass;
   float imp_k, imp_b;        // reference spring constants after refsafe (mj_makeImpedance)

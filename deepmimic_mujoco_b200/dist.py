@@ -35,12 +35,15 @@ class RecordGather:
     ``g(local)`` is the blocking form (gather on the current stream, used by the CPU/gloo tests and simple callers).
     ``launch(local)`` / ``wait()`` is the overlapped form used by the rollout loops: the collective runs on a side
     stream, gated by an event recorded after the step kernel, and writes the gathered record of step t into
-    ``out_buffers[t % 2]`` while the compute stream already runs step t + 1 (the env step never waits for the
-    slowest rank's previous kernel; SURVEY.md section 5 "Distributed communication backend").  ``wait()`` makes the
-    current stream wait for the oldest outstanding gather and returns its buffer.
+    ``out_buffers[t % depth]`` while the compute stream already runs the following steps (the env step never waits
+    for the slowest rank's previous kernel; SURVEY.md section 5 "Distributed communication backend").  ``wait()`` makes
+    the current stream wait for the oldest outstanding gather and returns its buffer.  ``depth`` outstanding gathers
+    let the ranks drift ``depth - 1`` steps apart: the step time of the heaviest env varies from step to step, and a
+    deeper pipeline averages that variation out instead of paying the slowest rank every step.  The caller keeps
+    the gathered tensors' source buffers alive for as long (``BatchedSim(rec_depth=...)``).
     """
 
-    def __init__(self, local_rec: torch.Tensor, num_envs_global: int, group=None):
+    def __init__(self, local_rec: torch.Tensor, num_envs_global: int, group=None, depth: int = 2):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -48,7 +51,8 @@ class RecordGather:
         width = local_rec.shape[1]
         self.equal = num_envs_global % self.world == 0
         kw = dict(dtype=local_rec.dtype, device=local_rec.device)
-        self.out_buffers = [torch.empty(num_envs_global, width, **kw) for _ in range(2)]
+        self.depth = max(2, int(depth))
+        self.out_buffers = [torch.empty(num_envs_global, width, **kw) for _ in range(self.depth)]
         self.out = self.out_buffers[0]
         if not self.equal:  # ragged shards: pad every rank to the largest shard, gather, then compact
             self.sizes = [shard_range(num_envs_global, self.world, r) for r in range(self.world)]
@@ -77,11 +81,11 @@ class RecordGather:
 
     def launch(self, local: torch.Tensor = None) -> None:
         """Start gathering ``local`` (default: the tensor given at construction) without blocking the current
-        stream.  At most two gathers may be outstanding (double buffer): call ``wait()`` before a third."""
+        stream.  At most ``depth`` gathers may be outstanding: call ``wait()`` before the next one."""
         local = self.local if local is None else local
-        if len(self._pending) >= 2:
-            raise RuntimeError("RecordGather: two gathers already outstanding; call wait() first")
-        out = self.out_buffers[self._t & 1]
+        if len(self._pending) >= self.depth:
+            raise RuntimeError(f"RecordGather: {self.depth} gathers already outstanding; call wait() first")
+        out = self.out_buffers[self._t % self.depth]
         self._t += 1
         if not self.cuda:
             self._gather(out, local)

@@ -70,7 +70,7 @@ class DPVecEnv:
     def __init__(self, num_envs: int, motions: Sequence[str] = ("walk",), device=None, seed: int = 0,
                  first_env_id: int = 0, reward_mode: int = 0, ctrl_mode: int = 0, reset_mode: int = 0,
                  auto_reset: bool = True, clip_ids: Optional[torch.Tensor] = None, phase_mode: int = 0,
-                 obs_mode: int = 0, **cfg_kw):
+                 obs_mode: int = 0, rec_depth: int = 4, **cfg_kw):
         """phase_mode 1: time-based mocap phase with lerp/slerp interpolation (instead of one frame per step);
         obs_mode 1: the 197-d DeepMimic state instead of qpos[7:] || qvel[6:]."""
         cfg = default_config(reward_mode=reward_mode, ctrl_mode=ctrl_mode, reset_mode=reset_mode,
@@ -80,7 +80,7 @@ class DPVecEnv:
             from .refaux import compute_ref_aux
             ref_aux = compute_ref_aux(motions)
         self.sim = BatchedSim(num_envs, motions=motions, device=device, seed=seed, first_env_id=first_env_id,
-                              config=cfg, clip_ids=clip_ids, ref_aux=ref_aux)
+                              config=cfg, clip_ids=clip_ids, ref_aux=ref_aux, rec_depth=rec_depth)
         self.num_envs = num_envs
         self.observation_space = _Box(-np.inf, np.inf, (self.sim.obs_dim,), np.float64)
         lo, hi = self.sim.tables.act_ctrlrange[:, 0], self.sim.tables.act_ctrlrange[:, 1]

@@ -57,7 +57,7 @@ class BatchedSim:
     def __init__(self, num_envs: int, motions: Sequence[str] = ("walk",), device: Optional[torch.device] = None,
                  seed: int = 0, first_env_id: int = 0, config: Optional[DmbConfig] = None,
                  model_tables: Optional[ModelTables] = None, clip_ids: Optional[torch.Tensor] = None,
-                 max_con: int = 16, max_efc: int = 40, ref_aux: Optional[np.ndarray] = None):
+                 max_con: int = 16, max_efc: int = 40, ref_aux: Optional[np.ndarray] = None, rec_depth: int = 4):
         if not torch.cuda.is_available():
             raise _lib.DmbError("BatchedSim needs a CUDA device: the hot path has no CPU fallback")
         self.L = _lib.load()
@@ -94,9 +94,9 @@ class BatchedSim:
         self.obs = torch.zeros(N, self.obs_dim, dtype=f32, device=d)
         self.reward = torch.zeros(N, dtype=f32, device=d)
         self.done = torch.zeros(N, dtype=torch.uint8, device=d)
-        # the packed (obs, reward, done) record is double-buffered: step t writes rec_buffers[t % 2], so that the
-        # all-gather of step t (dist.RecordGather, on its own stream) can overlap step t + 1
-        self.rec_buffers = [torch.zeros(N, self.obs_dim + 2, dtype=f32, device=d) for _ in range(2)]
+        # the packed (obs, reward, done) record is multi-buffered: step t writes rec_buffers[t % rec_depth], so that
+        # the all-gather of step t (dist.RecordGather, on its own stream) can overlap the following steps
+        self.rec_buffers = [torch.zeros(N, self.obs_dim + 2, dtype=f32, device=d) for _ in range(max(2, int(rec_depth)))]
         self.rec_index = 0
         self.rec = self.rec_buffers[0]    # the record of the latest step
         self.last_ret = torch.zeros(N, dtype=f32, device=d)
@@ -151,7 +151,7 @@ class BatchedSim:
         if action.device != self.device or action.dtype != torch.float32 or not action.is_contiguous() \
                 or tuple(action.shape) != (self.N, self.nu):
             raise ValueError("action must be a contiguous CUDA float32 tensor of shape [N, nu] on the sim's device")
-        self.rec_index ^= 1
+        self.rec_index = (self.rec_index + 1) % len(self.rec_buffers)
         self.rec = self.rec_buffers[self.rec_index]
         self._out.rec = self.rec.data_ptr()
         with torch.cuda.device(self.device):

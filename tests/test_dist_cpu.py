@@ -30,6 +30,10 @@ def _worker(rank, world, port, n_global, q):
     s, e = shard_range(n_global, world, rank)
     local = torch.arange(s, e, dtype=torch.float32)[:, None] * torch.ones(1, 58) + torch.arange(58) * 1e-3
     g = RecordGather(local, n_global)
+    g4 = RecordGather(local, n_global, depth=4)
+    for k in range(4):
+        g4.launch(local * (k + 1))
+    deep_ok = all(bool(torch.equal(g4.wait(), (torch.arange(n_global, dtype=torch.float32)[:, None] * torch.ones(1, 58) + torch.arange(58) * 1e-3) * (k + 1))) for k in range(4))
     out = g()
     expect = torch.arange(n_global, dtype=torch.float32)[:, None] * torch.ones(1, 58) + torch.arange(58) * 1e-3
     ok = bool(torch.equal(out, expect))
@@ -39,7 +43,7 @@ def _worker(rank, world, port, n_global, q):
         g.launch(local)
     a = g.wait().clone(); b = g.wait()
     ok = ok and bool(torch.equal(a, expect)) and bool(torch.equal(b, expect * 2)) and a.data_ptr() != b.data_ptr()
-    q.put((rank, ok))
+    q.put((rank, ok and deep_ok))
     dist.barrier()
     dist.destroy_process_group()
 

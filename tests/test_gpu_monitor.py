@@ -59,3 +59,23 @@ def test_sim_data_views_write_through():
     env.set_state(env.mocap.data_config[3], env.mocap.data_vel[3])       # dp_env_v3.py:196 idiom
     assert np.abs(env.sim.data.qpos - np.float32(env.mocap.data_config[3])).max() < 1e-6
     env.close()
+
+
+def test_bad_clip_ids_rejected_and_launch_counter():
+    """Caller-supplied clip ids are validated up front (a bad id would index the clip tables out of bounds), and the
+    library counts the kernels it launches (bench.py reports that count)."""
+    import torch
+    from deepmimic_mujoco_b200.sim import BatchedSim
+    with pytest.raises(ValueError):
+        BatchedSim(8, motions=("walk", "run"), clip_ids=torch.tensor([0, 1, 2, 0, 1, 0, 1, 0], dtype=torch.int32))
+    with pytest.raises(ValueError):
+        BatchedSim(8, motions=("walk",), clip_ids=torch.zeros(7, dtype=torch.int32))
+    sim = BatchedSim(64, motions=("walk",), seed=0)
+    sim.reset()
+    n0 = sim.kernel_launches()
+    act = torch.zeros(64, 28, device=sim.device)
+    for _ in range(16):
+        sim.step(act)
+    n = sim.kernel_launches() - n0
+    assert 16 + 2 <= n <= 32          # 16 step kernels + the scheduler sort on every 8th step (every step at most)
+    sim.close()

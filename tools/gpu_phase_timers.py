@@ -33,10 +33,11 @@ names = {1: "wait @stage barrier", 16: "kinematics", 2: "comPos", 11: "crb: comp
          5: "geom poses + collision", 6: "count rows + J rows + row scalars", 7: "half solve (unshared path)",
          18: "wait @barrier A (rows assembled)", 19: "half-solve tasks (shared)", 20: "wait @barrier B", 21: "Gram tasks (shared)",
          8: "wait @barrier C", 9: "wait @solve barrier",
-         14: "solve: warmstart + residual", 15: "solve: PGS sweeps", 10: "solve: Y'f + L solve"}
+         14: "solve: warmstart + residual", 15: "solve: PGS sweeps", 10: "solve: Y'f + L solve",
+         25: "step prologue / RK4 update between stages", 22: "RK4 final update", 23: "reward (FK + features)", 24: "done / reset / obs / state store"}
 per = buf.astype(np.float64) / (T * E * 4)
-order = [1, 16, 2, 11, 12, 13, 3, 17, 4, 5, 6, 7, 18, 19, 20, 21, 8, 9, 14, 15, 10]
+order = [25, 1, 16, 2, 11, 12, 13, 3, 17, 4, 5, 6, 7, 18, 19, 20, 21, 8, 9, 14, 15, 10, 22, 23, 24]
 tot = sum(per[i] for i in order)
-print(f"cycles per stage and warp: {tot:9.0f}  ({tot*4/1.965e3:7.1f} us per env-step at 1.965 GHz)")
+print(f"cycles per stage and warp (step-level buckets 22-25 divided by 4): {tot:9.0f}  ({tot*4/1.965e3:7.1f} us per env-step at 1.965 GHz)")
 for i in order:
     print(f"  {names[i]:30s} {per[i]:9.0f}  {100*per[i]/tot:5.1f}%")
