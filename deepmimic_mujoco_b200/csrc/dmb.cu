@@ -557,7 +557,10 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
       if (round > 0) break;
       if (threadIdx.x == 0) s_base[0] = 0;
       __syncthreads();
-      const int idx = warp * (int)gridDim.x + (int)blockIdx.x;
+      // (spread 2 deals the rows of the sorted list alternately left-to-right and right-to-left: the CTA that gets
+      // the heaviest env of a row gets the lightest of the next one)
+      const int col = (M.spread == 2 && (warp & 1)) ? (int)gridDim.x - 1 - (int)blockIdx.x : (int)blockIdx.x;
+      const int idx = warp * (int)gridDim.x + col;
       if (idx < N) env = P.order[idx];
     } else if (LOCKSTEP) {
       group_barrier(bar_id, bar_n);
@@ -1087,7 +1090,7 @@ static int build_model(const dmb_model_t* m, const dmb_config_t* c, const dmb_mo
   S.ngroups = 1;
   S.cost_mode = 0;
   S.spread = 1;
-  if (const char* sp = getenv("DMB_SPREAD")) S.spread = atoi(sp) != 0;
+  if (const char* sp = getenv("DMB_SPREAD")) S.spread = atoi(sp);
   if (const char* cm = getenv("DMB_COST_MODE")) S.cost_mode = atoi(cm);
   S.sync_mask = 0x41;  // barriers at the start of every RK stage and before the constraint solve (sweep on B200)
   if (const char* sm = getenv("DMB_SYNC_MASK")) S.sync_mask = (int)strtol(sm, nullptr, 0);

@@ -1299,59 +1299,6 @@ __device__ __forceinline__ int pgs_sweeps_reg(const ModelS& M, const float* AR, 
   return iter;
 }
 
-// Stages with many rows (DMB_PAIR_MIN .. 32) are the ones the other warps of a lockstep CTA wait for, and their sweep
-// is a pure latency chain: FMNMX -> SHFL -> FFMA per row, the shuffle alone ~24 cycles.  Here a lane owns TWO
-// consecutive rows (2L, 2L+1): the second row sees the first one's increment through a local FFMA, both increments are
-// broadcast together, and the chain per PAIR is FMNMX -> FFMA -> FMNMX -> SHFL -> FFMA -> FFMA (~44 cycles instead of
-// 62).  The four AR entries a lane needs per pair step come from memory (packed triangle; issued at the top of the
-// step, off the chain); they cost ~2x the instructions per row of the register-column sweep, which is why light
-// stages keep that one.  Same Gauss-Seidel order, same per-row arithmetic, same stopping rule.
-#ifndef DMB_PAIR_MIN
-#define DMB_PAIR_MIN 17
-#endif
-__device__ __forceinline__ int pgs_sweeps_pair(const ModelS& M, const float* AR, int lane, int nefc, float& f0, float& res0) {
-  const int ra = 2 * lane, rb = 2 * lane + 1;
-  const bool aa = ra < nefc, ab = rb < nefc;
-  const int ta = tri(ra), tb = tri(rb);
-  const float da = aa ? AR[ta + ra] : 1.f, db = ab ? AR[tb + rb] : 1.f;
-  const float na = aa ? -rcp(da) : 0.f, nb = ab ? -rcp(db) : 0.f;   // rows without an owner: zero (scaled) columns
-  const float cab = ab ? AR[tb + ra] * nb : 0.f;                    // the second row's view of the first one's increment
-  // lane = row  ->  lane = pair
-  float fa = __shfl_sync(DMB_FULL, f0, ra & 31), fb = __shfl_sync(DMB_FULL, f0, rb & 31);
-  float sa = __shfl_sync(DMB_FULL, res0, ra & 31) * na, sb = __shfl_sync(DMB_FULL, res0, rb & 31) * nb;
-  if (!aa) fa = 0.f;
-  if (!ab) fb = 0.f;
-  const int npair = (nefc + 1) >> 1;
-  int iter = 0;
-  while (iter < M.iterations) {
-    const float fsa = fa, fsb = fb, ssa = sa, ssb = sb;
-    for (int P = 0; P < npair; P++) {
-      const int ja = 2 * P, jb = ja + 1, tja = tri(ja), tjb = tri(jb);
-      // entries (row, column) of the packed lower triangle: tri(max) + min; rows / columns past nefc read a valid
-      // word of the triangle and are multiplied by a zero scale
-      const int iaa = ja <= ra ? ta + ja : tja + ra, iab = jb <= ra ? ta + jb : tjb + ra;
-      const int iba = ja <= rb ? tb + ja : tja + rb, ibb = jb <= rb ? tb + jb : tjb + rb;
-      const float eaa = AR[aa ? iaa : 0] * na, eab = AR[(aa && jb < nefc) ? iab : 0] * na;
-      const float eba = AR[ab ? iba : 0] * nb, ebb = AR[(ab && jb < nefc) ? ibb : 0] * nb;
-      const float ma = fmaxf(-fa, sa);
-      const float mb = fmaxf(-fb, fmaf(cab, ma, sb));
-      const float dla = __shfl_sync(DMB_FULL, ma, P), dlb = __shfl_sync(DMB_FULL, mb, P);
-      if (lane == P) { fa += ma; fb += mb; }
-      sa = fmaf(eab, dlb, fmaf(eaa, dla, sa));
-      sb = fmaf(ebb, dlb, fmaf(eba, dla, sb));
-    }
-    iter++;
-    const float imp = warp_sum(0.5f * (da * (fa - fsa) * (sa + ssa) + db * (fb - fsb) * (sb + ssb))) * M.pgs_scale;
-    if (imp < M.tolerance) break;
-  }
-  // lane = pair  ->  lane = row
-  const float ra_f = __shfl_sync(DMB_FULL, fa, lane >> 1), rb_f = __shfl_sync(DMB_FULL, fb, lane >> 1);
-  const float ra_r = __shfl_sync(DMB_FULL, -sa * da, lane >> 1), rb_r = __shfl_sync(DMB_FULL, -sb * db, lane >> 1);
-  f0 = (lane & 1) ? rb_f : ra_f;
-  res0 = (lane & 1) ? rb_r : ra_r;
-  return iter;
-}
-
 // ------------------------------------------------------------------------------------------
 // mj_fwdConstraint: warmstart + PGS on the dual, then qacc = L^-1 D^-1/2 (y_s + Y' f).
 // S.qacc holds qacc_warmstart on entry and the new acceleration on exit.
@@ -1388,12 +1335,13 @@ __device__ DMB_PHASE_FN void solve_constraints(const ModelS& M, EnvS& S, int lan
     cost = warp_sum(cost);
     if (cost > 0.f) { f0 = 0.f; f1 = 0.f; res0 = b0; res1 = b1; }
     DMB_TICK(14);
-    // light stages: one row per lane, its column of AR in registers; DMB_PAIR_MIN .. 32 rows: two rows per lane;
-    // more than 32: one row per lane plus a second row on lanes 0..7, AR read from the tile
+    // up to 32 rows: one row per lane, its column of AR in registers; more: a second row on lanes 0..7, AR in the tile.
+    // (Tried: two consecutive rows per lane with a local pair update and AR entries read per step -- one shuffle round
+    // trip per two rows.  The 4 x index arithmetic + loads per pair step made it 45 instructions per pair against 16,
+    // and a lone warp is issue-limited too: 7.63 M vs 8.47 M env-steps/s when used from 17 rows up.)
     if (OVF) iter = nefc > 32 ? pgs_sweeps<true>(M, V.AR, lane, nefc, f0, f1, res0, res1)
-                              : pgs_sweeps_pair(M, V.AR, lane, nefc, f0, res0);
-    else if (nefc >= DMB_PAIR_MIN) iter = pgs_sweeps_pair(M, V.AR, lane, nefc, f0, res0);
-    else iter = pgs_sweeps_reg<DMB_PAIR_MIN <= 9 ? 8 : (DMB_PAIR_MIN <= 17 ? 16 : RF)>(M, V.AR, lane, nefc, f0, res0);
+                              : pgs_sweeps_reg<32>(M, V.AR, lane, nefc, f0, res0);
+    else iter = pgs_sweeps_reg<RF>(M, V.AR, lane, nefc, f0, res0);
     DMB_TICK(15);
     __syncwarp();
     if (a0) V.e_f[r0] = f0;
