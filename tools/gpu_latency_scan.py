@@ -24,7 +24,7 @@ if len(sys.argv) > 1:
     ms = e0.elapsed_time(e1) / 100
     print(f"{k:2d} envs/CTA x {rounds} round(s)  N={E:5d}  {ms*1e3:7.1f} us/step  {E/ms/1e3:6.3f} M env-steps/s  launch {env.sim.launch_info()}")
 else:
-    for k in (1, 2, 4, 7, 10, 14):
+    for k in (1, 2, 4, 7, 14, 21, 28):
         subprocess.run([sys.executable, __file__, str(k)], env=dict(os.environ, DMB_ENVS_PER_CTA=str(k)))
     subprocess.run([sys.executable, __file__, "1"], env=dict(os.environ, DMB_ENVS_PER_CTA="1", DMB_LOCKSTEP="0"))
-    subprocess.run([sys.executable, __file__, "14"], env=dict(os.environ, DMB_ENVS_PER_CTA="14", DMB_LOCKSTEP="0"))
+    subprocess.run([sys.executable, __file__, "28"], env=dict(os.environ, DMB_ENVS_PER_CTA="28", DMB_LOCKSTEP="0"))
