@@ -156,3 +156,33 @@ extern "C" int dmb_policy_act(const dmb_policy_t* p, const float* obs, int32_t n
   k_policy_act<<<grid, Wp * 32, smem, (cudaStream_t)stream>>>(*p, obs, n, stochastic, seed, step, first_row, ac, vpred, mean_out);
   return cudaGetLastError() == cudaSuccess ? DMB_OK : DMB_ERR_CUDA;
 }
+
+// GAE(lambda) over a [T][n] segment, one thread per env walking its T steps backwards (trpo.py:83-94
+// add_vtarg_and_adv): nonterminal = 1 - new[t+1] (0 after the last step is handled by nextvpred being pre-masked),
+// delta = rew[t] + gamma * vpred[t+1] * nonterminal - vpred[t], adv[t] = delta + gamma * lam * nonterminal * adv[t+1].
+namespace dmb {
+__global__ void k_gae(const float* __restrict__ rew, const float* __restrict__ vpred, const float* __restrict__ isnew,
+                      const float* __restrict__ nextvpred, int T, int n, float gamma, float lam, float* adv, float* tdlamret) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float last = 0.f, nextv = nextvpred[e], nextnew = 0.f;
+  for (int t = T - 1; t >= 0; t--) {
+    const size_t k = (size_t)t * n + e;
+    const float nonterminal = 1.f - nextnew, v = vpred[k];
+    const float delta = rew[k] + gamma * nextv * nonterminal - v;
+    last = delta + gamma * lam * nonterminal * last;
+    adv[k] = last;
+    tdlamret[k] = last + v;
+    nextv = v;
+    nextnew = isnew[k];
+  }
+}
+}  // namespace dmb
+
+extern "C" int dmb_gae(const float* rew, const float* vpred, const float* isnew, const float* nextvpred, int32_t T, int32_t n,
+                       float gamma, float lam, float* adv, float* tdlamret, void* stream) {
+  if (!rew || !vpred || !isnew || !nextvpred || !adv || !tdlamret || T <= 0 || n <= 0) return DMB_ERR_ARG;
+  dmb::k_gae<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rew, vpred, isnew, nextvpred, T, n, gamma, lam, adv, tdlamret);
+  return cudaGetLastError() == cudaSuccess ? DMB_OK : DMB_ERR_CUDA;
+}
+

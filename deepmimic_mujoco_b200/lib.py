@@ -51,7 +51,7 @@ _lib: Optional[C.CDLL] = None
 
 EXPORTS = ("dmb_version", "dmb_sizeof_model", "dmb_sizeof_config", "dmb_sizeof_mocap", "dmb_sizeof_tile", "dmb_create", "dmb_destroy", "dmb_reset", "dmb_step", "dmb_get_obs", "dmb_forward_debug",
            "dmb_debug_stride", "dmb_debug_offset", "dmb_launch_info", "dmb_kernel_launches", "dmb_last_error", "dmb_obs_dim", "dmb_mocap_sample", "dmb_get_trace")
-POLICY_EXPORTS = ("dmb_policy_act",)   # include/dmb_policy.h
+POLICY_EXPORTS = ("dmb_policy_act", "dmb_gae")   # include/dmb_policy.h
 
 
 def load() -> C.CDLL:
@@ -88,6 +88,7 @@ def load() -> C.CDLL:
     L.dmb_debug_offset.restype = C.c_int32
     L.dmb_launch_info.argtypes = [hp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                   C.POINTER(C.c_int32)]
+    L.dmb_gae.argtypes = [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
     L.dmb_last_error.argtypes = [hp]
     L.dmb_last_error.restype = C.c_char_p
     _lib = L

@@ -15,9 +15,25 @@ from .policy import MlpPolicy
 
 
 def add_vtarg_and_adv(seg: Dict[str, torch.Tensor], gamma: float, lam: float) -> None:
-    """GAE(lambda) over [T, N] tensors; seg['new'][t] = 1 if step t starts a new episode (trpo.py:83-94)."""
+    """GAE(lambda) over [T, N] tensors; seg['new'][t] = 1 if step t starts a new episode (trpo.py:83-94).
+    CUDA segments go through one kernel (``dmb_gae``, one thread per env); CPU tensors (tests) use the loop."""
     rew, vpred, new = seg["rew"], seg["vpred"], seg["new"]
     T = rew.shape[0]
+    if rew.is_cuda:
+        import ctypes as C
+        from . import lib as _lib
+        L = _lib.load()
+        rew, vpred, new = rew.contiguous().float(), vpred.contiguous().float(), new.contiguous().float()
+        nextv = seg["nextvpred"].contiguous().float()
+        adv, ret = torch.empty_like(rew), torch.empty_like(rew)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        with torch.cuda.device(rew.device):
+            rc = L.dmb_gae(p(rew), p(vpred), p(new), p(nextv), T, rew.shape[1], float(gamma), float(lam), p(adv), p(ret),
+                           C.c_void_p(torch.cuda.current_stream(rew.device).cuda_stream))
+        if rc != 0:
+            raise _lib.DmbError(f"dmb_gae failed ({rc})")
+        seg["adv"], seg["tdlamret"] = adv, ret
+        return
     nextv = torch.cat([vpred[1:], seg["nextvpred"][None]], dim=0)
     nextnew = torch.cat([new[1:], torch.zeros_like(new[:1])], dim=0)
     adv = torch.empty_like(rew)

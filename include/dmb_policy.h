@@ -33,6 +33,12 @@ typedef struct dmb_policy {
 int dmb_policy_act(const dmb_policy_t* p, const float* obs, int32_t n, int32_t stochastic, uint64_t seed,
                    uint32_t step, uint32_t first_row, float* ac, float* vpred, float* mean_out, void* stream);
 
+/* GAE(lambda) over a [T][n] rollout segment on the device (replaces the numpy loop of trpo.py:83-94
+ * add_vtarg_and_adv): rew, vpred, isnew are [T][n] fp32 (isnew[t] = 1 when step t starts a new episode), nextvpred [n]
+ * is the bootstrap value already masked by (1 - new after the last step); writes adv and tdlamret = adv + vpred. */
+int dmb_gae(const float* rew, const float* vpred, const float* isnew, const float* nextvpred, int32_t T, int32_t n,
+            float gamma, float lam, float* adv, float* tdlamret, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ def test_library_exports_header_symbols():
         assert hasattr(L, name), name
     assert L.dmb_version() == 2
     phdr = open(os.path.join(common.ROOT, "include", "dmb_policy.h")).read()
-    assert set(re.findall(r"\b(dmb_policy_[a-z_0-9]+)\s*\(", phdr)) == set(lib.POLICY_EXPORTS)
+    assert set(re.findall(r"\b(dmb_(?:policy_[a-z_0-9]+|gae))\s*\(", phdr)) == set(lib.POLICY_EXPORTS)
     for name in lib.POLICY_EXPORTS:
         assert hasattr(L, name), name
     assert L.dmb_debug_stride() > 0 and L.dmb_debug_offset(b"qacc") > 0 and L.dmb_debug_offset(b"nope") == -1

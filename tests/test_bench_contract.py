@@ -45,3 +45,29 @@ def test_stdout_carries_only_the_json_line():
     assert p.returncode == 0, p.stderr
     assert p.stdout.splitlines() == ['{"metric": "m", "value": 1.5}', "after"]
     assert "python chatter" in p.stderr and "child chatter" in p.stderr
+
+
+def test_config_flags_select_the_baseline_configurations(monkeypatch):
+    """--config 2..5 = BASELINE.json configs[1..4] (envs per GPU, clips, seed); --scaling strong keeps the global batch."""
+    sys.path.insert(0, common.ROOT)
+    import bench
+
+    def parse(argv, world=1):
+        monkeypatch.setattr(sys, "argv", ["bench.py"] + argv)
+        monkeypatch.setenv("WORLD_SIZE", str(world))
+        return bench.parse()
+
+    a = parse([])
+    assert (a.config, a.envs_per_gpu, a.motions, a.seed, a.scaling) == (2, 4096, ["walk"], 0, "weak")
+    a = parse(["--config", "3"])
+    assert (a.envs_per_gpu, a.motions, a.seed) == (16384, ["spinkick"], 1)
+    a = parse(["--config", "4", "--gpus", "8"], world=8)
+    assert (a.envs_per_gpu, a.envs_global, a.motions) == (8192, 65536, ["walk"])
+    a = parse(["--config", "4", "--scaling", "strong", "--envs-global", "65536"], world=2)
+    assert (a.envs_per_gpu, a.envs_global) == (32768, 65536)
+    a = parse(["--config", "5"], world=8)
+    assert (a.envs_per_gpu, a.envs_global, a.motions, a.seed) == (4096, 32768, ["walk", "dance_b", "spinkick"], 2)
+    a = parse(["--motions", "run,walk", "--envs-per-gpu", "128"])
+    assert a.motions == ["run", "walk"] and a.envs_per_gpu == 128 and a.envs_global == 128
+    with pytest.raises(SystemExit):
+        parse(["--scaling", "strong", "--envs-global", "100"], world=8)

@@ -46,11 +46,12 @@ def test_restated_monitor_matches_reference_golden(seed, tmp_path):
 @pytest.mark.skipif(not os.path.exists("/root/reference/src/bench/monitor.py"), reason="reference not on this box")
 def test_restated_monitor_matches_reference_class(tmp_path):
     install_gym_shim()
-    sys.path.insert(0, "/root/reference/src")
-    try:
-        from bench.monitor import Monitor
-    finally:
-        sys.path.remove("/root/reference/src")
+    # load the reference file under its own module name (this repo's bench.py may already be imported as `bench`)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("reference_bench_monitor", "/root/reference/src/bench/monitor.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    Monitor = mod.Monitor
     for seed in (5, 6):
         a, b = ScriptedEnv(seed), ScriptedEnv(seed)
         ref, mine = Monitor(a, str(tmp_path / f"ref{seed}")), MonitorContract(b, str(tmp_path / f"mine{seed}"))

@@ -99,6 +99,25 @@ def test_policy_kernel_matches_numpy():
 
 
 @pytest.mark.gpu
+def test_gae_kernel_matches_reference_formula():
+    """dmb_gae (one thread per env) vs the numpy restatement of trpo.py:83-94, and vs the CPU torch loop."""
+    from deepmimic_mujoco_b200.rollout import add_vtarg_and_adv
+    rng = np.random.default_rng(1)
+    T, N = 33, 301
+    rew = rng.normal(size=(T, N)).astype(np.float32); vp = rng.normal(size=(T, N)).astype(np.float32)
+    new = (rng.uniform(size=(T, N)) < 0.15).astype(np.float32); nxt = rng.normal(size=N).astype(np.float32)
+    seg = {k: torch.tensor(v).cuda() for k, v in dict(rew=rew, vpred=vp, new=new, nextvpred=nxt).items()}
+    add_vtarg_and_adv(seg, 0.995, 0.97)
+    cpu = dict(rew=torch.tensor(rew), vpred=torch.tensor(vp), new=torch.tensor(new), nextvpred=torch.tensor(nxt))
+    add_vtarg_and_adv(cpu, 0.995, 0.97)
+    assert (seg["adv"].cpu() - cpu["adv"]).abs().max() < 1e-5 and (seg["tdlamret"].cpu() - cpu["tdlamret"]).abs().max() < 1e-5
+    for i in (0, 7, 300):
+        adv, ret = gae_reference(rew[:, i], vp[:, i], new[:, i], nxt[i], 0.995, 0.97)
+        assert np.abs(seg["adv"][:, i].cpu().numpy() - adv).max() < 1e-5
+        assert np.abs(seg["tdlamret"][:, i].cpu().numpy() - ret).max() < 1e-5
+
+
+@pytest.mark.gpu
 def test_segment_generator_shapes_and_bookkeeping():
     from deepmimic_mujoco_b200.env import DPVecEnv
     from deepmimic_mujoco_b200.policy import MlpPolicy
