@@ -3,13 +3,15 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
 //
 // Kernel design (DESIGN.md has the full account):
-//   * one warp per env, W envs per CTA, persistent grid (<= #SMs CTAs); CTAs pull W envs at a
-//     time from a queue sorted by last step's constraint work (k_order) and walk the RK stages in
-//     lockstep (one instruction stream per SM);
-//   * the fp32 model tables are staged once per CTA in shared memory; each warp owns an
-//     EnvS tile (qpos/qvel, kinematic tree, sparse inertia factor, contact list, the
-//     half-solved constraint Jacobian Y and the packed Delassus matrix AR) -- per-env state
-//     crosses HBM exactly once per step in each direction (coalesced env-major rows);
+//   * one warp per env, W = 28 envs per CTA (896 threads, 72 registers), persistent grid (<= #SMs CTAs): 148 x 28
+//     warps hold a 4096-env batch at once.  With more envs than resident warps CTAs pull W envs at a time from a
+//     queue sorted by last step's constraint work (k_order); with one round the sorted list is dealt round robin.
+//     All warps of a CTA walk the RK stages in lockstep (one instruction stream per SM);
+//   * the fp32 model tables are staged once per CTA in shared memory (one TMA bulk copy); each warp owns a 7.8 KB
+//     EnvS tile whose overlay is time-shared by the phases of a forward evaluation (kinematics / inertia / RNE
+//     temporaries, then geom poses + contact geometry, then the half-solved constraint Jacobian Y and the packed
+//     Delassus matrix AR) -- per-env state crosses HBM exactly once per step in each direction (one 128-bit
+//     load / store per lane for the three state rows);
 //   * the whole RK4 step (4 forward evaluations incl. collision and PGS), mocap lookup /
 //     interpolation, reward, termination, auto-reset and the observation (56-d or the 197-d
 //     DeepMimic state) are fused in this one kernel.

@@ -1374,7 +1374,7 @@ __device__ DMB_PHASE_FN void solve_constraints(const ModelS& M, EnvS& S, int lan
 }
 
 // ------------------------------------------------------------------------------------------
-// One full forward evaluation (mj_forward) at (S.qpos, S.qvel, S.ctrlf, S.warm) -> S.qacc.
+// One full forward evaluation (mj_forward) at (S.qpos, S.qvel, S.ctrlf; S.qacc = qacc_warmstart) -> S.qacc.
 // Returns the whole-body CoM height of this evaluation (what DPEnv.is_done reads from the
 // stale mjData.xipos after mj_step, dp_env_v3.py:134-139).
 // ------------------------------------------------------------------------------------------
