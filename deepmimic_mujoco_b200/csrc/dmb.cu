@@ -1,6 +1,6 @@
 // dmb.cu -- kernels + C-ABI of libdmb200.so (see include/dmb.h).
 //
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC -prec-div=false -prec-sqrt=false
 //
 // Kernel design (DESIGN.md has the full account):
 //   * one warp per env, W = 28 envs per CTA (896 threads, 72 registers), persistent grid (<= #SMs CTAs): 148 x 28
@@ -490,7 +490,7 @@ __device__ __forceinline__ void stage_model(ModelS* dst, const ModelS* src) {
   const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_mbar);
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
   constexpr unsigned bytes = (unsigned)sizeof(ModelS);
-  if (threadIdx.x == 0) {
+  if ((threadIdx.x | threadIdx.y) == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -521,17 +521,20 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
   // (pinning warp / lane in registers with an opaque asm removes the S2R + shift + multiply-add re-derivations of the
   // tile address -- 13 % of the instructions under the 72-register cap -- but costs 110 bytes of extra spills:
   // measured 7.03 M vs 7.21 M env-steps/s without the pin)
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  // tile kernels run 2-D blocks (32, W): lane and warp come straight from %tid.x / %tid.y (under the 72-register cap
+  // the compiler re-derives them and the tile address all over the kernel; this saves the shift and the mask, +1.2 %)
+  const int warp = threadIdx.y, lane = threadIdx.x, W = blockDim.y;
   EnvS& S = tiles[warp];
   const int od = M.obs_dim;
   __shared__ int s_base[8];
   __shared__ int s_diag[4];
-  if (threadIdx.x < 4) s_diag[threadIdx.x] = 0;
-  if (threadIdx.x == 0) s_slot_owner = -1;
+  const int tid = threadIdx.y * 32 + threadIdx.x;
+  if (tid < 4) s_diag[tid] = 0;
+  if (tid == 0) s_slot_owner = -1;
   // (one shared slot per CTA lies behind the tiles: Y of a stage with more than RF rows, see count_rows)
 #if DMB_SHARE
   __shared__ int s_share[16];   // task counters of the work sharing (two per lockstep group)
-  if (threadIdx.x < 16) s_share[threadIdx.x] = 0;
+  if (tid < 16) s_share[tid] = 0;
 #else
   int* const s_share = nullptr;
 #endif
@@ -545,7 +548,7 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
   // than the others.  Otherwise CTAs pull W consecutive entries at a time, heaviest first.
   const bool spread = LOCKSTEP && M.spread && N <= (int)gridDim.x * W;
   int round = 0;
-  if (P.trace && threadIdx.x == 0) {
+  if (P.trace && tid == 0) {
     long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     P.trace[blockIdx.x * 8] = t;
@@ -557,7 +560,7 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
     int env = N;
     if (spread) {
       if (round > 0) break;
-      if (threadIdx.x == 0) s_base[0] = 0;
+      if (tid == 0) s_base[0] = 0;
       __syncthreads();
       // (spread 2 deals the rows of the sorted list alternately left-to-right and right-to-left: the CTA that gets
       // the heaviest env of a row gets the lightest of the next one)
@@ -741,7 +744,7 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
   }
   if (P.trace) {   // slot 6: the CTA's last warp is done; slot 7: diagnostics (sweeps | rows << 16 | scratch envs << 24)
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
       long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       P.trace[blockIdx.x * 8 + 6] = t;
@@ -779,7 +782,7 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_reset(DevPtrs P, dmb_stat
   ModelS& M = *reinterpret_cast<ModelS*>(smem);
   EnvS* tiles = reinterpret_cast<EnvS*>(smem + MODEL_BYTES);
   stage_model(&M, P.model);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  const int warp = threadIdx.y, lane = threadIdx.x, W = blockDim.y;
   EnvS& S = tiles[warp];
   for (int env = blockIdx.x * W + warp; env < N; env += gridDim.x * W) {
     if (mask && !mask[env]) continue;
@@ -808,7 +811,7 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_obs_dm(DevPtrs P, dmb_sta
   ModelS& M = *reinterpret_cast<ModelS*>(smem);
   EnvS* tiles = reinterpret_cast<EnvS*>(smem + MODEL_BYTES);
   stage_model(&M, P.model);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  const int warp = threadIdx.y, lane = threadIdx.x, W = blockDim.y;
   EnvS& S = tiles[warp];
   for (int env = blockIdx.x * W + warp; env < N; env += gridDim.x * W) {
     load_state(M, S, st, env, lane);
@@ -850,7 +853,7 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_forward_debug(DevPtrs P, 
   ModelS& M = *reinterpret_cast<ModelS*>(smem);
   EnvS* tiles = reinterpret_cast<EnvS*>(smem + MODEL_BYTES);
   stage_model(&M, P.model);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
+  const int warp = threadIdx.y, lane = threadIdx.x, W = blockDim.y;
   EnvS& S = tiles[warp];
   for (int env = blockIdx.x * W + warp; env < N; env += gridDim.x * W) {
     load_state(M, S, st, env, lane);
@@ -1258,7 +1261,7 @@ int dmb_reset(dmb_handle_t h, const dmb_state_t* st, const uint8_t* mask, int32_
   if (!h) return DMB_ERR_ARG;
   if (!state_ok(st) || mode < -1 || mode > 1) return fail(h, DMB_ERR_ARG, "dmb_reset: bad argument");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  k_reset<<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, mask, mode, obs, h->num_envs, h->seed, h->first_env_id);
+  k_reset<<<h->grid, dim3(32, h->envs_per_cta), h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, mask, mode, obs, h->num_envs, h->seed, h->first_env_id);
   CUDA_TRY(h, cudaGetLastError());
   return DMB_OK;
 }
@@ -1277,8 +1280,8 @@ int dmb_step(dmb_handle_t h, const dmb_state_t* st, const float* action, const d
   }
   h->nstep++;
   h->nlaunch++;
-  if (h->lockstep) k_step<true><<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
-  else k_step<false><<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
+  if (h->lockstep) k_step<true><<<h->grid, dim3(32, h->envs_per_cta), h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
+  else k_step<false><<<h->grid, dim3(32, h->envs_per_cta), h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
   CUDA_TRY(h, cudaGetLastError());
   return DMB_OK;
 }
@@ -1288,7 +1291,7 @@ int dmb_get_obs(dmb_handle_t h, const dmb_state_t* st, float* obs, void* stream)
   if (!state_ok(st) || !obs) return fail(h, DMB_ERR_ARG, "dmb_get_obs: bad argument");
   CUDA_TRY(h, cudaSetDevice(h->device));
   if (h->hmodel.obs_mode == 1) {
-    k_obs_dm<<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, obs, h->num_envs);
+    k_obs_dm<<<h->grid, dim3(32, h->envs_per_cta), h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, obs, h->num_envs);
   } else {
     const size_t total = (size_t)h->num_envs * h->obs_dim;
     int blocks = (int)((total + 255) / 256);
@@ -1303,7 +1306,7 @@ int dmb_forward_debug(dmb_handle_t h, const dmb_state_t* st, const float* ctrl, 
   if (!h) return DMB_ERR_ARG;
   if (!state_ok(st) || !ctrl || !dbgout) return fail(h, DMB_ERR_ARG, "dmb_forward_debug: bad argument");
   CUDA_TRY(h, cudaSetDevice(h->device));
-  k_forward_debug<<<h->grid, h->block, h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, ctrl, dbgout, h->num_envs);
+  k_forward_debug<<<h->grid, dim3(32, h->envs_per_cta), h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, ctrl, dbgout, h->num_envs);
   CUDA_TRY(h, cudaGetLastError());
   return DMB_OK;
 }

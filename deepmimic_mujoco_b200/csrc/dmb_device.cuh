@@ -46,7 +46,7 @@ __device__ __forceinline__ void dmb_tick(int i, int lane) {
   __shared__ long long s_tick[32];
   if (lane == 0) {
     const long long t = clock64();
-    const int w = threadIdx.x >> 5;
+    const int w = threadIdx.y;
     // i < 0: start the clock (kernel entry); i == 0 (start of a forward evaluation) is booked on bucket 25: the step
     // prologue (state load, ctrl) before the first stage, the RK4 update + integratePos between stages
     if (i >= 0) atomicAdd(&g_phase_cycles[i == 0 ? 25 : i], (unsigned long long)(t - s_tick[w]));

@@ -16,8 +16,11 @@ CSRC = os.path.join(_PKG, "csrc")
 QSTRIDE = 36
 VSTRIDE = 36
 
+# -prec-div=false / -prec-sqrt=false: 2-ulp MUFU-based division and square root instead of the IEEE sequences (15
+# instructions + a slow path per division): 7 % less code, +2.3 % env-steps/s, no measurable change of the
+# kernel-vs-oracle errors (profiles/r2_c19_*); the kernel is fp32 against a float64 reference either way
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+              "-Xcompiler", "-fPIC", "-prec-div=false", "-prec-sqrt=false"]
 
 
 class DmbState(C.Structure):
