@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--term-mode", type=int, default=0, help="1 = add the DeepMimic fall-contact termination rule")
     ap.add_argument("--sync-gather", action="store_true", help="all-gather on the compute stream (no overlap)")
+    ap.add_argument("--nccl-ctas", type=int, default=1, help="CTAs of the all-gather kernel (0 = NCCL default)")
     ap.add_argument("--gather-depth", type=int, default=4, help="outstanding all-gathers (record buffers) in the overlapped form")
     ap.add_argument("--reward-mode", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -337,7 +338,23 @@ def run_ours(a):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # The step kernel is one persistent CTA per SM that owns the SM's whole shared memory, so a collective kernel
+        # cannot share an SM with it: the all-gather gets ONE CTA (NCCL max_ctas; 8 MB over NVLink per step needs no
+        # more) and the step kernel leaves one SM free for it (DMB_RESERVE_SMS, read by dmb_create).  Without this the
+        # gather's CTAs sit in front of the next step's CTAs on a few SMs and delay them (8 GPUs: 0.474 vs 0.445 ms).
+        os.environ.setdefault("DMB_RESERVE_SMS", "1")
+        opts = None
+        if a.nccl_ctas > 0:
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.config.min_ctas = 1
+                opts.config.max_ctas = a.nccl_ctas
+            except Exception:
+                opts = None
+        if opts is not None:
+            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+        else:
+            dist.init_process_group("nccl", device_id=dev)
     E = a.envs_per_gpu
     n_global = E * world
     first = rank * E
@@ -456,10 +473,17 @@ def run_ours(a):
             e1.close()
         except Exception as ex:   # diagnostics only
             gym_sps = f"failed: {ex}"
+    spread = None
     if world > 1:
+        tmin = torch.tensor([t_dev, t_kernel], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         tt = torch.tensor([t_dev, t_kernel, t_e2e], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_dev, t_kernel, t_e2e = [float(x) for x in tt.tolist()]
+        # how much of the multi-GPU step time is rank-to-rank variation of the kernel itself (different envs on
+        # every rank: the slowest env of the slowest rank sets the pace) and how much is the collective
+        spread = {"kernel_ms_per_step_min_rank": 1e3 * float(tmin[1]) / K, "kernel_ms_per_step_max_rank": 1e3 * t_kernel / K,
+                  "step_ms_min_rank": 1e3 * float(tmin[0]) / K, "step_ms_max_rank": 1e3 * t_dev / K}
     if rank == 0:
         value = n_global * K / t_dev
         peak, peak_src = measured_peak_hbm()
@@ -484,7 +508,8 @@ def run_ours(a):
                            "parallelism": f"env-shard x{world}",
                            "collective": (f"nccl all_gather [N,{rec_w}] f32 per step, "
                                           + ("on the compute stream" if a.sync_gather else
-                                             f"side stream, overlapped with the following steps ({D} record buffers)"))
+                                             f"side stream, overlapped with the following steps ({D} record buffers, "
+                                             f"{a.nccl_ctas or 'default'} NCCL CTA(s), {os.environ.get('DMB_RESERVE_SMS', '0')} SM(s) left free)"))
                                          if world > 1 else "none",
                            "l2": "no flush" if a.no_flush else "L2 flushed between timed steps (192 MiB memset, untimed)",
                            "launch": sim.launch_info()},
@@ -497,6 +522,8 @@ def run_ours(a):
                 # (scheduler sort; every step with dynamic pulling, every 8th step when one round holds every env)
                 "gpu_launches": launches,
                 "clocks": clocks}
+        if spread is not None:
+            line["rank_spread"] = spread
         if world > 1:
             line["nvlink"] = {"gather_bytes_in_per_rank_per_step": (world - 1) * E * rec_w * 4,
                               "gather_bytes_out_per_rank_per_step": E * rec_w * 4}

@@ -1214,7 +1214,11 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
   h->envs_per_cta = W; h->block = 32 * W;
   h->smem = (int)(MODEL_BYTES + (size_t)W * sizeof(EnvS) + SLOT_BYTES);
   int need = (num_envs + W - 1) / W;
-  h->grid = need < prop.multiProcessorCount ? need : prop.multiProcessorCount;
+  int nsm = prop.multiProcessorCount;
+  // DMB_RESERVE_SMS=k leaves k SMs without a persistent CTA: a concurrent kernel of the caller (the NCCL all-gather of
+  // the previous step's record, on its own stream) cannot share an SM with a CTA that owns the SM's whole shared memory
+  if (const char* rs = getenv("DMB_RESERVE_SMS")) { const int k = atoi(rs); if (k > 0 && k < nsm) nsm -= k; }
+  h->grid = need < nsm ? need : nsm;
   for (auto fn : tile_kernels) {
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, h->smem);
     if (e != cudaSuccess) { dmb_destroy(h); return fail(nullptr, DMB_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e)); }
