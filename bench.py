@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--term-mode", type=int, default=0, help="1 = add the DeepMimic fall-contact termination rule")
     ap.add_argument("--sync-gather", action="store_true", help="all-gather on the compute stream (no overlap)")
-    ap.add_argument("--nccl-ctas", type=int, default=1, help="CTAs of the all-gather kernel (0 = NCCL default)")
+    ap.add_argument("--nccl-ctas", type=int, default=0, help="NCCL max_ctas for the all-gather (0 = NCCL default)")
     ap.add_argument("--gather-depth", type=int, default=4, help="outstanding all-gathers (record buffers) in the overlapped form")
     ap.add_argument("--reward-mode", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -338,11 +338,12 @@ def run_ours(a):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # The step kernel is one persistent CTA per SM that owns the SM's whole shared memory, so a collective kernel
-        # cannot share an SM with it: the all-gather gets ONE CTA (NCCL max_ctas; 8 MB over NVLink per step needs no
-        # more) and the step kernel leaves one SM free for it (DMB_RESERVE_SMS, read by dmb_create).  Without this the
-        # gather's CTAs sit in front of the next step's CTAs on a few SMs and delay them (8 GPUs: 0.474 vs 0.445 ms).
-        os.environ.setdefault("DMB_RESERVE_SMS", "1")
+        # The step kernel is one persistent CTA per SM that owns the SM's whole shared memory, so NCCL's CTAs cannot share an
+        # SM with it: when the gather of step t is still waiting for the slowest rank, its CTAs sit on 16-32 SMs in front
+        # of the CTAs of step t + 1, which couples the ranks (8 GPUs: the kernel takes 0.468 ms on EVERY rank instead of
+        # 0.445).  Two knobs were measured against that (profiles/r2_c22_nccl_cta_experiment.txt) and are OFF by default:
+        # --nccl-ctas k (NCCL max_ctas; 1 CTA makes the gather itself take 1 ms, 4 CTAs 0.6 ms) and DMB_RESERVE_SMS=k
+        # (dmb_create leaves k SMs without a persistent CTA; costs 1.5 % at 8192 envs per GPU).
         opts = None
         if a.nccl_ctas > 0:
             try:
