@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=None)
     ap.add_argument("--term-mode", type=int, default=0, help="1 = add the DeepMimic fall-contact termination rule")
     ap.add_argument("--sync-gather", action="store_true", help="all-gather on the compute stream (no overlap)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="p2p: all-gather fused into the step kernel over NVLink peer memory; nccl: ncclAllGather on a side stream")
     ap.add_argument("--nccl-ctas", type=int, default=0, help="NCCL max_ctas for the all-gather (0 = NCCL default)")
     ap.add_argument("--gather-depth", type=int, default=4, help="outstanding all-gathers (record buffers) in the overlapped form")
     ap.add_argument("--reward-mode", type=int, default=4)
@@ -323,7 +325,7 @@ def restore_stdout(saved_fd):
 def run_ours(a):
     import torch
     import torch.distributed as dist
-    from deepmimic_mujoco_b200.dist import RecordGather, mixed_clip_ids
+    from deepmimic_mujoco_b200.dist import PeerRecordGather, RecordGather, mixed_clip_ids
     from deepmimic_mujoco_b200.env import DPVecEnv
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -366,7 +368,19 @@ def run_ours(a):
     sim = env.sim
     env.reset()
     D = max(2, a.gather_depth)
-    gather = RecordGather(sim.rec, n_global, depth=D) if world > 1 else None
+    p2p = world > 1 and a.gather == "p2p" and not a.sync_gather
+    gather = RecordGather(sim.rec, n_global, depth=D) if world > 1 and not p2p else None
+    # fused form: the step kernel itself stores every record row into all ranks' gathered buffers (NVLink peer memory)
+    # and signals them; the consumer's wait for step t - 2 is folded into the kernel of step t
+    peer, p2p_error = None, None
+    if p2p:
+        try:
+            peer = PeerRecordGather(sim, n_global, first, depth=max(D, 6))
+        except Exception as ex:          # no CUDA IPC / peer access on this box: every rank fails alike -> NCCL form
+            p2p_error = f"{type(ex).__name__}: {ex}"
+            p2p = False
+            gather = RecordGather(sim.rec, n_global, depth=D)
+    LAG = 1   # the wait for step t - 2 is folded into the kernel of step t; 6 buffers >= 2 * 2 + 1 (see PeerRecordGather)
     g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
     pool = torch.rand(16, E, sim.nu, device=dev, generator=g) - 0.5          # U(-0.5, 0.5) actions
     flush = None if a.no_flush else torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -377,6 +391,10 @@ def run_ours(a):
     # after the kernel of step t + D - 1, so every gather lies inside some step's timed interval (the last D - 1
     # are drained and timed after the loop).
     def one_step(i):
+        if peer is not None:
+            peer.arm()
+            if i >= LAG + 1:
+                peer.wait(in_next_step=True)   # step i - LAG - 1 ... folded into this step's kernel
         env.step(pool[i % 16])
         if gather is not None:
             if a.sync_gather:
@@ -390,6 +408,8 @@ def run_ours(a):
         one_step(i)
     if gather is not None:
         gather.drain()
+    if peer is not None:
+        peer.drain()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -406,6 +426,12 @@ def run_ours(a):
         if flush is not None:
             flush.zero_()
         ev0[i].record()
+        if peer is not None:
+            peer.arm()
+            if peer._t - peer._waited > LAG + 1:
+                # every rank's rows of step i - LAG - 1 must have arrived before this step's kernel completes: one
+                # thread of the kernel polls the flag at its start (the wait costs no launch of its own)
+                peer.wait(in_next_step=True)
         env.step(pool[i % 16])
         evk[i].record()
         if gather is not None:
@@ -418,6 +444,8 @@ def run_ours(a):
         ev1[i].record()
     if gather is not None:
         gather.drain()                     # the last gather has nothing to hide behind: it is timed on its own
+    if peer is not None:
+        peer.drain()
     evd.record()
     launches = sim.kernel_launches() - launches0
     torch.cuda.synchronize()
@@ -435,7 +463,11 @@ def run_ours(a):
 
     def e2e_step(i):
         d_act.copy_(h_act[i % 4], non_blocking=True)
+        if peer is not None:
+            peer.arm()
         env.step(d_act)
+        if peer is not None:
+            peer.wait()                    # the caller consumes this step's gathered record: no overlap here
         if gather is not None:
             gather.launch(sim.rec)
             gather.wait()                  # the caller consumes this step's gathered record: no overlap here
@@ -507,7 +539,9 @@ def run_ours(a):
                                        f"{', clip = env index % ' + str(nclip) if nclip > 1 else ''}",
                            "baseline_config": a.config, "envs_global": n_global, "envs_per_gpu": E,
                            "parallelism": f"env-shard x{world}",
-                           "collective": (f"nccl all_gather [N,{rec_w}] f32 per step, "
+                           "collective": (f"all-gather of the [N,{rec_w}] f32 record fused into the step kernel: peer stores over NVLink "
+                                          f"+ arrival flags, consumer waits for step t-{LAG + 1} inside the step kernel ({max(D, 6)} buffers); no NCCL kernel") if p2p else
+                                         (f"nccl all_gather [N,{rec_w}] f32 per step, "
                                           + ("on the compute stream" if a.sync_gather else
                                              f"side stream, overlapped with the following steps ({D} record buffers, "
                                              f"{a.nccl_ctas or 'default'} NCCL CTA(s), {os.environ.get('DMB_RESERVE_SMS', '0')} SM(s) left free)"))
@@ -525,6 +559,8 @@ def run_ours(a):
                 "clocks": clocks}
         if spread is not None:
             line["rank_spread"] = spread
+        if p2p_error is not None:
+            line["config"]["p2p_gather_unavailable"] = p2p_error
         if world > 1:
             line["nvlink"] = {"gather_bytes_in_per_rank_per_step": (world - 1) * E * rec_w * 4,
                               "gather_bytes_out_per_rank_per_step": E * rec_w * 4}
@@ -542,6 +578,8 @@ def run_ours(a):
                                                      "what": "same port, one ctypes call per env step (mujoco-py-like call overhead)"}
             cpu.close()
         emit_json(line, real_stdout)
+    if peer is not None:
+        peer.close()
     env.close()
     if world > 1:
         dist.barrier()

@@ -38,6 +38,15 @@ struct DevPtrs {
   const float* ref_aux;    // [F][DMB_REF_AUX]
   long long* trace;        // DMB_TRACE=1: [grid][8] globaltimer at kernel start and after each scheduler round
   float* gscratch;         // [grid * W][gs::stride] row storage of stages with more than RF constraint rows
+  // fused all-gather (dmb_set_peer_gather): every env's record row is also stored into the gathered [N_global][od+2]
+  // buffer of each of the n_peer ranks (peer memory over NVLink, self included) at row row0 + env; the last CTA to
+  // finish bumps every peer's arrival flag
+  float* peer_rec[DMB_MAX_PEER];
+  int* peer_flag[DMB_MAX_PEER];
+  int n_peer, row0;
+  int* ticket;             // CTAs done in this launch (last one signals the peers and rewinds it)
+  const int* wait_flag;    // dmb_set_peer_wait: this launch does not complete before *wait_flag >= wait_target
+  int wait_target;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -553,6 +562,17 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     P.trace[blockIdx.x * 8] = t;
   }
+  if (P.wait_flag && blockIdx.x == 0 && tid == 0) {
+    // consumer side of the fused all-gather folded into this launch (no extra kernel on the stream): one thread
+    // polls the arrival flag of an earlier step -- normally long satisfied -- so that the completion of this
+    // kernel implies that every rank's rows of that step have landed (acquire, system scope)
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(P.wait_flag) : "memory");
+      if (v < P.wait_target) __nanosleep(200);
+    } while (v < P.wait_target);
+    __threadfence_system();
+  }
   for (;;) {
     // Scheduling: envs are handed out in order of decreasing constraint work (k_order); a group
     // takes gsz consecutive entries at a time so that its warps see similar work between the
@@ -727,6 +747,19 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
       __syncwarp();
     }
     emit_obs(M, S, clip, idx_init, idx_curr, ep_len, out.obs, out.rec, env, lane);
+    if (P.n_peer > 0) {
+      // fused all-gather: the record row (obs, reward, done) goes straight into every rank's gathered buffer --
+      // posted stores over NVLink that overlap the rest of the kernel; no collective kernel competes for the SMs
+      const size_t rowoff = (size_t)(P.row0 + env) * (od + 2);
+      const int np = M.nq - 7;
+      for (int o = lane; o < od + 2; o += 32) {
+        float v;
+        if (o >= od) v = o == od ? rew : (done ? 1.f : 0.f);
+        else if (M.obs_mode == 1) v = S.o.k.cinert[o];                 // staged by write_obs_dm
+        else v = o < np ? S.qpos[7 + o] : S.qvel[6 + o - np];          // dp_env_v3.py:62-65
+        for (int p = 0; p < P.n_peer; p++) P.peer_rec[p][rowoff + o] = v;
+      }
+    }
     store_state(M, S, st, env, lane);
     __syncwarp();
     DMB_TICK(24);
@@ -740,6 +773,20 @@ __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_step(DevPtrs P, dmb_state
       atomicMax(&s_diag[0], S.diag & 0xffff);
       atomicMax(&s_diag[1], S.diag >> 16);
       if ((S.diag >> 16) > RF) atomicAdd(&s_diag[2], 1);
+    }
+  }
+  if (P.n_peer > 0) {
+    // release pattern of a put-with-signal: every thread fences its peer stores at system scope, the CTA counts itself
+    // done, and the last CTA of the launch (which has observed every other CTA's count) signals all peers
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      const int done_ctas = atomicAdd(P.ticket, 1);
+      if (done_ctas == (int)gridDim.x - 1) {
+        __threadfence_system();
+        for (int p = 0; p < P.n_peer; p++) atomicAdd_system(P.peer_flag[p], 1);
+        *P.ticket = 0;
+      }
     }
   }
   if (P.trace) {   // slot 6: the CTA's last warp is done; slot 7: diagnostics (sweeps | rows << 16 | scratch envs << 24)
@@ -774,6 +821,16 @@ __global__ void k_order(const int* __restrict__ cost, int* __restrict__ order, i
   }
   __syncthreads();
   for (int i = threadIdx.x; i < N; i += blockDim.x) order[atomicAdd(&cursor[min(255, max(0, cost[i]))], 1)] = i;
+}
+
+// consumer side of the fused all-gather: one thread polls this rank's arrival flag (acquire, system scope)
+__global__ void k_peer_wait(const int* flag, int target) {
+  int v;
+  do {
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v < target) __nanosleep(200);
+  } while (v < target);
+  __threadfence_system();
 }
 
 __global__ void __launch_bounds__(DMB_MAXTHREADS, 1) k_reset(DevPtrs P, dmb_state_t st, const unsigned char* __restrict__ mask, int mode, float* obs, int N,
@@ -909,6 +966,12 @@ struct dmb_handle_s {
   int sort_period = 1;      // single-round schedule: re-sort the env list every sort_period steps
   long long nstep = 0;
   long long nlaunch = 0;    // kernels launched through this handle so far
+  int n_peer = 0, row0 = 0;  // fused all-gather targets (dmb_set_peer_gather)
+  float* peer_rec[DMB_MAX_PEER] = {nullptr};
+  int* peer_flag[DMB_MAX_PEER] = {nullptr};
+  int* d_ticket = nullptr;
+  const int* wait_flag = nullptr;   // one-shot: consumed by the next dmb_step
+  int wait_target = 0;
   std::string err;
 };
 
@@ -1165,6 +1228,8 @@ int dmb_create(const dmb_model_t* model, const dmb_config_t* config, const dmb_m
   e = cudaMalloc((void**)&h->dmodel, sizeof(ModelS));
   if (e == cudaSuccess) e = cudaMemcpy(h->dmodel, &h->hmodel, sizeof(ModelS), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_counter, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_ticket, sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(h->d_ticket, 0, sizeof(int));
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_cost, sizeof(int) * (size_t)num_envs);
   if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_order, sizeof(int) * (size_t)num_envs);
   if (e == cudaSuccess) e = cudaMemset(h->d_cost, 0, sizeof(int) * (size_t)num_envs);
@@ -1250,7 +1315,7 @@ int32_t dmb_get_trace(dmb_handle_t h, int64_t* host_out, int32_t max_ctas) {
 int dmb_destroy(dmb_handle_t h) {
   if (!h) return DMB_ERR_ARG;
   cudaSetDevice(h->device);
-  cudaFree(h->d_counter); cudaFree(h->d_cost); cudaFree(h->d_order); cudaFree(h->dmodel); cudaFree(h->d_cfg); cudaFree(h->d_vel); cudaFree(h->d_aux); cudaFree(h->d_trace); cudaFree(h->d_scratch);
+  cudaFree(h->d_counter); cudaFree(h->d_cost); cudaFree(h->d_order); cudaFree(h->dmodel); cudaFree(h->d_cfg); cudaFree(h->d_vel); cudaFree(h->d_aux); cudaFree(h->d_trace); cudaFree(h->d_scratch); cudaFree(h->d_ticket);
   delete h;
   return DMB_OK;
 }
@@ -1259,7 +1324,7 @@ static bool state_ok(const dmb_state_t* st) {
   return st && st->qpos && st->qvel && st->warm && st->clip && st->idx_init && st->idx_curr && st->reset_count &&
          st->ep_len && st->ep_ret && st->flags;
 }
-static DevPtrs devptrs(dmb_handle_t h) { DevPtrs P; P.counter = h->d_counter; P.cost = h->d_cost; P.order = h->d_order; P.model = h->dmodel; P.mocap_cfg = h->d_cfg; P.mocap_vel = h->d_vel; P.ref_aux = h->d_aux; P.trace = h->d_trace; P.gscratch = h->d_scratch; return P; }
+static DevPtrs devptrs(dmb_handle_t h) { DevPtrs P; P.counter = h->d_counter; P.cost = h->d_cost; P.order = h->d_order; P.model = h->dmodel; P.mocap_cfg = h->d_cfg; P.mocap_vel = h->d_vel; P.ref_aux = h->d_aux; P.trace = h->d_trace; P.gscratch = h->d_scratch; P.n_peer = h->n_peer; P.row0 = h->row0; P.ticket = h->d_ticket; P.wait_flag = nullptr; P.wait_target = 0; for (int p = 0; p < DMB_MAX_PEER; p++) { P.peer_rec[p] = h->peer_rec[p]; P.peer_flag[p] = h->peer_flag[p]; } return P; }
 
 int dmb_reset(dmb_handle_t h, const dmb_state_t* st, const uint8_t* mask, int32_t mode, float* obs, void* stream) {
   if (!h) return DMB_ERR_ARG;
@@ -1284,8 +1349,11 @@ int dmb_step(dmb_handle_t h, const dmb_state_t* st, const float* action, const d
   }
   h->nstep++;
   h->nlaunch++;
-  if (h->lockstep) k_step<true><<<h->grid, dim3(32, h->envs_per_cta), h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
-  else k_step<false><<<h->grid, dim3(32, h->envs_per_cta), h->smem, (cudaStream_t)stream>>>(devptrs(h), *st, action, *out, h->num_envs, h->seed, h->first_env_id);
+  DevPtrs P = devptrs(h);
+  P.wait_flag = h->wait_flag; P.wait_target = h->wait_target;   // one-shot (dmb_set_peer_wait)
+  h->wait_flag = nullptr; h->wait_target = 0;
+  if (h->lockstep) k_step<true><<<h->grid, dim3(32, h->envs_per_cta), h->smem, (cudaStream_t)stream>>>(P, *st, action, *out, h->num_envs, h->seed, h->first_env_id);
+  else k_step<false><<<h->grid, dim3(32, h->envs_per_cta), h->smem, (cudaStream_t)stream>>>(P, *st, action, *out, h->num_envs, h->seed, h->first_env_id);
   CUDA_TRY(h, cudaGetLastError());
   return DMB_OK;
 }
@@ -1330,6 +1398,56 @@ int dmb_mocap_sample(dmb_handle_t h, const int32_t* clip, const double* frame_co
 }
 
 int32_t dmb_obs_dim(dmb_handle_t h) { return h ? h->obs_dim : DMB_ERR_ARG; }
+
+/* ---- fused all-gather over NVLink peer memory (see include/dmb.h) ---- */
+int dmb_peer_alloc(int32_t cuda_device, uint64_t bytes, void** ptr, uint8_t* handle64) {
+  if (!ptr || !handle64 || bytes == 0) return DMB_ERR_ARG;
+  if (cudaSetDevice(cuda_device) != cudaSuccess) return DMB_ERR_CUDA;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return DMB_ERR_CUDA;
+  cudaIpcMemHandle_t hnd;
+  if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess ||
+      cudaIpcGetMemHandle(&hnd, p) != cudaSuccess) { cudaFree(p); return DMB_ERR_CUDA; }
+  memcpy(handle64, &hnd, 64);
+  *ptr = p;
+  return DMB_OK;
+}
+int dmb_peer_open(int32_t cuda_device, const uint8_t* handle64, void** ptr) {
+  if (!ptr || !handle64) return DMB_ERR_ARG;
+  if (cudaSetDevice(cuda_device) != cudaSuccess) return DMB_ERR_CUDA;
+  cudaIpcMemHandle_t hnd;
+  memcpy(&hnd, handle64, 64);
+  // mapped into THIS device's address space; peer access to the owning GPU is enabled on first use
+  if (cudaIpcOpenMemHandle(ptr, hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); return DMB_ERR_CUDA; }
+  return DMB_OK;
+}
+int dmb_peer_close(void* ptr) { return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? DMB_OK : DMB_ERR_CUDA; }
+int dmb_peer_free(void* ptr) { return cudaFree(ptr) == cudaSuccess ? DMB_OK : DMB_ERR_CUDA; }
+
+int dmb_set_peer_gather(dmb_handle_t h, int32_t n_peer, float* const* rec_peer, int32_t* const* flag_peer, int32_t row0) {
+  if (!h) return DMB_ERR_ARG;
+  if (n_peer < 0 || n_peer > DMB_MAX_PEER || (n_peer > 0 && (!rec_peer || !flag_peer)) || row0 < 0)
+    return fail(h, DMB_ERR_ARG, "dmb_set_peer_gather: bad argument");
+  h->n_peer = n_peer; h->row0 = row0;
+  for (int p = 0; p < DMB_MAX_PEER; p++) {
+    h->peer_rec[p] = p < n_peer ? rec_peer[p] : nullptr;
+    h->peer_flag[p] = p < n_peer ? (int*)flag_peer[p] : nullptr;
+  }
+  return DMB_OK;
+}
+int dmb_set_peer_wait(dmb_handle_t h, const int32_t* flag, int32_t target) {
+  if (!h) return DMB_ERR_ARG;
+  h->wait_flag = (const int*)flag; h->wait_target = target;
+  return DMB_OK;
+}
+int dmb_peer_wait(dmb_handle_t h, const int32_t* flag, int32_t target, void* stream) {
+  if (!h || !flag) return DMB_ERR_ARG;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  k_peer_wait<<<1, 1, 0, (cudaStream_t)stream>>>((const int*)flag, target);
+  CUDA_TRY(h, cudaGetLastError());
+  return DMB_OK;
+}
 
 int64_t dmb_kernel_launches(dmb_handle_t h) { return h ? h->nlaunch : DMB_ERR_ARG; }
 

@@ -53,7 +53,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 _lib: Optional[C.CDLL] = None
 
 EXPORTS = ("dmb_version", "dmb_sizeof_model", "dmb_sizeof_config", "dmb_sizeof_mocap", "dmb_sizeof_tile", "dmb_create", "dmb_destroy", "dmb_reset", "dmb_step", "dmb_get_obs", "dmb_forward_debug",
-           "dmb_debug_stride", "dmb_debug_offset", "dmb_launch_info", "dmb_kernel_launches", "dmb_last_error", "dmb_obs_dim", "dmb_mocap_sample", "dmb_get_trace")
+           "dmb_debug_stride", "dmb_debug_offset", "dmb_launch_info", "dmb_kernel_launches", "dmb_peer_alloc", "dmb_peer_open",
+           "dmb_peer_close", "dmb_peer_free", "dmb_set_peer_gather", "dmb_peer_wait", "dmb_set_peer_wait", "dmb_last_error", "dmb_obs_dim", "dmb_mocap_sample", "dmb_get_trace")
 POLICY_EXPORTS = ("dmb_policy_act", "dmb_gae")   # include/dmb_policy.h
 
 
@@ -83,6 +84,13 @@ def load() -> C.CDLL:
     L.dmb_get_trace.restype = C.c_int32
     L.dmb_obs_dim.argtypes = [hp]
     L.dmb_kernel_launches.argtypes = [hp]
+    L.dmb_peer_alloc.argtypes = [C.c_int32, C.c_uint64, C.POINTER(C.c_void_p), C.c_char_p]
+    L.dmb_peer_open.argtypes = [C.c_int32, C.c_char_p, C.POINTER(C.c_void_p)]
+    L.dmb_peer_close.argtypes = [C.c_void_p]
+    L.dmb_peer_free.argtypes = [C.c_void_p]
+    L.dmb_set_peer_gather.argtypes = [hp, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32]
+    L.dmb_peer_wait.argtypes = [hp, C.c_void_p, C.c_int32, C.c_void_p]
+    L.dmb_set_peer_wait.argtypes = [hp, C.c_void_p, C.c_int32]
     L.dmb_kernel_launches.restype = C.c_int64
     L.dmb_obs_dim.restype = C.c_int32
     L.dmb_mocap_sample.argtypes = [hp, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -38,6 +38,7 @@ extern "C" {
 #define DMB_VERSION 2
 #define DMB_QSTRIDE 36 /* floats per qpos row (nq = 35 padded) */
 #define DMB_VSTRIDE 36 /* floats per qvel / warmstart row (nv = 34 padded) */
+#define DMB_MAX_PEER 8 /* ranks of one NVLink domain served by the fused all-gather */
 
 typedef enum dmb_status {
   DMB_OK = 0,
@@ -121,6 +122,26 @@ int32_t dmb_debug_stride(void);
  * names: xpos xquat xipos com qM qLD qfrc_bias qfrc_smooth qacc_smooth ncon nefc iter contact
  *        efc_pos efc_R efc_aref efc_b efc_force efc_AR_diag qacc z_com cvel */
 int32_t dmb_debug_offset(const char* name);
+
+/* Fused all-gather of the step record over NVLink peer memory ("a single all-gather of (obs, reward,
+ * done) per step"; replaces the ncclAllGather that would follow dmb_step).  Every rank allocates its gathered
+ * [N_global][obs_dim + 2] buffers and int32 arrival flags with dmb_peer_alloc (cudaMalloc + CUDA IPC handle, zeroed),
+ * exchanges the 64-byte handles (any out-of-band channel, e.g. torch.distributed.all_gather_object), maps the other
+ * ranks' buffers with dmb_peer_open, and before a step names the n_peer (<= DMB_MAX_PEER, self included) target
+ * buffers and flags: dmb_step then stores every env's record row into ALL of them at row row0 + env (posted peer
+ * stores from the step kernel's epilogue, overlapping the rest of the kernel) and the last CTA adds 1 to every peer
+ * flag (release at system scope).  A consumer enqueues dmb_peer_wait(flag, target) on its stream: one polling thread
+ * that returns once `target` ranks' steps have arrived (acquire).  No collective kernel, no SMs taken from the step
+ * kernel, no rank waits for another unless it consumes.  n_peer = 0 turns it off. */
+int dmb_peer_alloc(int32_t cuda_device, uint64_t bytes, void** ptr, uint8_t* handle64);
+int dmb_peer_open(int32_t cuda_device, const uint8_t* handle64, void** ptr);
+int dmb_peer_close(void* ptr);
+int dmb_peer_free(void* ptr);
+int dmb_set_peer_gather(dmb_handle_t h, int32_t n_peer, float* const* rec_peer, int32_t* const* flag_peer, int32_t row0);
+int dmb_peer_wait(dmb_handle_t h, const int32_t* flag, int32_t target, void* stream);
+/* the same wait folded into the NEXT dmb_step (one thread of its first CTA polls at kernel start, no extra launch): the
+ * completion of that step then implies the arrival; flag = NULL cancels */
+int dmb_set_peer_wait(dmb_handle_t h, const int32_t* flag, int32_t target);
 
 /* kernels launched by dmb_step through this handle so far (bench.py reports the count of its timed region) */
 int64_t dmb_kernel_launches(dmb_handle_t h);
