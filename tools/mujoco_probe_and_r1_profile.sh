@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 call 1: MuJoCo probe on the GPU box, GPU test-suite, bench of the shipped binary, sanitizer runs,
-# latency scan, ncu of the shipped binary.  Outputs: gpurun_out/r2c1_*
+# latency scan, ncu of the shipped binary.  Outputs: gpurun_out/probe_*
 set -u
 O=gpurun_out
 mkdir -p $O

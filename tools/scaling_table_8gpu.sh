@@ -4,9 +4,9 @@ set -u
 O=gpurun_out
 run() { # nproc, tag, args...
   n=$1; tag=$2; shift 2
-  if [ $n -eq 1 ]; then python bench.py --gpus 1 "$@" > $O/r2c20_$tag.json 2> $O/r2c20_$tag.err
-  else python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus $n "$@" > $O/r2c20_$tag.json 2> $O/r2c20_$tag.err; fi
-  python - "$O/r2c20_$tag.json" "$tag" <<'PY'
+  if [ $n -eq 1 ]; then python bench.py --gpus 1 "$@" > $O/scale_$tag.json 2> $O/scale_$tag.err
+  else python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus $n "$@" > $O/scale_$tag.json 2> $O/scale_$tag.err; fi
+  python - "$O/scale_$tag.json" "$tag" <<'PY'
 import json, sys
 try:
     d = json.load(open(sys.argv[1])); print(f"{sys.argv[2]:34s} {d['value']/1e6:8.2f} M  {d['ms_per_step']:.4f} ms  e2e {d['e2e']['value']/1e6:7.2f} M  n_gpus {d['n_gpus']} envs {d['config']['envs_global']}")
