@@ -65,6 +65,8 @@ def parse():
     ap.add_argument("--reward-mode", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--e2e-memcpy", action="store_true",
+                    help="end-to-end number through cudaMemcpyAsync + step + cudaMemcpyAsync only (skip the host-mapped step)")
     a = ap.parse_args()
     # BASELINE.json configs[1..4]: (envs per GPU, clips, seed)
     envs, motions, seed = {2: (4096, "walk", 0), 3: (16384, "spinkick", 1), 4: (8192, "walk", 0),
@@ -323,6 +325,7 @@ def restore_stdout(saved_fd):
 
 
 def run_ours(a):
+    import numpy as np
     import torch
     import torch.distributed as dist
     from deepmimic_mujoco_b200.dist import PeerRecordGather, RecordGather, mixed_clip_ids
@@ -474,16 +477,77 @@ def run_ours(a):
         h_rec.copy_(sim.rec, non_blocking=True)
         torch.cuda.current_stream().synchronize()   # the caller consumes obs/reward/done on the host
 
-    for i in range(3):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for i in range(K):
-        e2e_step(i)
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
+    def time_e2e(step_fn):
+        for i in range(3):
+            step_fn(i)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for i in range(K):
+            step_fn(i)
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    t_e2e_copy = time_e2e(e2e_step)
+    # The same through DPVecEnv.step_host: the step kernel itself loads the action rows from, and stores the record
+    # rows to, pinned device-mapped host memory over PCIe -- one launch per step, no cudaMemcpyAsync on either side.
+    # (With the NCCL fallback gather the record has to stay on the device, so the copy form is kept there.)
+    t_e2e, e2e_mode, e2e_note, t_e2e_mapped = t_e2e_copy, "memcpy", None, None
+
+    def all_ranks(ok):                         # every rank takes the same branch (time_e2e holds a barrier)
+        if world == 1:
+            return bool(ok)
+        f = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(f, op=dist.ReduceOp.MIN)
+        return bool(f.item())
+
+    if not a.e2e_memcpy and gather is None:
+        m_act = m_rec = None
+        try:
+            m_act = [sim.alloc_host((E, sim.nu)) for _ in range(4)]
+            for b, src in zip(m_act, h_act):
+                b.array[:] = src.numpy()
+            m_rec = sim.alloc_host((E, sim.obs_dim + 2))
+        except Exception as ex:                # the memcpy form stands
+            e2e_note = f"host-mapped buffers unavailable ({type(ex).__name__}: {ex})"
+            m_rec = None
+        if all_ranks(m_rec is not None):
+            def e2e_step_mapped(i):
+                if peer is not None:
+                    peer.arm()
+                env.step_host(m_act[i % 4], m_rec)
+                if peer is not None:
+                    peer.wait()                # the caller consumes this step's gathered record: no overlap here
+                torch.cuda.current_stream().synchronize()   # the caller consumes obs/reward/done on the host
+
+            same, t_mapped = False, None
+            try:
+                t_mapped = time_e2e(e2e_step_mapped)
+                od = sim.obs_dim               # the host record of the last step must be what the device buffers hold
+                same = (np.array_equal(m_rec.array[:, :od], sim.obs.cpu().numpy())
+                        and np.array_equal(m_rec.array[:, od], sim.reward.cpu().numpy())
+                        and np.array_equal(m_rec.array[:, od + 1] != 0, sim.done.cpu().numpy() != 0))
+            except Exception as ex:
+                if world > 1:                  # the other ranks are inside a collective: nothing to fall back to
+                    raise
+                e2e_note = f"host-mapped step failed ({type(ex).__name__}: {ex})"
+            if t_mapped is None:
+                pass
+            elif all_ranks(same):
+                if world > 1:                  # one decision for the job: compare the slowest ranks
+                    tm = torch.tensor([t_mapped, t_e2e_copy], device=dev, dtype=torch.float64)
+                    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                    t_mapped, t_e2e_copy = float(tm[0]), float(tm[1])
+                t_e2e_mapped = t_mapped
+                if t_mapped <= t_e2e_copy:
+                    t_e2e, e2e_mode = t_mapped, "host_mapped"
+                else:
+                    e2e_note = "host-mapped form measured slower than the memcpy form on this box: memcpy form reported"
+            else:
+                e2e_note = "host-mapped record differs from the device buffers on some rank"
+        elif e2e_note is None:
+            e2e_note = "host-mapped buffers unavailable on another rank"
     clocks = sampler.stop() if sampler else None
     # ---- N = 1 gym surface (the reference's own use: trpo.py with one env): DPEnv.step latency, numpy in / out
     gym_sps = None
@@ -510,9 +574,9 @@ def run_ours(a):
     if world > 1:
         tmin = torch.tensor([t_dev, t_kernel], device=dev, dtype=torch.float64)
         dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
-        tt = torch.tensor([t_dev, t_kernel, t_e2e], device=dev, dtype=torch.float64)
+        tt = torch.tensor([t_dev, t_kernel, t_e2e, t_e2e_copy], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_dev, t_kernel, t_e2e = [float(x) for x in tt.tolist()]
+        t_dev, t_kernel, t_e2e, t_e2e_copy = [float(x) for x in tt.tolist()]
         # how much of the multi-GPU step time is rank-to-rank variation of the kernel itself (different envs on
         # every rank: the slowest env of the slowest rank sets the pace) and how much is the collective
         spread = {"kernel_ms_per_step_min_rank": 1e3 * float(tmin[1]) / K, "kernel_ms_per_step_max_rank": 1e3 * t_kernel / K,
@@ -551,14 +615,21 @@ def run_ours(a):
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                              "traffic": traffic, "peak_source": peak_src,
                              "note": "compute/latency-bound fp32 kernel: ~1e3 FLOP/B, see DESIGN.md"},
+                # e2e: DPVecEnv.step_host -- the step kernel reads the pinned host action rows and writes the pinned host
+                # record rows itself over PCIe (mode host_mapped) -- or, where that is unavailable, cudaMemcpyAsync H2D +
+                # DPVecEnv.step + cudaMemcpyAsync D2H (mode memcpy; always measured and reported beside it)
                 "e2e": {"value": n_global * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": world * E * sim.nu * 4,
-                        "d2h_bytes_per_step": world * h_rec.numel() * 4},   # job totals over all ranks
+                        "d2h_bytes_per_step": world * h_rec.numel() * 4,   # job totals over all ranks
+                        "mode": e2e_mode, "memcpy_form_value": n_global * K / t_e2e_copy,
+                        "host_mapped_form_value": n_global * K / t_e2e_mapped if t_e2e_mapped else None},
                 # our kernels in the timed region, counted by the library: k_step (fused env step) every step + k_order
                 # (scheduler sort; every step with dynamic pulling, every 8th step when one round holds every env)
                 "gpu_launches": launches,
                 "clocks": clocks}
         if spread is not None:
             line["rank_spread"] = spread
+        if e2e_note is not None:
+            line["e2e"]["note"] = e2e_note
         if p2p_error is not None:
             line["config"]["p2p_gather_unavailable"] = p2p_error
         if world > 1:
@@ -566,7 +637,7 @@ def run_ours(a):
                               "gather_bytes_out_per_rank_per_step": E * rec_w * 4}
         if gym_sps is not None:
             line["gym_surface_n1"] = {"value": gym_sps, "unit": "env-steps/s",
-                                      "what": "DPEnv.step (N = 1, numpy in/out, H2D + 2 launches + D2H per step)"}
+                                      "what": "DPEnv.step (N = 1, numpy in/out; one launch per step, action and record in pinned host memory)"}
         if not a.no_cpu_baseline and world == 1:   # the CPU baseline is reported by the single-GPU run only
             cpu = CpuRollout(1, a.motions, a.reward_mode)
             v, n, w = cpu.run(150000)

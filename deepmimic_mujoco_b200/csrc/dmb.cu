@@ -1425,6 +1425,25 @@ int dmb_peer_open(int32_t cuda_device, const uint8_t* handle64, void** ptr) {
 int dmb_peer_close(void* ptr) { return cudaIpcCloseMemHandle(ptr) == cudaSuccess ? DMB_OK : DMB_ERR_CUDA; }
 int dmb_peer_free(void* ptr) { return cudaFree(ptr) == cudaSuccess ? DMB_OK : DMB_ERR_CUDA; }
 
+/* ---- host-mapped I/O: pinned host memory the step kernel reads (action) / writes (record) directly over PCIe ---- */
+int dmb_host_alloc(int32_t cuda_device, uint64_t bytes, void** host_ptr, void** dev_ptr) {
+  if (!host_ptr || !dev_ptr || bytes == 0) return DMB_ERR_ARG;
+  if (cudaSetDevice(cuda_device) != cudaSuccess) return DMB_ERR_CUDA;
+  void *hp = nullptr, *dp = nullptr;
+  if (cudaHostAlloc(&hp, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return DMB_ERR_CUDA; }
+  if (cudaHostGetDevicePointer(&dp, hp, 0) != cudaSuccess) { cudaGetLastError(); cudaFreeHost(hp); return DMB_ERR_CUDA; }
+  memset(hp, 0, bytes);
+  *host_ptr = hp; *dev_ptr = dp;
+  return DMB_OK;
+}
+int dmb_host_free(void* host_ptr) { return cudaFreeHost(host_ptr) == cudaSuccess ? DMB_OK : DMB_ERR_CUDA; }
+int dmb_host_device_pointer(int32_t cuda_device, void* host_ptr, void** dev_ptr) {
+  if (!host_ptr || !dev_ptr) return DMB_ERR_ARG;
+  if (cudaSetDevice(cuda_device) != cudaSuccess) return DMB_ERR_CUDA;
+  if (cudaHostGetDevicePointer(dev_ptr, host_ptr, 0) != cudaSuccess) { cudaGetLastError(); return DMB_ERR_ARG; }
+  return DMB_OK;
+}
+
 int dmb_set_peer_gather(dmb_handle_t h, int32_t n_peer, float* const* rec_peer, int32_t* const* flag_peer, int32_t row0) {
   if (!h) return DMB_ERR_ARG;
   if (n_peer < 0 || n_peer > DMB_MAX_PEER || (n_peer > 0 && (!rec_peer || !flag_peer)) || row0 < 0)

@@ -103,6 +103,13 @@ class DPVecEnv:
         self.step_async(actions)
         return self.step_wait()
 
+    def step_host(self, act=None, rec=None):
+        """``step`` for a host-resident policy: actions are read from, and the packed (obs, reward, done) record is
+        written to, pinned host arrays by the step kernel itself (``BatchedSim.step_host``; buffers from
+        ``self.sim.enable_host_io()`` / ``self.sim.alloc_host``).  Returns the record HostArray; synchronise the
+        stream before reading it.  Finished-episode statistics stay on the device (``self.sim.last_ret/last_len``)."""
+        return self.sim.step_host(act, rec)
+
     def state_dict(self):
         s = self.sim
         return {k: getattr(s, k).clone() for k in ("qpos", "qvel", "warm", "clip", "idx_init", "idx_curr",
@@ -160,7 +167,7 @@ class _SimData:
 
     @property
     def ctrl(self):
-        return self._env._act[0].double().cpu().numpy()
+        return self._env._hact.array[0].astype(np.float64)
 
 
 class _SimView:
@@ -171,7 +178,7 @@ class _SimView:
         self._env = env
 
     def forward(self):
-        self._env._forward(self._env._act)
+        self._env._forward()
 
 
 class _MocapView:
@@ -215,6 +222,8 @@ class DPEnv(_EnvBase):
                                  (t.nu,), np.float32)
         self.np_random = np.random.RandomState(seed)
         self._act = torch.zeros(1, t.nu, dtype=torch.float32, device=self._sim.device)
+        # one launch per step: the kernel reads the action from / writes the record to pinned host memory
+        self._hact, self._hrec = self._sim.enable_host_io()
         # gym MujocoEnv.__init__ side effect: one probe step with a random action
         ob, _, done, _ = self.step(self.action_space.sample())
         assert not done
@@ -259,19 +268,20 @@ class DPEnv(_EnvBase):
     def _get_obs(self):
         return self._sim.get_obs()[0].double().cpu().numpy()
 
-    def _forward(self, ctrl: torch.Tensor):
-        """gym ``MujocoEnv.set_state`` ends with ``sim.forward()``: one mj_forward that leaves
-        qacc_warmstart = qacc for the next step (the batched auto-reset path starts from 0 instead)."""
-        self._sim.forward_debug(ctrl)
+    def _forward(self):
+        """gym ``MujocoEnv.set_state`` ends with ``sim.forward()``: one mj_forward (data.ctrl = the last action) that
+        leaves qacc_warmstart = qacc for the next step (the batched auto-reset path starts from 0 instead)."""
+        self._act.copy_(self._hact.tensor)
+        self._sim.forward_debug(self._act)
 
     def set_state(self, qpos, qvel):
         self._sim.set_state(np.asarray(qpos)[None], np.asarray(qvel)[None])
-        self._forward(self._act)                                  # data.ctrl still holds the last action
+        self._forward()                                           # data.ctrl still holds the last action
 
     def reset(self):
         ob = self._sim.reset(mode=0)[0].double().cpu().numpy()   # reset_model(): mocap RSI
-        self._act.zero_()                                         # sim.reset() clears data.ctrl
-        self._forward(self._act)
+        self._hact.array[:] = 0.0                                 # sim.reset() clears data.ctrl
+        self._forward()
         return ob
 
     def reset_model(self):
@@ -287,9 +297,10 @@ class DPEnv(_EnvBase):
         a = np.asarray(action, dtype=np.float32).reshape(1, -1)
         if a.shape[1] != self._sim.nu:
             raise ValueError(f"action must have {self._sim.nu} entries")
-        self._act.copy_(torch.from_numpy(a))
-        obs, rew, done = self._sim.step(self._act)
-        out = torch.cat([obs[0], rew, done.float()]).double().cpu().numpy()
+        self._hact.array[:] = a
+        self._sim.step_host(self._hact, self._hrec)
+        torch.cuda.current_stream(self._sim.device).synchronize()
+        out = self._hrec.array[0].astype(np.float64)
         return out[:-2], float(out[-2]), bool(out[-1] != 0.0), {}
 
     def render(self, mode="human"):

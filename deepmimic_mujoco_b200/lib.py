@@ -54,7 +54,7 @@ _lib: Optional[C.CDLL] = None
 
 EXPORTS = ("dmb_version", "dmb_sizeof_model", "dmb_sizeof_config", "dmb_sizeof_mocap", "dmb_sizeof_tile", "dmb_create", "dmb_destroy", "dmb_reset", "dmb_step", "dmb_get_obs", "dmb_forward_debug",
            "dmb_debug_stride", "dmb_debug_offset", "dmb_launch_info", "dmb_kernel_launches", "dmb_peer_alloc", "dmb_peer_open",
-           "dmb_peer_close", "dmb_peer_free", "dmb_set_peer_gather", "dmb_peer_wait", "dmb_set_peer_wait", "dmb_last_error", "dmb_obs_dim", "dmb_mocap_sample", "dmb_get_trace")
+           "dmb_peer_close", "dmb_peer_free", "dmb_set_peer_gather", "dmb_peer_wait", "dmb_set_peer_wait", "dmb_host_alloc", "dmb_host_free", "dmb_host_device_pointer", "dmb_last_error", "dmb_obs_dim", "dmb_mocap_sample", "dmb_get_trace")
 POLICY_EXPORTS = ("dmb_policy_act", "dmb_gae")   # include/dmb_policy.h
 
 
@@ -91,6 +91,9 @@ def load() -> C.CDLL:
     L.dmb_set_peer_gather.argtypes = [hp, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int32]
     L.dmb_peer_wait.argtypes = [hp, C.c_void_p, C.c_int32, C.c_void_p]
     L.dmb_set_peer_wait.argtypes = [hp, C.c_void_p, C.c_int32]
+    L.dmb_host_alloc.argtypes = [C.c_int32, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.dmb_host_free.argtypes = [C.c_void_p]
+    L.dmb_host_device_pointer.argtypes = [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]
     L.dmb_kernel_launches.restype = C.c_int64
     L.dmb_obs_dim.restype = C.c_int32
     L.dmb_mocap_sample.argtypes = [hp, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -51,6 +51,30 @@ def make_mocap_struct(mc: MocapTables, ref_aux: Optional[np.ndarray] = None):
     return s, (cfg, vel, aux)
 
 
+class HostArray:
+    """Pinned, device-mapped float32 host array (``dmb_host_alloc``): ``array`` / ``tensor`` are numpy / torch views of
+    the same bytes, ``dev_ptr`` is the address the step kernel uses to read or write them over PCIe."""
+
+    def __init__(self, L, device_index: int, shape):
+        self.shape = tuple(int(x) for x in shape)
+        n = int(np.prod(self.shape))
+        hp, dp = C.c_void_p(), C.c_void_p()
+        rc = L.dmb_host_alloc(int(device_index), C.c_uint64(4 * n), C.byref(hp), C.byref(dp))
+        if rc != 0:
+            raise _lib.DmbError(f"dmb_host_alloc({4 * n} bytes) failed ({rc})")
+        self._L, self.host_ptr, self.dev_ptr = L, hp.value, dp.value
+        self._buf = (C.c_float * n).from_address(self.host_ptr)
+        self.array = np.frombuffer(self._buf, dtype=np.float32).reshape(self.shape)
+        self.tensor = torch.from_numpy(self.array)
+
+    def free(self):
+        """Release the pinned memory; the views must not be used afterwards."""
+        if self.host_ptr:
+            self.array = self.tensor = self._buf = None
+            self._L.dmb_host_free(C.c_void_p(self.host_ptr))
+            self.host_ptr = self.dev_ptr = 0
+
+
 class BatchedSim:
     """N envs on one GPU.  All tensors are CUDA, env-major, contiguous."""
 
@@ -108,6 +132,9 @@ class BatchedSim:
                                     self.rec.data_ptr(), self.last_ret.data_ptr(), self.last_len.data_ptr())
         qpos0 = torch.tensor(self.tables.qpos0, dtype=f32, device=d)
         self.qpos[:, : self.nq] = qpos0
+        self.host_act: Optional[HostArray] = None    # step_host() defaults, allocated on first use
+        self.host_rec: Optional[HostArray] = None
+        self._host_arrays = []
 
     # ------------------------------------------------------------------------------------
     def _stream(self):
@@ -115,6 +142,12 @@ class BatchedSim:
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle:
+            if torch.cuda.is_available():
+                torch.cuda.synchronize(self.device)     # no kernel may still be writing a host-mapped record
+            for a in getattr(self, "_host_arrays", []):
+                a.free()
+            self._host_arrays = []
+            self.host_act = self.host_rec = None
             self.L.dmb_destroy(self.handle)
             self.handle = None
 
@@ -158,6 +191,38 @@ class BatchedSim:
             _lib.check(self.L.dmb_step(self.handle, C.byref(self._st), C.c_void_p(action.data_ptr()),
                                        C.byref(self._out), self._stream()), self.handle, "dmb_step")
         return self.obs, self.reward, self.done
+
+    # --- host-mapped I/O (include/dmb.h "Host-mapped I/O"): for a policy that lives on the host ---------------------
+    def alloc_host(self, shape) -> HostArray:
+        """A pinned, device-mapped float32 host array owned by this sim (freed by ``close``)."""
+        a = HostArray(self.L, self.device.index, shape)
+        self._host_arrays.append(a)
+        return a
+
+    def enable_host_io(self):
+        """Allocate the default host action [N, nu] and record [N, obs_dim + 2] arrays of ``step_host``."""
+        if self.host_act is None:
+            self.host_act = self.alloc_host((self.N, self.nu))
+            self.host_rec = self.alloc_host((self.N, self.obs_dim + 2))
+        return self.host_act, self.host_rec
+
+    def step_host(self, act: Optional[HostArray] = None, rec: Optional[HostArray] = None) -> HostArray:
+        """One env step in ONE launch with host-resident inputs and outputs: the kernel loads every env's action row
+        from the pinned host array ``act`` and stores its (obs, reward, done) record row into the pinned host array
+        ``rec`` over PCIe -- no cudaMemcpyAsync on either side.  Asynchronous like ``step``: synchronise the stream
+        before reading ``rec.array`` (and before overwriting ``act``).  obs / reward / done / last_ret / last_len are
+        still written to the device tensors; the device record ``self.rec`` is NOT written by this call."""
+        if act is None or rec is None:
+            self.enable_host_io()
+            act = self.host_act if act is None else act
+            rec = self.host_rec if rec is None else rec
+        if act.shape != (self.N, self.nu) or rec.shape != (self.N, self.obs_dim + 2) or not act.dev_ptr or not rec.dev_ptr:
+            raise ValueError("step_host: act must be a live HostArray [N, nu] and rec a live HostArray [N, obs_dim + 2]")
+        self._out.rec = rec.dev_ptr
+        with torch.cuda.device(self.device):
+            _lib.check(self.L.dmb_step(self.handle, C.byref(self._st), C.c_void_p(act.dev_ptr), C.byref(self._out),
+                                       self._stream()), self.handle, "dmb_step")
+        return rec
 
     def get_obs(self) -> torch.Tensor:
         with torch.cuda.device(self.device):

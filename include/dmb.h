@@ -143,6 +143,18 @@ int dmb_peer_wait(dmb_handle_t h, const int32_t* flag, int32_t target, void* str
  * completion of that step then implies the arrival; flag = NULL cancels */
 int dmb_set_peer_wait(dmb_handle_t h, const int32_t* flag, int32_t target);
 
+/* Host-mapped I/O for callers whose policy lives on the host (the reference's own use: trpo.py:49 computes the action
+ * on the CPU and reads ob/rew/new back every step, dp_env_v3.py:106-132).  `action` and `out->rec` of dmb_step may point
+ * to PINNED, device-mapped host memory: the step kernel then loads each env's action row and stores its record row
+ * directly over PCIe (one 112-byte read and 232 bytes of posted writes per env, overlapping the kernel), so a step is
+ * ONE launch instead of cudaMemcpyAsync + kernel + cudaMemcpyAsync.  The host may read the record after it has
+ * synchronised with the stream.  dmb_host_alloc returns such a buffer (cudaHostAlloc mapped + portable, zeroed) with
+ * its host and device addresses; dmb_host_device_pointer resolves the device address of a buffer the caller pinned
+ * itself (cudaHostAlloc / cudaHostRegister, e.g. torch's pin_memory()).  All other arrays stay device memory. */
+int dmb_host_alloc(int32_t cuda_device, uint64_t bytes, void** host_ptr, void** dev_ptr);
+int dmb_host_free(void* host_ptr);
+int dmb_host_device_pointer(int32_t cuda_device, void* host_ptr, void** dev_ptr);
+
 /* kernels launched by dmb_step through this handle so far (bench.py reports the count of its timed region) */
 int64_t dmb_kernel_launches(dmb_handle_t h);
 
