@@ -90,17 +90,19 @@ class DPVecEnv:
     def reset(self) -> torch.Tensor:
         return self.sim.reset()
 
-    def step_async(self, actions: torch.Tensor) -> None:
-        self._pending = actions
+    def step_async(self, actions: torch.Tensor, rec_host=None) -> None:
+        self._pending = (actions, rec_host)
 
     def step_wait(self):
-        obs, rew, done = self.sim.step(self._pending)
+        obs, rew, done = self.sim.step(self._pending[0], rec_host=self._pending[1])
         self._pending = None
         infos = {"episode_return": self.sim.last_ret, "episode_length": self.sim.last_len, "flags": self.sim.flags}
         return obs, rew, done, infos
 
-    def step(self, actions: torch.Tensor):
-        self.step_async(actions)
+    def step(self, actions: torch.Tensor, rec_host=None):
+        """``rec_host`` (a ``sim.alloc_host((N, obs_dim + 2))`` array): the kernel writes the packed (obs, reward, done)
+        record of this step straight into pinned host memory -- no device-to-host copy to enqueue afterwards."""
+        self.step_async(actions, rec_host)
         return self.step_wait()
 
     def step_host(self, act=None, rec=None):

@@ -130,6 +130,7 @@ class BatchedSim:
                                                            self.flags)])
         self._out = _lib.DmbStepOut(self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
                                     self.rec.data_ptr(), self.last_ret.data_ptr(), self.last_len.data_ptr())
+        self._st_ref, self._out_ref = C.byref(self._st), C.byref(self._out)
         qpos0 = torch.tensor(self.tables.qpos0, dtype=f32, device=d)
         self.qpos[:, : self.nq] = qpos0
         self.host_act: Optional[HostArray] = None    # step_host() defaults, allocated on first use
@@ -178,18 +179,34 @@ class BatchedSim:
                                         self._stream()), self.handle, "dmb_reset")
         return self.obs
 
-    def step(self, action: torch.Tensor):
-        """One env step for all envs.  action: CUDA float32 [N, nu].  Returns (obs, reward, done) tensors
-        (views of internal buffers, overwritten by the next call)."""
-        if action.device != self.device or action.dtype != torch.float32 or not action.is_contiguous() \
-                or tuple(action.shape) != (self.N, self.nu):
-            raise ValueError("action must be a contiguous CUDA float32 tensor of shape [N, nu] on the sim's device")
-        self.rec_index = (self.rec_index + 1) % len(self.rec_buffers)
-        self.rec = self.rec_buffers[self.rec_index]
-        self._out.rec = self.rec.data_ptr()
-        with torch.cuda.device(self.device):
-            _lib.check(self.L.dmb_step(self.handle, C.byref(self._st), C.c_void_p(action.data_ptr()),
-                                       C.byref(self._out), self._stream()), self.handle, "dmb_step")
+    def step(self, action, rec_host: Optional["HostArray"] = None):
+        """One env step for all envs.  action: CUDA float32 [N, nu] (or a HostArray, see ``step_host``).  Returns
+        (obs, reward, done) tensors (views of internal buffers, overwritten by the next call).  With ``rec_host`` the
+        kernel stores the packed record rows into that pinned host array instead of the device record ``self.rec``."""
+        if isinstance(action, HostArray):
+            if action.shape != (self.N, self.nu) or not action.dev_ptr:
+                raise ValueError("action HostArray must be live and of shape [N, nu]")
+            act_ptr = action.dev_ptr
+        else:
+            if action.device != self.device or action.dtype != torch.float32 or not action.is_contiguous() \
+                    or tuple(action.shape) != (self.N, self.nu):
+                raise ValueError("action must be a contiguous CUDA float32 tensor of shape [N, nu] on the sim's device")
+            act_ptr = action.data_ptr()
+        if rec_host is not None:
+            if rec_host.shape != (self.N, self.obs_dim + 2) or not rec_host.dev_ptr:
+                raise ValueError("rec_host must be a live HostArray of shape [N, obs_dim + 2]")
+            self._out.rec = rec_host.dev_ptr
+        else:
+            self.rec_index = (self.rec_index + 1) % len(self.rec_buffers)
+            self.rec = self.rec_buffers[self.rec_index]
+            self._out.rec = self.rec.data_ptr()
+        if torch.cuda.current_device() == self.device.index:     # the usual case: skip the device-guard round trip
+            rc = self.L.dmb_step(self.handle, self._st_ref, act_ptr, self._out_ref, self._stream())
+        else:
+            with torch.cuda.device(self.device):
+                rc = self.L.dmb_step(self.handle, self._st_ref, act_ptr, self._out_ref, self._stream())
+        if rc != 0:
+            _lib.check(rc, self.handle, "dmb_step")
         return self.obs, self.reward, self.done
 
     # --- host-mapped I/O (include/dmb.h "Host-mapped I/O"): for a policy that lives on the host ---------------------
@@ -211,17 +228,16 @@ class BatchedSim:
         from the pinned host array ``act`` and stores its (obs, reward, done) record row into the pinned host array
         ``rec`` over PCIe -- no cudaMemcpyAsync on either side.  Asynchronous like ``step``: synchronise the stream
         before reading ``rec.array`` (and before overwriting ``act``).  obs / reward / done / last_ret / last_len are
-        still written to the device tensors; the device record ``self.rec`` is NOT written by this call."""
+        still written to the device tensors; the device record ``self.rec`` is NOT written by this call.  The two
+        sides are independent: ``step(cuda_action, rec_host=rec)`` keeps the action on the device (copied by the DMA
+        engine, which moves a large batch faster than SM loads over PCIe do) and only writes the record to the host."""
         if act is None or rec is None:
             self.enable_host_io()
             act = self.host_act if act is None else act
             rec = self.host_rec if rec is None else rec
-        if act.shape != (self.N, self.nu) or rec.shape != (self.N, self.obs_dim + 2) or not act.dev_ptr or not rec.dev_ptr:
-            raise ValueError("step_host: act must be a live HostArray [N, nu] and rec a live HostArray [N, obs_dim + 2]")
-        self._out.rec = rec.dev_ptr
-        with torch.cuda.device(self.device):
-            _lib.check(self.L.dmb_step(self.handle, C.byref(self._st), C.c_void_p(act.dev_ptr), C.byref(self._out),
-                                       self._stream()), self.handle, "dmb_step")
+        if not isinstance(act, HostArray) or not isinstance(rec, HostArray):
+            raise ValueError("step_host: act must be a HostArray [N, nu] and rec a HostArray [N, obs_dim + 2]")
+        self.step(act, rec_host=rec)
         return rec
 
     def get_obs(self) -> torch.Tensor:

@@ -25,13 +25,19 @@ def test_step_host_bit_identical_to_device_path():
     for t in range(40):
         act = (rng.random((n, 28), dtype=np.float32) - 0.5) * (3.0 if t % 7 == 3 else 1.0)
         obs, rew, done, info = a.step(torch.from_numpy(act).cuda())
-        src = hact if t % 2 == 0 else hact2
-        src.array[:] = act
-        out = b.step_host(src, hrec)
-        assert out is hrec
+        dact = torch.from_numpy(act).cuda()
+        if t % 3 == 0:                                       # both sides host-mapped
+            hact.array[:] = act
+            assert b.step_host(hact, hrec) is hrec
+        elif t % 3 == 1:                                     # device action, record straight to the host
+            b.step(dact, rec_host=hrec)
+        else:                                                # host-mapped action (a caller-rotated buffer), device record
+            hact2.array[:] = act
+            b.step(hact2)
         torch.cuda.synchronize()
         rec = a.sim.rec.cpu().numpy()
-        assert np.array_equal(hrec.array, rec), t
+        got = hrec.array if t % 3 != 2 else b.sim.rec.cpu().numpy()
+        assert np.array_equal(got, rec), t
         assert torch.equal(b.sim.obs, obs) and torch.equal(b.sim.reward, rew) and torch.equal(b.sim.done, done)
         assert torch.equal(b.sim.last_len, info["episode_length"])
         ndone += int(done.sum())
