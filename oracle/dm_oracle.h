@@ -11,6 +11,11 @@
  * restates MuJoCo's published computation pipeline (mj_step with RK4 + PGS, as
  * documented for the open-sourced >=2.1 engine) for the MJCF subset of dp_env_v3.xml,
  * plus the env logic of dp_env_v3.py.  Deviations are listed in DESIGN.md.
+ * The only MuJoCo-PRODUCED data in the reference is the episode monitor of its training run
+ * (src/log_tmp/DeepMimic/trpo-walk-0/monitor.json.monitor.csv); the oracle reproduces its
+ * time-to-fall distribution under the same protocol (tests/test_oracle_physics.py,
+ * tests/golden/ref_episode_lengths.json) -- a statistical pin of the whole pipeline, not a
+ * state-level one, so the status above stands.
  */
 #ifndef DM_ORACLE_H_
 #define DM_ORACLE_H_

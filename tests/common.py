@@ -104,3 +104,12 @@ MEASURED = {}
 def record(label, key, value):
     d = MEASURED.setdefault(label, {})
     d[key] = max(float(value), d.get(key, 0.0))
+
+
+def ref_fall_lengths(k=100):
+    """Episode lengths of the reference's own MuJoCo run under its freshly initialised policy
+    (tests/golden/make_ref_episode_golden.py): the first k episodes that start from the standing pose."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_episode_lengths.json")) as f:
+        g = json.load(f)
+    return np.asarray(g["lengths_from_standing_pose"][:k], dtype=np.float64)

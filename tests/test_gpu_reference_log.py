@@ -1,0 +1,38 @@
+"""The CUDA path against the one MuJoCo-PRODUCED artefact of the reference: the episode monitor of its own training
+run (tests/golden/ref_episode_lengths.json, made by tests/golden/make_ref_episode_golden.py).  Same protocol as the
+rows were recorded with (trpo.py:27-80): standing pose +- 0.01 (reset_model_init, dp_env_v3.py:158-164), N(0,1)
+actions of the freshly initialised Gaussian policy clamped to the ctrlrange, reward 1.0 per step, done when the CoM
+height leaves [0.7, 2.0].  tests/test_oracle_physics.py holds the same check for the float64 oracle."""
+import numpy as np
+import pytest
+import torch
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fall_time_distribution_matches_reference_monitor_log():
+    from scipy import stats
+    from deepmimic_mujoco_b200.env import DPVecEnv
+    ref = common.ref_fall_lengths(100)
+    n = 2048
+    env = DPVecEnv(n, motions=("walk",), seed=21, reward_mode=0, reset_mode=1, auto_reset=True)
+    env.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(3)
+    first = torch.zeros(n, dtype=torch.int32, device="cuda")          # length of every env's FIRST episode (no
+    for t in range(400):                                              # window bias towards short episodes)
+        obs, rew, done, info = env.step(torch.randn(n, 28, device="cuda", generator=g))
+        new = (done != 0) & (first == 0)
+        first = torch.where(new, info["episode_length"].to(torch.int32), first)
+        if t > 20 and bool((first > 0).all()):
+            break
+    lens = first.cpu().numpy().astype(np.float64)
+    env.close()
+    assert (lens > 0).all(), "some env never fell under N(0,1) torques"
+    # oracle, same protocol, 2000 episodes: mean - reference mean = -0.8 (reference sample error 0.8), KS D = 0.08
+    assert abs(lens.mean() - ref.mean()) < 3.0, (lens.mean(), ref.mean())
+    assert 0.75 < lens.std() / ref.std() < 1.25, (lens.std(), ref.std())
+    ks = stats.ks_2samp(lens, ref)
+    assert ks.pvalue > 0.01, ks
+    assert np.abs(np.percentile(lens, [25, 50, 75]) - np.percentile(ref, [25, 50, 75])).max() <= 3.0
