@@ -113,3 +113,61 @@ def ref_fall_lengths(k=100):
     with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_episode_lengths.json")) as f:
         g = json.load(f)
     return np.asarray(g["lengths_from_standing_pose"][:k], dtype=np.float64)
+
+
+class RefTrainedPolicy:
+    """The policy the reference's own TRPO run trained IN MuJoCo 2.0, read from the TensorFlow checkpoint the reference
+    ships (tests/golden/make_ref_policy_golden.py; network of mlp_policy_trpo.py:24-60): obz = clip((ob - mean) / std,
+    -5, 5), two tanh layers of 100, a linear head of 28, action = mean + exp(logstd) * N(0, 1).  ``monitor_window(w)``
+    = the episode lengths the reference's monitor recorded for the w episodes before and the w after the moment the
+    checkpoint was written (older / newer policies within TRPO's max_kl 0.01 per update of the saved one)."""
+
+    def __init__(self):
+        g = np.load(os.path.join(GOLDEN, "ref_trained_policy.npz"))
+        cnt = g["pi_obfilter_count"]
+        self.ob_mean = (g["pi_obfilter_runningsum"] / cnt).astype(np.float32).astype(np.float64)
+        var = (g["pi_obfilter_runningsumsq"] / cnt).astype(np.float32).astype(np.float64) - self.ob_mean ** 2
+        self.ob_std = np.sqrt(np.maximum(var, 1e-2))                      # utils/misc_util.py:53-54
+        self.layers = [(g[f"pi_{n}_w"].astype(np.float64), g[f"pi_{n}_b"].astype(np.float64))
+                       for n in ("polfc1", "polfc2", "polfinal")]
+        self.act_std = np.exp(g["pi_logstd"][0].astype(np.float64))
+        self._lens = g["monitor_last_lengths"].astype(np.float64)
+        self._k = int(g["checkpoint_index"])
+
+    def mean_action(self, ob):
+        """ob [n, 56] -> mean action [n, 28] (float64 numpy)."""
+        h = np.clip((np.asarray(ob, dtype=np.float64) - self.ob_mean) / self.ob_std, -5.0, 5.0)
+        for i, (w, b) in enumerate(self.layers):
+            h = h @ w + b
+            if i < 2:
+                h = np.tanh(h)
+        return h
+
+    def torch_mean_action(self, ob):
+        """The same network on a torch tensor ob [n, 56] (any device, float32) -> mean action [n, 28]."""
+        import torch
+        c = lambda a: torch.as_tensor(a, dtype=torch.float32, device=ob.device)
+        h = torch.clamp((ob - c(self.ob_mean)) / c(self.ob_std), -5.0, 5.0)
+        for i, (w, b) in enumerate(self.layers):
+            h = h @ c(w) + c(b)
+            if i < 2:
+                h = torch.tanh(h)
+        return h
+
+    def monitor_window(self, w=50):
+        return self._lens[max(0, self._k - w): self._k + w].copy()
+
+
+def trained_policy_verdict(lens, ref):
+    """The acceptance rule of the trained-policy pin, shared by the oracle test, the GPU test
+    and tools/trained_policy_sensitivity.py: survival time of the reference's MuJoCo-trained policy, this
+    implementation (``lens``) vs the reference's own monitor rows (``ref``).  The distribution is heavy-tailed
+    (roughly geometric beyond ~100 steps), so the rule uses the mean, the median, the lower quartile and a two-sample
+    Kolmogorov-Smirnov test; 100 reference episodes put ~6 % standard error on the reference mean and the policy
+    itself drifts by a few % across the window."""
+    from scipy import stats
+    lens, ref = np.asarray(lens, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    return bool(abs(lens.mean() / ref.mean() - 1.0) < 0.2
+                and abs(np.median(lens) / np.median(ref) - 1.0) < 0.2
+                and abs(np.percentile(lens, 25) / np.percentile(ref, 25) - 1.0) < 0.2
+                and stats.ks_2samp(lens, ref).pvalue > 0.01)

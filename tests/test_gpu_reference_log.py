@@ -1,5 +1,6 @@
 """The CUDA path against the one MuJoCo-PRODUCED artefact of the reference: the episode monitor of its own training
-run (tests/golden/ref_episode_lengths.json, made by tests/golden/make_ref_episode_golden.py).  Same protocol as the
+run (tests/golden/ref_episode_lengths.json, made by tests/golden/make_ref_episode_golden.py) and the policy that run
+trained in MuJoCo (tests/golden/ref_trained_policy.npz, made by tests/golden/make_ref_policy_golden.py).  Same protocol as the
 rows were recorded with (trpo.py:27-80): standing pose +- 0.01 (reset_model_init, dp_env_v3.py:158-164), N(0,1)
 actions of the freshly initialised Gaussian policy clamped to the ctrlrange, reward 1.0 per step, done when the CoM
 height leaves [0.7, 2.0].  tests/test_oracle_physics.py holds the same check for the float64 oracle."""
@@ -36,3 +37,35 @@ def test_fall_time_distribution_matches_reference_monitor_log():
     ks = stats.ks_2samp(lens, ref)
     assert ks.pvalue > 0.01, ks
     assert np.abs(np.percentile(lens, [25, 50, 75]) - np.percentile(ref, [25, 50, 75])).max() <= 3.0
+
+
+def test_trained_policy_survival_matches_reference_monitor_log():
+    """The policy the reference's TRPO run trained in MuJoCo 2.0 (its shipped TensorFlow checkpoint) keeps the MuJoCo
+    humanoid up for ~290 steps (monitor rows around the save; a random policy: ~35).  The same weights, same protocol
+    (reset_model_init, stochastic actions mean + exp(logstd) N(0,1), done on CoM height), on the CUDA path: first
+    episode of 2048 envs.  Acceptance rule and the oracle's numbers (mean 279 +- 3, median 238): common.py,
+    tests/test_oracle_physics.py::test_trained_policy_survival_matches_reference_monitor_log."""
+    from deepmimic_mujoco_b200.env import DPVecEnv
+    pol = common.RefTrainedPolicy()
+    ref = pol.monitor_window(50)
+    n, horizon = 2048, 3000
+    env = DPVecEnv(n, motions=("walk",), seed=22, reward_mode=0, reset_mode=1, auto_reset=True)
+    obs = env.reset()
+    g = torch.Generator(device="cuda"); g.manual_seed(4)
+    sd = torch.as_tensor(pol.act_std, dtype=torch.float32, device="cuda")
+    first = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for t in range(horizon):
+        act = pol.torch_mean_action(obs) + sd * torch.randn(n, 28, device="cuda", generator=g)
+        obs, rew, done, info = env.step(act.contiguous())
+        new = (done != 0) & (first == 0)
+        first = torch.where(new, info["episode_length"].to(torch.int32), first)
+        if t % 100 == 99 and bool((first > 0).all()):
+            break
+    still_up = int((first == 0).sum())
+    first = torch.where(first == 0, torch.full_like(first, horizon), first)   # censored at the horizon (oracle: < 0.1 %)
+    lens = first.cpu().numpy().astype(np.float64)
+    env.close()
+    assert still_up <= n // 100, f"{still_up} envs still up after {horizon} steps"
+    assert lens.mean() > 5 * common.ref_fall_lengths(100).mean()
+    assert common.trained_policy_verdict(lens, ref), (lens.mean(), np.percentile(lens, [25, 50, 75]), ref.mean(),
+                                                      np.percentile(ref, [25, 50, 75]))

@@ -234,6 +234,44 @@ def test_fall_time_distribution_matches_reference_monitor_log():
     assert np.abs(np.percentile(lens, [25, 50, 75]) - np.percentile(ref, [25, 50, 75])).max() <= 3.0
 
 
+
+def test_trained_policy_survival_matches_reference_monitor_log():
+    """The reference ships the policy its TRPO run trained IN MuJoCo 2.0 (checkpoint_tmp/.../trpo-walk-0, read without
+    TensorFlow by tests/golden/make_ref_policy_golden.py; its logstd reproduces the entropy logged by update 1899 to
+    1e-5, which dates the file) and the monitor rows of the episodes that policy played.  A random policy falls after
+    ~35 steps; this one keeps the MuJoCo humanoid up for ~290 (mean of the 100 episodes around the save, median 246,
+    heavy tail).  The same weights under the same protocol (trpo.py:27-80: reset_model_init, stochastic actions,
+    done on CoM height) must keep the ORACLE's humanoid up for as long: mean, median and lower quartile within 20 %,
+    Kolmogorov-Smirnov not rejecting at 1 % (measured with 4500 episodes over 3 seeds: mean 278 = -4 %, median 238 =
+    -3 %, KS p 0.4-0.8 on 200-episode samples).  tools/trained_policy_sensitivity.py shows what this resolves that
+    the random-policy test cannot: actuator gear x 0.8 / x 1.25 (+32 % / -36 %), timestep x 0.8 / x 1.25."""
+    mt, o = common.tables(), make()
+    pol = common.RefTrainedPolicy()
+    ref = pol.monitor_window(50)
+    assert len(ref) == 100 and 250 < ref.mean() < 330
+    rng = np.random.default_rng(5)
+    lens = []
+    for ep in range(250):
+        o.set_state(mt.qpos0 + rng.uniform(-0.01, 0.01, mt.nq), rng.uniform(-0.01, 0.01, mt.nv))
+        for t in range(3000):
+            ob = np.concatenate([o.qpos[7:], o.qvel[6:]])               # _get_obs, dp_env_v3.py:62-65
+            o.d.arr("ctrl")[:mt.nu] = pol.mean_action(ob[None])[0] + pol.act_std * rng.normal(size=mt.nu)
+            o.step()
+            z = o.d.arr("com")[2]
+            if z < 0.7 or z > 2.0:
+                break
+        lens.append(t + 1)
+    lens = np.asarray(lens, dtype=np.float64)
+    assert lens.mean() > 5 * common.ref_fall_lengths(100).mean()        # nothing like the random policy's 35 steps
+    assert common.trained_policy_verdict(lens, ref), (lens.mean(), np.percentile(lens, [25, 50, 75]), ref.mean(),
+                                                      np.percentile(ref, [25, 50, 75]))
+    import torch                                                         # the torch form the GPU test uses
+    x = rng.normal(size=(64, 56)) * 0.5
+    assert np.abs(pol.torch_mean_action(torch.as_tensor(x, dtype=torch.float32)).numpy() - pol.mean_action(x)).max() < 1e-4
+    wide = pol.monitor_window(100)                                       # and against the wider window of the log
+    assert abs(lens.mean() / wide.mean() - 1.0) < 0.2 and abs(np.median(lens) / np.median(wide) - 1.0) < 0.2
+
+
 def test_ref_aux_matches_independent_numpy():
     """Reference-pose features (end effectors in the heading frame, CoM velocity): the oracle's C routine
     vs the product's host numpy implementation (independent code paths)."""

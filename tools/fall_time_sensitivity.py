@@ -60,11 +60,7 @@ def variant(**kw):
     return m
 
 
-print(f"reference (first 100 episodes): mean {ref.mean():.2f} sd {ref.std():.2f} quartiles {np.percentile(ref, [25, 50, 75])}")
-print(f"{EPISODES} oracle episodes per variant")
-print(f"{'as shipped':34s}", verdict(run(common.model())))
-print(f"{'as shipped, another seed':34s}", verdict(run(common.model(), seed=11)))
-cases = [
+CASES = [
     ("gravity x 0.8", dict(gravity=lambda v, i, j: 0.8 * v)),
     ("gravity x 1.25", dict(gravity=lambda v, i, j: 1.25 * v)),
     ("actuator gear x 0.5", dict(act_gear=lambda v, i, j: 0.5 * v)),
@@ -78,8 +74,19 @@ cases = [
     ("no joint limits", dict(jnt_limited=lambda v, i, j: 0)),
     ("no contacts (0 pairs)", dict(npair=lambda v, i, j: 0)),
 ]
-for name, kw in cases:
-    print(f"{name:34s}", verdict(run(variant(**kw))))
-print(f"{'termination height 0.6':34s}", verdict(run(common.model(), z_min=0.6)))
-print(f"{'termination height 0.8':34s}", verdict(run(common.model(), z_min=0.8)))
-print(f"{'action sd 0.25 (not the init policy)':34s}", verdict(run(common.model(), act_sd=0.25)))
+
+
+def main():
+    print(f"reference (first 100 episodes): mean {ref.mean():.2f} sd {ref.std():.2f} quartiles {np.percentile(ref, [25, 50, 75])}")
+    print(f"{EPISODES} oracle episodes per variant")
+    print(f"{'as shipped':34s}", verdict(run(common.model())))
+    print(f"{'as shipped, another seed':34s}", verdict(run(common.model(), seed=11)))
+    for name, kw in CASES:
+        print(f"{name:34s}", verdict(run(variant(**kw))))
+    print(f"{'termination height 0.6':34s}", verdict(run(common.model(), z_min=0.6)))
+    print(f"{'termination height 0.8':34s}", verdict(run(common.model(), z_min=0.8)))
+    print(f"{'action sd 0.25 (not the init policy)':34s}", verdict(run(common.model(), act_sd=0.25)))
+
+
+if __name__ == "__main__":
+    main()
