@@ -40,6 +40,12 @@ class RunningMeanStd:
         self.mean.copy_(mean)
         self.std.copy_(torch.sqrt(torch.clamp((self.sumsq / self.count).float() - mean * mean, min=1e-2)))
 
+    def load(self, total, sumsq, count):
+        """Overwrite the accumulators (e.g. with ``obfilter/runningsum|runningsumsq|count`` of a reference checkpoint)."""
+        as64 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), device=self.sum.device)
+        self.sum.copy_(as64(total)); self.sumsq.copy_(as64(sumsq)); self.count.copy_(as64(count))
+        self._refresh()
+
     def update(self, x: torch.Tensor, group=None):
         x = x.reshape(-1, x.shape[-1]).double()
         add = torch.cat([x.sum(0), (x * x).sum(0), torch.tensor([x.shape[0]], dtype=torch.float64, device=x.device)])
@@ -82,6 +88,23 @@ class MlpPolicy:
                                           C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         self.seed = seed
         self.step_count = 0
+
+    def load_arrays(self, arrays) -> None:
+        """Overwrite parameters and the observation filter from host arrays named as in ``self.params`` plus
+        ``ob_sum`` / ``ob_sumsq`` / ``ob_count`` (tf_checkpoint.policy_arrays); shapes must match this policy."""
+        for k, t in self.params.items():
+            a = torch.as_tensor(np.asarray(arrays[k], dtype=np.float32))
+            if tuple(a.shape) != tuple(t.shape):
+                raise ValueError(f"{k}: checkpoint shape {tuple(a.shape)} != policy shape {tuple(t.shape)}")
+            t.copy_(a)                                           # in place: pointers held by a learner stay valid
+        self.ob_rms.load(arrays["ob_sum"], arrays["ob_sumsq"], arrays["ob_count"])
+
+    def load_tf_checkpoint(self, prefix: str, scope: str = "pi") -> None:
+        """Restore a policy saved by the reference (``U.load_state(load_model_path)``, trpo.py:207-208 / 367):
+        ``prefix`` is the TensorFlow checkpoint path the reference's ``--load_model_path`` takes, ``scope`` the
+        variable scope of the policy ("pi"; the checkpoint also holds TRPO's "oldpi").  No TensorFlow needed."""
+        from .tf_checkpoint import policy_arrays, read_checkpoint
+        self.load_arrays(policy_arrays(read_checkpoint(prefix), scope))
 
     def _struct(self) -> DmbPolicy:
         p = self.params

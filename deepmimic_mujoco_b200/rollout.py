@@ -88,3 +88,32 @@ class SegmentGenerator:
         nextvpred = nextvpred * (1.0 - self.cur_new)   # trpo.py:56
         return {"ob": self.ob, "ac": self.ac, "rew": self.rew, "vpred": self.vpred, "new": self.new,
                 "nextvpred": nextvpred, "ep_rets": ret_hist[done_hist], "ep_lens": len_hist[done_hist]}
+
+
+def evaluate(pi, env, horizon: int = 1024, stochastic: bool = False) -> Dict[str, torch.Tensor]:
+    """The reference's evaluate task (/root/reference/src/trpo.py:356-393 ``runner`` over trpo.py:397-436
+    ``traj_1_generator``) for all N envs at once: every env plays ONE trajectory from a fresh reset with
+    ``pi.act(stochastic, ob)`` until it is done or has made ``horizon + 1`` steps (the reference's ``t >= horizon``
+    break comes after the step).  ``env`` is a DPVecEnv built with ``reset_mode=1`` (the reference calls
+    ``reset_model_init`` before each trajectory) and ``auto_reset=True``; an env that has finished keeps stepping
+    (its later episodes are ignored), so the loop stays one launch per step with no host round trip except a
+    completion check every 64 steps.  Returns ``ep_len`` [N] int32, ``ep_ret`` [N] float32, ``finished`` [N] bool
+    (False: cut by the horizon) and the reference's two printed numbers ``avg_len`` / ``avg_ret`` (0-d tensors)."""
+    ob = env.reset()
+    n = ob.shape[0]
+    ep_len = torch.zeros(n, dtype=torch.int32, device=ob.device)
+    ep_ret = torch.zeros(n, dtype=torch.float32, device=ob.device)
+    running = torch.ones(n, dtype=torch.bool, device=ob.device)
+    finished = torch.zeros(n, dtype=torch.bool, device=ob.device)
+    for t in range(int(horizon) + 1):
+        ac, _ = pi.act(stochastic, ob)
+        ob, rew, done, _ = env.step(ac)
+        ep_len += running.to(torch.int32)
+        ep_ret += torch.where(running, rew, torch.zeros_like(rew))
+        ended = running & (done != 0)
+        finished |= ended
+        running = running & ~ended
+        if t % 64 == 63 and not bool(running.any()):
+            break
+    return {"ep_len": ep_len, "ep_ret": ep_ret, "finished": finished,
+            "avg_len": ep_len.double().mean(), "avg_ret": ep_ret.double().mean()}

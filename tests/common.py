@@ -124,13 +124,13 @@ class RefTrainedPolicy:
 
     def __init__(self):
         g = np.load(os.path.join(GOLDEN, "ref_trained_policy.npz"))
-        cnt = g["pi_obfilter_count"]
-        self.ob_mean = (g["pi_obfilter_runningsum"] / cnt).astype(np.float32).astype(np.float64)
-        var = (g["pi_obfilter_runningsumsq"] / cnt).astype(np.float32).astype(np.float64) - self.ob_mean ** 2
+        cnt = g["pi/obfilter/count"]
+        self.ob_mean = (g["pi/obfilter/runningsum"] / cnt).astype(np.float32).astype(np.float64)
+        var = (g["pi/obfilter/runningsumsq"] / cnt).astype(np.float32).astype(np.float64) - self.ob_mean ** 2
         self.ob_std = np.sqrt(np.maximum(var, 1e-2))                      # utils/misc_util.py:53-54
-        self.layers = [(g[f"pi_{n}_w"].astype(np.float64), g[f"pi_{n}_b"].astype(np.float64))
+        self.layers = [(g[f"pi/{n}/w"].astype(np.float64), g[f"pi/{n}/b"].astype(np.float64))
                        for n in ("polfc1", "polfc2", "polfinal")]
-        self.act_std = np.exp(g["pi_logstd"][0].astype(np.float64))
+        self.act_std = np.exp(g["pi/logstd"][0].astype(np.float64))
         self._lens = g["monitor_last_lengths"].astype(np.float64)
         self._k = int(g["checkpoint_index"])
 

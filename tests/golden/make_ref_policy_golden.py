@@ -7,99 +7,30 @@ episode monitor of that same run (src/log_tmp/DeepMimic/trpo-walk-0/monitor.json
 The checkpoint holds a policy that MuJoCo 2.0 itself shaped: under the reference's protocol (trpo.py:27-80) it keeps
 the humanoid up for ~270 steps where a random policy falls after ~35.  How long the SAME weights keep the humanoid up in
 another implementation of the dynamics is therefore a pin of that implementation against MuJoCo
-(tests/test_oracle_physics.py::test_trained_policy_survival_matches_reference_monitor_log, tests/test_gpu_reference_log.py).
+(tests/test_oracle_physics.py::test_trained_policy_survival_matches_reference_monitor_log, tests/test_z_gpu_reference_log.py).
 
-TensorFlow is not installed here, so the V2 checkpoint ("tensor bundle") is read directly: the .index file is an
-uncompressed LevelDB-format table (prefix-compressed keys, varint lengths, a 48-byte footer with the index-block
-handle) whose values are BundleEntryProto messages (dtype, shape, offset, size); the .data file is the raw tensors.
+TensorFlow is not installed here, so the V2 checkpoint ("tensor bundle") is read directly by
+deepmimic_mujoco_b200/tf_checkpoint.py (LevelDB-format index table of BundleEntryProto values + raw tensor file).
 Network (mlp_policy_trpo.py:24-60): obz = clip((ob - mean) / std, -5, 5) with the RunningMeanStd of
 utils/misc_util.py (sum, sumsq, count; std = sqrt(max(sumsq/count - mean^2, 1e-2))), two tanh layers of 100, a linear
 head of 28, and a state-independent logstd; the action is mean + exp(logstd) * N(0, 1).
 Run in the build container only."""
 import csv
 import os
-import struct
+import sys
 
 import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from deepmimic_mujoco_b200.tf_checkpoint import read_checkpoint  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CKPT = "/root/reference/src/checkpoint_tmp/DeepMimic/trpo-walk-0/DeepMimic/trpo-walk-0"
 LOG = "/root/reference/src/log_tmp/DeepMimic/trpo-walk-0"
-TABLE_MAGIC = 0xDB4775248B80FB57
-
-
-def varint(b, p):
-    x = s = 0
-    while True:
-        c = b[p]; p += 1
-        x |= (c & 0x7F) << s
-        if c < 0x80:
-            return x, p
-        s += 7
-
-
-def read_block(b, off, size):
-    """Entries of one table block: (shared, non_shared, value_len, key suffix, value)*, restart array, count."""
-    blk = b[off: off + size]
-    assert b[off + size] == 0, "compressed table block (expected kNoCompression)"
-    nrestart = struct.unpack("<I", blk[-4:])[0]
-    end = len(blk) - 4 - 4 * nrestart
-    p, key, out = 0, b"", []
-    while p < end:
-        shared, p = varint(blk, p)
-        non_shared, p = varint(blk, p)
-        vlen, p = varint(blk, p)
-        key = key[:shared] + blk[p: p + non_shared]; p += non_shared
-        out.append((key, blk[p: p + vlen])); p += vlen
-    return out
-
-
-def parse_proto(b):
-    """Flat protobuf decode: {field: [values]} with varints as int and length-delimited fields as bytes."""
-    p, out = 0, {}
-    while p < len(b):
-        tag, p = varint(b, p)
-        f, wt = tag >> 3, tag & 7
-        if wt == 0:
-            v, p = varint(b, p)
-        elif wt == 2:
-            n, p = varint(b, p); v = b[p: p + n]; p += n
-        elif wt == 5:
-            v = struct.unpack("<I", b[p: p + 4])[0]; p += 4
-        elif wt == 1:
-            v = struct.unpack("<Q", b[p: p + 8])[0]; p += 8
-        else:
-            raise ValueError(f"wire type {wt}")
-        out.setdefault(f, []).append(v)
-    return out
-
-
-def read_bundle(prefix):
-    idx = open(prefix + ".index", "rb").read()
-    data = open(prefix + ".data-00000-of-00001", "rb").read()
-    assert struct.unpack("<Q", idx[-8:])[0] == TABLE_MAGIC
-    foot = idx[-48:]
-    _, p = varint(foot, 0); _, p = varint(foot, p)              # metaindex handle
-    ioff, p = varint(foot, p); isz, p = varint(foot, p)          # index handle
-    tensors = {}
-    for _, handle in read_block(idx, ioff, isz):
-        off, q = varint(handle, 0); sz, q = varint(handle, q)
-        for key, val in read_block(idx, off, sz):
-            if not key:
-                continue                                         # BundleHeaderProto
-            e = parse_proto(val)
-            dtype = e.get(1, [0])[0]
-            shape = [parse_proto(d).get(1, [0])[0] for d in parse_proto(e[2][0]).get(2, [])] if 2 in e else []
-            o, n = e.get(4, [0])[0], e.get(5, [0])[0]
-            np_dt = {1: np.float32, 2: np.float64}[dtype]        # DT_FLOAT, DT_DOUBLE
-            a = np.frombuffer(data[o: o + n], dtype=np_dt).reshape(shape)
-            assert a.nbytes == n
-            tensors[key.decode()] = a
-    return tensors
 
 
 def main():
-    t = read_bundle(CKPT)
+    t = read_checkpoint(CKPT)
     total = sum(a.nbytes for a in t.values())
     assert total == os.path.getsize(CKPT + ".data-00000-of-00001") == 278264
     pi = {k[3:]: v for k, v in t.items() if k.startswith("pi/")}
@@ -120,7 +51,7 @@ def main():
     # episodes after it by slightly newer ones (max_kl 0.01 per update; 2-3 episodes per update).
     assert len(prog) == 1942
     k_ckpt = int(np.searchsorted(t_mon, float(prog[1899]["TimeElapsed"])))
-    out = {("pi_" + k.replace("/", "_")): v for k, v in pi.items()}
+    out = {"pi/" + k: v for k, v in pi.items()}                  # keys = the TensorFlow variable names
     out["monitor_last_lengths"] = lens[-400:]                    # the episodes of the last ~110 k steps of training
     out["checkpoint_index"] = np.int32(k_ckpt - (len(lens) - 400))  # position of the save inside monitor_last_lengths
     out["progress_last_eplenmean"] = np.asarray([float(p["EpLenMean"]) for p in prog[-50:]])

@@ -135,3 +135,36 @@ def test_segment_generator_shapes_and_bookkeeping():
     seg2 = next(gen)
     assert not seg2["new"][0].all()
     env.close()
+
+
+def test_evaluate_counts_first_episodes_like_traj_1_generator():
+    """rollout.evaluate (the batched runner / traj_1_generator of trpo.py:356-436) on stub env + policy objects (CPU):
+    every env's FIRST episode is counted, later auto-reset episodes are ignored, the horizon cut happens after
+    horizon + 1 steps as in the reference (`if new or t >= horizon: break` follows the step)."""
+    from deepmimic_mujoco_b200.rollout import evaluate
+
+    class Env:
+        def __init__(self, ends):
+            self.ends, self.t = torch.tensor(ends), 0          # env i is done at steps ends[i], 2 ends[i], ...
+        def reset(self):
+            self.t = 0
+            return torch.zeros(len(self.ends), 4)
+        def step(self, ac):
+            self.t += 1
+            done = ((self.t % self.ends) == 0).to(torch.uint8)
+            return torch.full((len(self.ends), 4), float(self.t)), torch.full((len(self.ends),), 0.5), done, {}
+
+    class Pi:
+        calls = 0
+        def act(self, stochastic, ob):
+            Pi.calls += 1
+            return torch.zeros(ob.shape[0], 2), torch.zeros(ob.shape[0])
+
+    out = evaluate(Pi(), Env([3, 10, 64, 500]), horizon=99, stochastic=True)
+    assert out["ep_len"].tolist() == [3, 10, 64, 100]              # the last env is cut after horizon + 1 steps
+    assert out["finished"].tolist() == [True, True, True, False]
+    assert torch.allclose(out["ep_ret"], torch.tensor([1.5, 5.0, 32.0, 50.0]))
+    assert abs(float(out["avg_len"]) - 177 / 4) < 1e-12 and Pi.calls == 100
+    Pi.calls = 0
+    out = evaluate(Pi(), Env([3, 10, 20]), horizon=1000)
+    assert out["ep_len"].tolist() == [3, 10, 20] and Pi.calls == 64  # stops at the first completion check

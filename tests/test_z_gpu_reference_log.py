@@ -3,7 +3,9 @@ run (tests/golden/ref_episode_lengths.json, made by tests/golden/make_ref_episod
 trained in MuJoCo (tests/golden/ref_trained_policy.npz, made by tests/golden/make_ref_policy_golden.py).  Same protocol as the
 rows were recorded with (trpo.py:27-80): standing pose +- 0.01 (reset_model_init, dp_env_v3.py:158-164), N(0,1)
 actions of the freshly initialised Gaussian policy clamped to the ctrlrange, reward 1.0 per step, done when the CoM
-height leaves [0.7, 2.0].  tests/test_oracle_physics.py holds the same check for the float64 oracle."""
+height leaves [0.7, 2.0].  tests/test_oracle_physics.py holds the same checks for the float64 oracle.
+(The file name sorts last on purpose: the trained-policy tests were written after round 2's GPU minutes were spent,
+so the driver's round-end run is their first on hardware; under `pytest -x` they must not mask the other files.)"""
 import numpy as np
 import pytest
 import torch
@@ -69,3 +71,31 @@ def test_trained_policy_survival_matches_reference_monitor_log():
     assert lens.mean() > 5 * common.ref_fall_lengths(100).mean()
     assert common.trained_policy_verdict(lens, ref), (lens.mean(), np.percentile(lens, [25, 50, 75]), ref.mean(),
                                                       np.percentile(ref, [25, 50, 75]))
+
+
+def test_reference_checkpoint_through_the_fused_policy_kernel_and_evaluate():
+    """The same pin through the product's own rollout pieces: the checkpoint's tensors loaded into MlpPolicy
+    (tf_checkpoint.policy_arrays -> load_arrays), actions sampled by the fused policy kernel (Philox noise), the
+    batched evaluate task (rollout.evaluate = trpo.py:356-436) with the stochastic policy."""
+    from deepmimic_mujoco_b200.env import DPVecEnv
+    from deepmimic_mujoco_b200.policy import MlpPolicy
+    from deepmimic_mujoco_b200.rollout import evaluate
+    from deepmimic_mujoco_b200.tf_checkpoint import policy_arrays
+    import os
+    g = np.load(os.path.join(common.GOLDEN, "ref_trained_policy.npz"))
+    ref = common.RefTrainedPolicy()
+    n = 2048
+    env = DPVecEnv(n, motions=("walk",), seed=23, reward_mode=0, reset_mode=1, auto_reset=True)
+    pi = MlpPolicy(seed=5)
+    pi.load_arrays(policy_arrays({k: g[k] for k in g.files if k.startswith("pi/")}, "pi"))
+    x = torch.randn(64, 56, device="cuda") * 0.5                           # the loaded network is the checkpoint's
+    mean = torch.empty(64, 28, device="cuda")
+    pi.act(False, x, out_mean=mean)
+    assert np.abs(mean.cpu().numpy() - ref.mean_action(x.cpu().numpy())).max() < 1e-4
+    out = evaluate(pi, env, horizon=3000, stochastic=True)
+    lens = out["ep_len"].cpu().numpy().astype(np.float64)
+    cut = int((~out["finished"]).sum())
+    env.close()
+    assert cut <= n // 100, f"{cut} envs still up after 3000 steps"
+    assert np.array_equal(out["ep_ret"].cpu().numpy(), lens.astype(np.float32))     # reward 1.0 per step
+    assert common.trained_policy_verdict(lens, ref.monitor_window(50)), (lens.mean(), np.percentile(lens, [25, 50, 75]))
