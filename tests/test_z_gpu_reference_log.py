@@ -14,18 +14,20 @@ import common
 
 pytestmark = pytest.mark.gpu
 
+DEVICE, N_ENVS = "cuda", 2048      # tools/dry_run_gpu_reference_tests.py overrides these (CPU stand-ins, fewer envs)
+
 
 def test_fall_time_distribution_matches_reference_monitor_log():
     from scipy import stats
     from deepmimic_mujoco_b200.env import DPVecEnv
     ref = common.ref_fall_lengths(100)
-    n = 2048
+    n = N_ENVS
     env = DPVecEnv(n, motions=("walk",), seed=21, reward_mode=0, reset_mode=1, auto_reset=True)
     env.reset()
-    g = torch.Generator(device="cuda"); g.manual_seed(3)
-    first = torch.zeros(n, dtype=torch.int32, device="cuda")          # length of every env's FIRST episode (no
+    g = torch.Generator(device=DEVICE); g.manual_seed(3)
+    first = torch.zeros(n, dtype=torch.int32, device=DEVICE)          # length of every env's FIRST episode (no
     for t in range(400):                                              # window bias towards short episodes)
-        obs, rew, done, info = env.step(torch.randn(n, 28, device="cuda", generator=g))
+        obs, rew, done, info = env.step(torch.randn(n, 28, device=DEVICE, generator=g))
         new = (done != 0) & (first == 0)
         first = torch.where(new, info["episode_length"].to(torch.int32), first)
         if t > 20 and bool((first > 0).all()):
@@ -50,14 +52,14 @@ def test_trained_policy_survival_matches_reference_monitor_log():
     from deepmimic_mujoco_b200.env import DPVecEnv
     pol = common.RefTrainedPolicy()
     ref = pol.monitor_window(50)
-    n, horizon = 2048, 3000
+    n, horizon = N_ENVS, 3000
     env = DPVecEnv(n, motions=("walk",), seed=22, reward_mode=0, reset_mode=1, auto_reset=True)
     obs = env.reset()
-    g = torch.Generator(device="cuda"); g.manual_seed(4)
-    sd = torch.as_tensor(pol.act_std, dtype=torch.float32, device="cuda")
-    first = torch.zeros(n, dtype=torch.int32, device="cuda")
+    g = torch.Generator(device=DEVICE); g.manual_seed(4)
+    sd = torch.as_tensor(pol.act_std, dtype=torch.float32, device=DEVICE)
+    first = torch.zeros(n, dtype=torch.int32, device=DEVICE)
     for t in range(horizon):
-        act = pol.torch_mean_action(obs) + sd * torch.randn(n, 28, device="cuda", generator=g)
+        act = pol.torch_mean_action(obs) + sd * torch.randn(n, 28, device=DEVICE, generator=g)
         obs, rew, done, info = env.step(act.contiguous())
         new = (done != 0) & (first == 0)
         first = torch.where(new, info["episode_length"].to(torch.int32), first)
@@ -84,12 +86,12 @@ def test_reference_checkpoint_through_the_fused_policy_kernel_and_evaluate():
     import os
     g = np.load(os.path.join(common.GOLDEN, "ref_trained_policy.npz"))
     ref = common.RefTrainedPolicy()
-    n = 2048
+    n = N_ENVS
     env = DPVecEnv(n, motions=("walk",), seed=23, reward_mode=0, reset_mode=1, auto_reset=True)
     pi = MlpPolicy(seed=5)
     pi.load_arrays(policy_arrays({k: g[k] for k in g.files if k.startswith("pi/")}, "pi"))
-    x = torch.randn(64, 56, device="cuda") * 0.5                           # the loaded network is the checkpoint's
-    mean = torch.empty(64, 28, device="cuda")
+    x = torch.randn(64, 56, device=DEVICE) * 0.5                           # the loaded network is the checkpoint's
+    mean = torch.empty(64, 28, device=DEVICE)
     pi.act(False, x, out_mean=mean)
     assert np.abs(mean.cpu().numpy() - ref.mean_action(x.cpu().numpy())).max() < 1e-4
     out = evaluate(pi, env, horizon=3000, stochastic=True)
