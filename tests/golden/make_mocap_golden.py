@@ -79,6 +79,19 @@ def main():
                             data=np.asarray(m.data), data_config=np.asarray(m.data_config),
                             data_vel=np.asarray(m.data_vel), durations=np.asarray(m.durations))
         print(clip, np.asarray(m.data_config).shape, np.asarray(m.data_vel).shape, m.dt)
+    # the other ten clips the reference ships: a digest instead of the full tables (every 5th frame + the last one of
+    # data_config / data_vel, and float64 column sums over ALL frames), tests/golden/mocap_digest.npz
+    digest = {}
+    for clip in ("cartwheel", "crawl", "dance_a", "getup_facedown", "getup_faceup", "jump", "kick", "punch", "roll", "spin"):
+        m = MocapDM()
+        m.load_mocap(os.path.join(REF_SRC, "mujoco/motions/humanoid3d_%s.txt" % clip))
+        cfg, vel = np.asarray(m.data_config), np.asarray(m.data_vel)
+        rows = np.unique(np.r_[np.arange(0, len(cfg), 5), len(cfg) - 1])
+        digest.update({clip + "/dt": np.float64(m.dt), clip + "/rows": rows, clip + "/cfg_rows": cfg[rows],
+                       clip + "/vel_rows": vel[rows], clip + "/cfg_colsum": cfg.sum(0), clip + "/vel_colsum": vel.sum(0),
+                       clip + "/cfg_abssum": np.abs(cfg).sum(0), clip + "/nframes": np.int64(len(cfg))})
+        print(clip, cfg.shape, m.dt)
+    np.savez_compressed(os.path.join(HERE, "mocap_digest.npz"), **digest)
     # known answers from transformations.py doctests (lines 1092-1093, 1106-1107, 1231-1232)
     kat = dict(
         euler_from_quaternion=np.array(T.euler_from_quaternion([0.06146124, 0, 0, 0.99810947])),

@@ -23,6 +23,24 @@ def test_against_reference_loader(name):
     assert np.all(c.data_vel[0] == 0.0)  # frame 0 has zero velocity (mocap_v2.py:100,110)
 
 
+OTHER_CLIPS = ("cartwheel", "crawl", "dance_a", "getup_facedown", "getup_faceup", "jump", "kick", "punch", "roll", "spin")
+
+
+@pytest.mark.parametrize("name", OTHER_CLIPS)
+def test_remaining_clips_against_reference_loader_digest(name):
+    """The other ten clips the reference ships (src/mujoco/motions/): every 5th frame and the last frame of the
+    reference loader's data_config / data_vel, and float64 column sums over all frames (mocap_digest.npz)."""
+    g = np.load(os.path.join(common.GOLDEN, "mocap_digest.npz"))
+    c = common.clip(name)
+    assert c.dt == float(g[name + "/dt"]) and len(c) == int(g[name + "/nframes"])
+    rows = g[name + "/rows"]
+    assert np.abs(c.data_config[rows] - g[name + "/cfg_rows"]).max() < 1e-12
+    assert np.abs(c.data_vel[rows] - g[name + "/vel_rows"]).max() < 1e-10
+    assert np.abs(c.data_config.sum(0) - g[name + "/cfg_colsum"]).max() < 1e-10
+    assert np.abs(np.abs(c.data_config).sum(0) - g[name + "/cfg_abssum"]).max() < 1e-10
+    assert np.abs(c.data_vel.sum(0) - g[name + "/vel_colsum"]).max() < 1e-8
+
+
 def test_survey_appendix_c_pins():
     walk0 = [0, -0, 0.847532, 0.998678, 0.014104, 0.049423, -0.000698, 0.019375, 0.008037255, -0.09523903, -0, 0, -0,
              -0.1555353, 0.2391943, 0.2073966, 0.170571, 0.3529632, -0.2610683, -0.2456053, 0.581348, 0.02035205,
