@@ -32,7 +32,7 @@ from __future__ import annotations
 
 import dataclasses
 import xml.etree.ElementTree as ET
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 import numpy as np
 

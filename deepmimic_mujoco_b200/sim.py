@@ -15,7 +15,7 @@ import torch
 
 from . import lib as _lib
 from .mjcf import ModelTables, load_tables
-from .mocap import Clip, MocapTables, concat_clips, load_clip
+from .mocap import MocapTables, concat_clips, load_clip
 from .model_blob import REF_AUX, DmbConfig, DmbMocap, DmbModel, default_config, pack_model
 
 ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")

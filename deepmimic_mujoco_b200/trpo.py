@@ -15,7 +15,7 @@ same arithmetic as the fused inference kernel (``dmb_policy_act``); a GPU test c
 from __future__ import annotations
 
 import math
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import Callable, Dict, List, Sequence
 
 import torch
 import torch.distributed as dist

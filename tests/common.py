@@ -1,7 +1,6 @@
 """Shared helpers for the test-suite: model/mocap loading, oracle wrappers, state generators."""
 from __future__ import annotations
 
-import ctypes as C
 import os
 import sys
 
