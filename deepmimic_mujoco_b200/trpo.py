@@ -99,6 +99,12 @@ def cg(f_Ax: Callable[[torch.Tensor], torch.Tensor], b: torch.Tensor, cg_iters: 
     return x
 
 
+def explained_variance(ypred: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """utils/math_util.py:25-38: 1 - Var[y - ypred] / Var[y] (population variance), NaN when Var[y] == 0."""
+    vary = y.var(unbiased=False)
+    return torch.where(vary == 0, torch.full_like(vary, float("nan")), 1.0 - (y - ypred).var(unbiased=False) / vary)
+
+
 class Adam:
     """mpi_adam.py:6-50 on a flat parameter view: the gradient is averaged over ranks, then plain Adam."""
 
@@ -209,4 +215,6 @@ class TRPO:
         with torch.no_grad():
             _, _, vp = policy_forward(P, self.pi.ob_rms.mean, self.pi.ob_rms.std, ob)
             stats["vferr"] = float(((vp - tdlamret) ** 2).mean())
+            if "vpred" in seg:                                            # trpo.py:298 (vpred before the update)
+                stats["ev_tdlam_before"] = float(explained_variance(seg["vpred"].detach().reshape(-1), tdlamret))
         return stats

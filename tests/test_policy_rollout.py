@@ -34,6 +34,19 @@ def test_gae_matches_reference_formula():
         assert np.abs(seg["tdlamret"][:, i].numpy() - ret).max() < 1e-5
 
 
+def test_gae_matches_the_reference_function_run_here():
+    """Golden advantages / TD(lambda) returns produced by the reference's own add_vtarg_and_adv (trpo.py:83-94, its
+    source lines executed unchanged: tests/golden/make_learner_golden.py), one env per column."""
+    import os
+    from deepmimic_mujoco_b200.rollout import add_vtarg_and_adv
+    g = np.load(os.path.join(common.GOLDEN, "learner_golden.npz"))
+    seg = dict(rew=torch.tensor(g["gae_rew"]), vpred=torch.tensor(g["gae_vpred"]),
+               new=torch.tensor(g["gae_new"].astype(np.float32)), nextvpred=torch.tensor(g["gae_nextvpred"]))
+    add_vtarg_and_adv(seg, float(g["gae_gamma"]), float(g["gae_lam"]))
+    assert np.abs(seg["adv"].numpy() - g["gae_adv"]).max() < 2e-6 * np.abs(g["gae_adv"]).max()
+    assert np.abs(seg["tdlamret"].numpy() - g["gae_tdlamret"]).max() < 2e-6 * np.abs(g["gae_tdlamret"]).max()
+
+
 def test_running_mean_std_semantics():
     pytest.importorskip("torch")
     if not torch.cuda.is_available():

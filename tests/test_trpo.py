@@ -32,6 +32,21 @@ def test_cg_solves_spd_system():
     assert np.abs(x.numpy() - np.linalg.solve(A, b)).max() < 1e-6   # stops at |r|^2 < 1e-10 like cg.py
 
 
+def test_cg_and_explained_variance_match_the_reference_routines_run_here():
+    """Golden vectors produced by the reference's own cg (cg.py:2-34, imported) and explained_variance
+    (utils/math_util.py:25-38, its source lines executed unchanged): tests/golden/make_learner_golden.py."""
+    g = np.load(os.path.join(common.GOLDEN, "learner_golden.npz"))
+    A, b = torch.tensor(g["cg_A"]), torch.tensor(g["cg_b"])
+    x10 = T.cg(lambda p: A @ p, b, cg_iters=10)                            # the reference's 10 iterations, unconverged
+    assert np.abs(x10.numpy() - g["cg_x10"]).max() < 1e-12 * max(1.0, np.abs(g["cg_x10"]).max())
+    x100 = T.cg(lambda p: A @ p, b, cg_iters=100)                          # early exit at residual_tol, as a mask here
+    assert np.abs(x100.numpy() - g["cg_x100"]).max() < 1e-9
+    ev = T.explained_variance(torch.tensor(g["ev_ypred"]), torch.tensor(g["ev_y"]))
+    assert abs(float(ev) - float(g["ev"])) < 1e-12
+    assert math.isnan(float(T.explained_variance(torch.tensor(g["ev_ypred"]), torch.ones(200, dtype=torch.float64))))
+    assert math.isnan(float(g["ev_const"]))
+
+
 def test_diag_gaussian_formulas():
     rng = np.random.default_rng(1)
     m0, m1 = torch.tensor(rng.normal(size=(4, 3))), torch.tensor(rng.normal(size=(4, 3)))
