@@ -77,14 +77,15 @@ class OracleSim:
 
 
 def install_shims():
+    """pyquaternion, mujoco_py and gym adapters (gym.core / gym.spaces come from tests/monitor_contract.py, so that the
+    reference's bench.Monitor can wrap the env as well)."""
+    from monitor_contract import install_gym_shim
+    gym = install_gym_shim()
+    Box = gym.spaces.Box
     pq = types.ModuleType("pyquaternion"); pq.Quaternion = Quaternion
     mj = types.ModuleType("mujoco_py"); mj.load_model_from_xml = mj.MjSim = mj.MjViewer = None
 
-    class Box:
-        def __init__(self, low, high, dtype=np.float32):
-            self.low, self.high, self.shape, self.dtype = np.asarray(low, dtype), np.asarray(high, dtype), np.shape(low), dtype
-
-    class MujocoEnv:
+    class MujocoEnv(gym.Env):
         def __init__(self, model_path, frame_skip):
             assert os.path.exists(model_path), model_path
             self.frame_skip = frame_skip
@@ -99,8 +100,8 @@ def install_shims():
             assert not done
             self.obs_dim = observation.size
             b = self.model.actuator_ctrlrange.copy()
-            self.action_space = Box(b[:, 0], b[:, 1])
-            self.observation_space = Box(-np.inf * np.ones(self.obs_dim), np.inf * np.ones(self.obs_dim))
+            self.action_space = Box(b[:, 0], b[:, 1], dtype=np.float32)
+            self.observation_space = Box(-np.inf * np.ones(self.obs_dim), np.inf * np.ones(self.obs_dim), dtype=np.float64)
 
         def seed(self, seed=None):
             self.np_random = np.random.RandomState(seed)
@@ -125,17 +126,22 @@ def install_shims():
             for _ in range(n_frames):
                 self.sim.step()
 
+        def render(self, *a, **k):
+            return None
+
+        def close(self):
+            pass
+
     class EzPickle:
         def __init__(self, *a, **k):
             pass
 
-    gym = types.ModuleType("gym")
     envs = types.ModuleType("gym.envs"); mjm = types.ModuleType("gym.envs.mujoco"); me = types.ModuleType("gym.envs.mujoco.mujoco_env")
-    utils = types.ModuleType("gym.utils"); spaces = types.ModuleType("gym.spaces")
-    me.MujocoEnv, utils.EzPickle, spaces.Box = MujocoEnv, EzPickle, Box
-    gym.envs, gym.utils, gym.spaces, envs.mujoco, mjm.mujoco_env = envs, utils, spaces, mjm, me
-    sys.modules.update({"pyquaternion": pq, "mujoco_py": mj, "gym": gym, "gym.envs": envs, "gym.envs.mujoco": mjm,
-                        "gym.envs.mujoco.mujoco_env": me, "gym.utils": utils, "gym.spaces": spaces})
+    utils = types.ModuleType("gym.utils")
+    me.MujocoEnv, utils.EzPickle = MujocoEnv, EzPickle
+    gym.envs, gym.utils, envs.mujoco, mjm.mujoco_env = envs, utils, mjm, me
+    sys.modules.update({"pyquaternion": pq, "mujoco_py": mj, "gym.envs": envs, "gym.envs.mujoco": mjm,
+                        "gym.envs.mujoco.mujoco_env": me, "gym.utils": utils})
 
 
 def main():
