@@ -106,6 +106,25 @@ class MlpPolicy:
         from .tf_checkpoint import policy_arrays, read_checkpoint
         self.load_arrays(policy_arrays(read_checkpoint(prefix), scope))
 
+    def host_arrays(self):
+        """Parameters and observation-filter accumulators as host numpy arrays (the dict ``load_arrays`` takes)."""
+        out = {k: t.detach().cpu().numpy() for k, t in self.params.items()}
+        out.update(ob_sum=self.ob_rms.sum.cpu().numpy(), ob_sumsq=self.ob_rms.sumsq.cpu().numpy(),
+                   ob_count=self.ob_rms.count.cpu().numpy())
+        return out
+
+    def save_tf_checkpoint(self, prefix: str, scopes=("pi", "oldpi")) -> None:
+        """Save in the reference's on-disk format (``U.save_state`` = ``tf.train.Saver().save``, trpo.py:220-224): a
+        TensorFlow V2 checkpoint holding this policy under every scope in ``scopes`` -- the reference's graph has the
+        policy twice, "pi" and TRPO's "oldpi" -- so that its ``--load_model_path`` / ``--pretrained_weight_path``
+        restore it."""
+        from .tf_checkpoint import policy_tensors, write_checkpoint, write_checkpoint_state
+        arrays, tensors = self.host_arrays(), {}
+        for sc in scopes:
+            tensors.update(policy_tensors(arrays, sc))
+        write_checkpoint(prefix, tensors)
+        write_checkpoint_state(prefix)
+
     def _struct(self) -> DmbPolicy:
         p = self.params
         s = DmbPolicy(self.obs_dim, self.act_dim, self.hid, 0, self.ob_rms.mean.data_ptr(), self.ob_rms.std.data_ptr())

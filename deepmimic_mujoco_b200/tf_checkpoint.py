@@ -17,6 +17,13 @@ path still has those files, so this module reads them directly:
 :func:`policy_arrays` maps the variables of one ``MlpPolicy`` scope (mlp_policy_trpo.py:24-60: ``polfc1/w`` ...
 ``vffinal/b``, ``logstd``, ``obfilter/runningsum|runningsumsq|count``) onto the parameter names of
 :class:`deepmimic_mujoco_b200.policy.MlpPolicy`; ``MlpPolicy.load_tf_checkpoint`` puts them on the device.
+
+:func:`write_checkpoint` is the other direction (a policy trained on the CUDA path handed back to the reference's
+``--task evaluate`` / ``--pretrained_weight_path``): it lays the files out the way TensorFlow's ``BundleWriter`` over the
+LevelDB table builder does -- keys sorted, restart point every 16 entries, one data block, an empty metaindex block, an
+index block keyed by the shortest successor of the last key, masked CRC32C in every block trailer and every entry --
+and is checked by regenerating the reference's own shipped ``.index`` and ``.data`` files byte for byte from the
+tensors read out of them (tests/test_tf_checkpoint.py).
 Host-side, load-time code: nothing here is on the hot path.
 """
 from __future__ import annotations
@@ -121,10 +128,129 @@ def read_checkpoint(prefix: str) -> Dict[str, np.ndarray]:
     return tensors
 
 
+def _crc_table():
+    tab = []
+    for i in range(256):
+        c = i
+        for _ in range(8):
+            c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+        tab.append(c)
+    return tab
+
+
+_CRC_TABLE = _crc_table()
+
+
+def crc32c(b: bytes, crc: int = 0) -> int:
+    """CRC-32C (Castagnoli), the checksum of LevelDB tables and tensor-bundle entries."""
+    crc ^= 0xFFFFFFFF
+    tab = _CRC_TABLE
+    for x in b:
+        crc = tab[(crc ^ x) & 0xFF] ^ (crc >> 8)
+    return crc ^ 0xFFFFFFFF
+
+
+def masked_crc32c(b: bytes) -> int:
+    c = crc32c(b)
+    return (((c >> 15) | (c << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def _vi(x: int) -> bytes:
+    out = bytearray()
+    while True:
+        c = x & 0x7F
+        x >>= 7
+        out.append(c | (0x80 if x else 0))
+        if not x:
+            return bytes(out)
+
+
+def _field(num: int, wire: int, payload: bytes) -> bytes:
+    return _vi((num << 3) | wire) + (_vi(len(payload)) + payload if wire == 2 else payload)
+
+
+def _table_block(entries, restart_interval: int = 16) -> bytes:
+    blk, restarts, prev = bytearray(), [], b""
+    for i, (k, v) in enumerate(entries):
+        shared = 0
+        if i % restart_interval == 0:
+            restarts.append(len(blk))
+        else:
+            while shared < min(len(k), len(prev)) and k[shared] == prev[shared]:
+                shared += 1
+        blk += _vi(shared) + _vi(len(k) - shared) + _vi(len(v)) + k[shared:] + v
+        prev = k
+    for r in restarts or [0]:
+        blk += struct.pack("<I", r)
+    return bytes(blk + struct.pack("<I", len(restarts or [0])))
+
+
+def _short_successor(key: bytes) -> bytes:
+    """LevelDB BytewiseComparator::FindShortSuccessor: cut after the first byte that can be incremented."""
+    for i, c in enumerate(key):
+        if c != 0xFF:
+            return key[:i] + bytes([c + 1])
+    return key
+
+
+def write_checkpoint(prefix: str, tensors: Dict[str, np.ndarray]) -> None:
+    """Write ``tensors`` (name -> float32 / float64 / int32 / int64 array) as a TensorFlow V2 checkpoint
+    ``<prefix>.index`` + ``<prefix>.data-00000-of-00001`` that ``tf.train.Saver().restore`` (the reference's
+    ``U.load_state``) reads; see the module docstring for the layout."""
+    enum = {np.dtype(v): k for k, v in _DTYPES.items()}
+    data = bytearray()
+    header = _field(1, 0, _vi(1)) + _field(3, 2, _field(1, 0, _vi(1)))     # num_shards 1, version {producer 1}
+    entries = [(b"", header)]
+    for name in sorted(tensors, key=lambda n: n.encode()):
+        a = np.asarray(tensors[name], order="C")
+        if a.dtype not in enum:
+            raise CheckpointError(f"variable {name}: dtype {a.dtype} is not supported")
+        raw = a.astype(a.dtype.newbyteorder("<"), copy=False).tobytes()
+        e = _field(1, 0, _vi(enum[a.dtype])) + _field(2, 2, b"".join(_field(2, 2, _field(1, 0, _vi(d))) for d in a.shape))
+        if len(data):
+            e += _field(4, 0, _vi(len(data)))
+        e += _field(5, 0, _vi(len(raw))) + _field(6, 5, struct.pack("<I", masked_crc32c(raw)))
+        entries.append((name.encode(), e))
+        data += raw
+    out = bytearray()
+
+    def emit(block: bytes):
+        off = len(out)
+        out.extend(block + b"\0" + struct.pack("<I", masked_crc32c(block + b"\0")))   # type 0 = no compression
+        return _vi(off) + _vi(len(block))
+
+    d_handle = emit(_table_block(entries))
+    m_handle = emit(_table_block([]))
+    i_handle = emit(_table_block([(_short_successor(entries[-1][0]), d_handle)]))
+    foot = m_handle + i_handle
+    out.extend(foot + b"\0" * (40 - len(foot)) + struct.pack("<Q", TABLE_MAGIC))
+    with open(prefix + ".index", "wb") as f:
+        f.write(bytes(out))
+    with open(prefix + ".data-00000-of-00001", "wb") as f:
+        f.write(bytes(data))
+
+
 # MlpPolicy parameter name <- reference variable name inside the policy scope (mlp_policy_trpo.py:35-46)
 _POLICY_VARS = dict(pw1="polfc1/w", pb1="polfc1/b", pw2="polfc2/w", pb2="polfc2/b", pw3="polfinal/w", pb3="polfinal/b",
                     vw1="vffc1/w", vb1="vffc1/b", vw2="vffc2/w", vb2="vffc2/b", vw3="vffinal/w", vb3="vffinal/b",
                     logstd="logstd")
+
+
+def policy_tensors(arrays: Dict[str, np.ndarray], scope: str = "pi") -> Dict[str, np.ndarray]:
+    """Inverse of :func:`policy_arrays`: MlpPolicy-named host arrays -> the reference's variables of one scope."""
+    out = {f"{scope}/{theirs}": np.asarray(arrays[mine], dtype=np.float32) for mine, theirs in _POLICY_VARS.items()}
+    out[f"{scope}/logstd"] = out[f"{scope}/logstd"].reshape(1, -1)          # mlp_policy_trpo.py:46: shape [1, act_dim]
+    for mine, theirs in (("ob_sum", "runningsum"), ("ob_sumsq", "runningsumsq"), ("ob_count", "count")):
+        out[f"{scope}/obfilter/{theirs}"] = np.asarray(arrays[mine], dtype=np.float64)
+    return out
+
+
+def write_checkpoint_state(prefix: str) -> None:
+    """The ``checkpoint`` file tf.train.Saver writes next to the data (for ``tf.train.latest_checkpoint``)."""
+    import os
+    name = os.path.basename(prefix)
+    with open(os.path.join(os.path.dirname(prefix) or ".", "checkpoint"), "w") as f:
+        f.write(f'model_checkpoint_path: "{name}"\nall_model_checkpoint_paths: "{name}"\n')
 
 
 def policy_arrays(tensors: Dict[str, np.ndarray], scope: str = "pi") -> Dict[str, np.ndarray]:

@@ -1,13 +1,13 @@
 """deepmimic_mujoco_b200/tf_checkpoint.py: reading the reference's saved policies (tf.train.Saver V2 checkpoints,
 utils/tf_util.py:314-329, trpo.py:207-208 / 220-224 / 367) without TensorFlow.
 
-* a bundle written by this test (LevelDB-format table with prefix compression and restart points, BundleEntryProto
-  values) round-trips through the reader;
+* write_checkpoint regenerates the reference's shipped .index / .data / checkpoint files BYTE FOR BYTE from the tensors
+  read out of them (table layout, restart points, shortest-successor index key, masked CRC32C of blocks and entries);
+* a bundle written by write_checkpoint round-trips through the reader;
 * the checkpoint the reference ships (checkpoint_tmp/DeepMimic/trpo-walk-0) reads to exactly the tensors committed
   in tests/golden/ref_trained_policy.npz (build container only: /root/reference is not on the GPU box);
 * the variable-name mapping onto policy.MlpPolicy and its shape checks; malformed files raise CheckpointError."""
 import os
-import struct
 
 import numpy as np
 import pytest
@@ -19,62 +19,18 @@ from deepmimic_mujoco_b200 import tf_checkpoint as tfc
 REF_CKPT = "/root/reference/src/checkpoint_tmp/DeepMimic/trpo-walk-0/DeepMimic/trpo-walk-0"
 
 
-def _vi(x):
-    out = bytearray()
-    while True:
-        c = x & 0x7F
-        x >>= 7
-        out.append(c | (0x80 if x else 0))
-        if not x:
-            return bytes(out)
-
-
-def _pb(field, wire, payload):
-    return _vi((field << 3) | wire) + (payload if wire != 2 else _vi(len(payload)) + payload)
-
-
-def _table_block(entries, restart_every=4):
-    blk, restarts, prev = bytearray(), [], b""
-    for i, (k, v) in enumerate(entries):
-        shared = 0
-        if i % restart_every == 0:
-            restarts.append(len(blk))
-        else:
-            while shared < min(len(k), len(prev)) and k[shared] == prev[shared]:
-                shared += 1
-        blk += _vi(shared) + _vi(len(k) - shared) + _vi(len(v)) + k[shared:] + v
-        prev = k
-    if not restarts:
-        restarts = [0]
-    for r in restarts:
-        blk += struct.pack("<I", r)
-    return bytes(blk + struct.pack("<I", len(restarts)))
-
-
 def write_bundle(prefix, tensors, compressed_tag=0):
-    """Minimal tensor-bundle writer (one data block, one shard), the inverse of tf_checkpoint.read_checkpoint."""
-    enum = {np.dtype(np.float32): 1, np.dtype(np.float64): 2, np.dtype(np.int32): 3, np.dtype(np.int64): 9}
-    data, entries = bytearray(), [(b"", _pb(1, 0, _vi(1)))]                # "" -> BundleHeaderProto{num_shards: 1}
-    for name in sorted(tensors):
-        a = np.asarray(tensors[name], order="C")              # (ascontiguousarray would turn 0-d into 1-d)
-        shape = b"".join(_pb(2, 2, _pb(1, 0, _vi(d))) for d in a.shape)
-        e = _pb(1, 0, _vi(enum[a.dtype])) + _pb(2, 2, shape)
-        if len(data):
-            e += _pb(4, 0, _vi(len(data)))
-        e += _pb(5, 0, _vi(a.nbytes)) + _pb(6, 5, struct.pack("<I", 0xDEADBEEF))
-        entries.append((name.encode(), e))
-        data += a.tobytes()
-    blocks = bytearray()
-    d = _table_block(entries)
-    d_handle = _vi(0) + _vi(len(d)); blocks += d + bytes([compressed_tag]) + b"\0\0\0\0"
-    m = _table_block([]); m_handle = _vi(len(blocks)) + _vi(len(m)); blocks += m + b"\0" + b"\0\0\0\0"
-    i = _table_block([(b"~", d_handle)]); i_handle = _vi(len(blocks)) + _vi(len(i)); blocks += i + b"\0" + b"\0\0\0\0"
-    foot = m_handle + i_handle
-    foot += b"\0" * (40 - len(foot)) + struct.pack("<Q", tfc.TABLE_MAGIC)
-    with open(prefix + ".index", "wb") as f:
-        f.write(bytes(blocks) + foot)
-    with open(prefix + ".data-00000-of-00001", "wb") as f:
-        f.write(bytes(data))
+    """The package's writer; ``compressed_tag`` overwrites the data block's compression byte to exercise the reader."""
+    tfc.write_checkpoint(prefix, tensors)
+    if compressed_tag:
+        raw = bytearray(open(prefix + ".index", "rb").read())
+        foot = raw[-48:]
+        _, p = tfc._varint(foot, 0); _, p = tfc._varint(foot, p)          # metaindex handle
+        ioff, p = tfc._varint(foot, p); isz, p = tfc._varint(foot, p)      # index handle
+        (_, handle), = tfc._block(bytes(raw), ioff, isz)                   # one data block: (offset, size)
+        off, q = tfc._varint(handle, 0); sz, q = tfc._varint(handle, q)
+        raw[off + sz] = compressed_tag                                      # the block's type byte
+        open(prefix + ".index", "wb").write(bytes(raw))
 
 
 def small_policy(rng, scope="pi", obs=5, hid=7, act=3):
@@ -148,6 +104,30 @@ def test_reference_checkpoint_reads_to_the_committed_golden():
     assert abs(float(np.sum(a["logstd"] + 0.5 * np.log(2 * np.pi * np.e))) - 35.71932) < 2e-5
 
 
+@pytest.mark.skipif(not os.path.exists(REF_CKPT + ".index"), reason="reference checkout not present (GPU box)")
+def test_writer_regenerates_the_reference_checkpoint_byte_for_byte(tmp_path):
+    r = tfc.read_checkpoint(REF_CKPT)
+    q = str(tmp_path / "trpo-walk-0")
+    tfc.write_checkpoint(q, r)
+    tfc.write_checkpoint_state(q)
+    for ext in (".index", ".data-00000-of-00001"):
+        assert open(q + ext, "rb").read() == open(REF_CKPT + ext, "rb").read(), ext
+    assert open(str(tmp_path / "checkpoint")).read() == open(os.path.join(os.path.dirname(REF_CKPT), "checkpoint")).read()
+    # and through the policy-level mapping: arrays -> scopes "pi" (the golden's) + "oldpi" -> same names and shapes
+    a = tfc.policy_arrays(r, "pi")
+    t = {**tfc.policy_tensors(a, "pi"), **tfc.policy_tensors(a, "oldpi")}
+    assert sorted(t) == sorted(r)
+    for k in r:
+        assert t[k].shape == r[k].shape and t[k].dtype == r[k].dtype, k
+        if k.startswith("pi/"):
+            assert np.array_equal(t[k], r[k]), k
+
+
+def test_crc32c_known_answers():
+    assert tfc.crc32c(b"123456789") == 0xE3069283                         # the CRC-32C check value
+    assert tfc.crc32c(b"") == 0 and tfc.crc32c(bytes(32)) == 0x8A9136AA   # RFC 3720 B.4: 32 bytes of zeros
+
+
 def test_policy_load_arrays_on_host_tensors():
     """MlpPolicy.load_arrays / RunningMeanStd.load (the device copy is plain tensor.copy_): exercised on CPU tensors by
     building the object without its CUDA-only constructor; the network evaluated from the loaded tensors must be the
@@ -170,3 +150,13 @@ def test_policy_load_arrays_on_host_tensors():
     bad = dict(a); bad["pw2"] = np.zeros((100, 99), np.float32)
     with pytest.raises(ValueError, match="pw2"):
         pol.load_arrays(bad)
+    h = pol.host_arrays()                                                  # and back out: save -> read -> same arrays
+    import tempfile
+    q = os.path.join(tempfile.mkdtemp(), "saved")
+    pol.save_tf_checkpoint(q)
+    back = tfc.read_checkpoint(q)
+    assert sorted(back) == sorted({**tfc.policy_tensors(h, "pi"), **tfc.policy_tensors(h, "oldpi")})
+    for sc in ("pi", "oldpi"):
+        b = tfc.policy_arrays(back, sc)
+        for k in a:
+            assert np.array_equal(np.asarray(b[k]), np.asarray(a[k])), (sc, k)

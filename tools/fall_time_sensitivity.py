@@ -60,6 +60,20 @@ def variant(**kw):
     return m
 
 
+def without_own_narrow_phase_pairs():
+    """The model with the 15 candidate pairs removed whose narrow phase is this repo's own routine (capsule-box,
+    box-box: DESIGN.md section 2 deviation 1) -- if a statistic does not move, it cannot depend on how those
+    routines differ from MuJoCo's."""
+    m = copy.deepcopy(common.model())
+    own = lambda a, b: m.geom_type[a] == 6 and m.geom_type[b] in (3, 6)
+    keep = [(m.pair_geom1[i], m.pair_geom2[i]) for i in range(m.npair)
+            if not (own(m.pair_geom1[i], m.pair_geom2[i]) or own(m.pair_geom2[i], m.pair_geom1[i]))]
+    for i, (a, b) in enumerate(keep):
+        m.pair_geom1[i], m.pair_geom2[i] = a, b
+    m.npair = len(keep)
+    return m
+
+
 CASES = [
     ("gravity x 0.8", dict(gravity=lambda v, i, j: 0.8 * v)),
     ("gravity x 1.25", dict(gravity=lambda v, i, j: 1.25 * v)),
@@ -83,6 +97,7 @@ def main():
     print(f"{'as shipped, another seed':34s}", verdict(run(common.model(), seed=11)))
     for name, kw in CASES:
         print(f"{name:34s}", verdict(run(variant(**kw))))
+    print(f"{'no capsule-box / box-box pairs':34s}", verdict(run(without_own_narrow_phase_pairs())))
     print(f"{'termination height 0.6':34s}", verdict(run(common.model(), z_min=0.6)))
     print(f"{'termination height 0.8':34s}", verdict(run(common.model(), z_min=0.8)))
     print(f"{'action sd 0.25 (not the init policy)':34s}", verdict(run(common.model(), act_sd=0.25)))

@@ -21,6 +21,9 @@ ap.add_argument("--reward-mode", type=int, default=4); ap.add_argument("--seed",
 ap.add_argument("--vf-batch", type=int, default=4096)
 ap.add_argument("--pretrained_weight_path", default=None,
                 help="TensorFlow checkpoint saved by the reference (trpo.py:207-208, 516); read without TensorFlow")
+ap.add_argument("--checkpoint_dir", default=None, help="save the policy there in the reference's TensorFlow checkpoint "
+                "format every --save_per_iter iterations (trpo.py:220-224, 494, 514) -- loadable by the reference")
+ap.add_argument("--save_per_iter", type=int, default=100)
 a = ap.parse_args()
 world, rank, lrank = int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(lrank)
@@ -36,6 +39,9 @@ t0, steps = time.time(), 0
 for it in range(a.iters):
     seg = next(gen)
     add_vtarg_and_adv(seg, learner.gamma, learner.lam)
+    if rank == 0 and a.checkpoint_dir and it % a.save_per_iter == 0:
+        os.makedirs(a.checkpoint_dir, exist_ok=True)
+        pi.save_tf_checkpoint(os.path.join(a.checkpoint_dir, f"trpo-{a.motion}-{a.seed}"))
     st = learner.update(seg)
     steps += a.envs * a.horizon * world
     if rank == 0:

@@ -48,7 +48,7 @@ def verdict(lens):
 
 
 if __name__ == "__main__":
-    from fall_time_sensitivity import CASES, variant
+    from fall_time_sensitivity import CASES, variant, without_own_narrow_phase_pairs
     MILD = [                                  # perturbations the random-policy pin (section 2 (ix)) cannot resolve
         ("gravity x 0.9", dict(gravity=lambda v, i, j: 0.9 * v)),
         ("gravity x 1.1", dict(gravity=lambda v, i, j: 1.1 * v)),
@@ -70,6 +70,7 @@ if __name__ == "__main__":
     print(f"{'as shipped, another seed':34s}", verdict(run(common.model(), seed=11)))
     for name, kw in CASES + MILD:
         print(f"{name:34s}", verdict(run(variant(**kw))), flush=True)
+    print(f"{'no capsule-box / box-box pairs':34s}", verdict(run(without_own_narrow_phase_pairs())))
     print(f"{'termination height 0.6':34s}", verdict(run(common.model(), z_min=0.6)))
     print(f"{'termination height 0.8':34s}", verdict(run(common.model(), z_min=0.8)))
     print(f"{'deterministic policy (mode)':34s}", verdict(run(common.model(), stochastic=False)))
