@@ -11,11 +11,17 @@
  * restates MuJoCo's published computation pipeline (mj_step with RK4 + PGS, as
  * documented for the open-sourced >=2.1 engine) for the MJCF subset of dp_env_v3.xml,
  * plus the env logic of dp_env_v3.py.  Deviations are listed in DESIGN.md.
- * The only MuJoCo-PRODUCED data in the reference is the episode monitor of its training run
- * (src/log_tmp/DeepMimic/trpo-walk-0/monitor.json.monitor.csv); the oracle reproduces its
- * time-to-fall distribution under the same protocol (tests/test_oracle_physics.py,
- * tests/golden/ref_episode_lengths.json) -- a statistical pin of the whole pipeline, not a
- * state-level one, so the status above stands.
+ * The only MuJoCo-PRODUCED data in the reference are the episode monitor of its training run
+ * (src/log_tmp/DeepMimic/trpo-walk-0/monitor.json.monitor.csv) and the policy that run trained
+ * (src/checkpoint_tmp/DeepMimic/trpo-walk-0, a TensorFlow checkpoint).  The oracle reproduces
+ * (a) the time-to-fall distribution of the initial random policy (tests/golden/ref_episode_lengths.json)
+ * and (b) the ~290-step survival of the trained policy replayed from the checkpoint
+ * (tests/golden/ref_trained_policy.npz; oracle / MuJoCo = 0.94 +- 0.03), also when driven by the
+ * reference's own rollout loop, env class and monitor (tools/reference_protocol_replay.py) --
+ * tests/test_oracle_physics.py, tests/test_reference_protocol_replay.py.  These are statistical
+ * pins of the whole pipeline, not state-level ones, so the status above stands.  The ENV LOGIC
+ * (dmo_env_*) is pinned state for state against the reference class dp_env_v3.DPEnv run over an
+ * adapter (tests/test_env_logic_golden.py).
  */
 #ifndef DM_ORACLE_H_
 #define DM_ORACLE_H_
