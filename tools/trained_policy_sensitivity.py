@@ -63,12 +63,24 @@ if __name__ == "__main__":
         ("timestep x 0.8", dict(timestep=lambda v, i, j: 0.8 * v)),
         ("timestep x 1.25", dict(timestep=lambda v, i, j: 1.25 * v)),
     ]
+    INTERNALS = [                             # parameters of the restated constraint model / solver (no MJCF attribute)
+        ("PGS iterations 20", dict(iterations=lambda v, i, j: 20)),
+        ("PGS iterations 200", dict(iterations=lambda v, i, j: 200)),
+        ("PGS tolerance 0 (never exits early)", dict(tolerance=lambda v, i, j: 0.0)),
+        ("invweight0 x 0.5 (stiffer rows)", dict(body_invweight0=lambda v, i, j: 0.5 * v, dof_invweight0=lambda v, i, j: 0.5 * v)),
+        ("invweight0 x 2 (softer rows)", dict(body_invweight0=lambda v, i, j: 2 * v, dof_invweight0=lambda v, i, j: 2 * v)),
+        ("solimp dmin/dmax 0.99", dict(solimp=lambda v, i, j: 0.99 if i < 2 else v)),
+        ("solimp dmin/dmax 0.8", dict(solimp=lambda v, i, j: 0.8 if i < 2 else v)),
+        ("solref timeconst 0.1", dict(solref=lambda v, i, j: 0.1 if i == 0 else v)),
+        ("contact margin 0.01", dict(margin=lambda v, i, j: 0.01)),
+        ("contact margin 0", dict(margin=lambda v, i, j: 0.0)),
+    ]
     print(f"reference monitor, {len(ref)} episodes around the checkpoint: mean {ref.mean():.1f} sd {ref.std():.1f} "
           f"quartiles {np.percentile(ref, [25, 50, 75])}")
     print(f"{EPISODES} oracle episodes per variant")
     print(f"{'as shipped':34s}", verdict(run(common.model())))
     print(f"{'as shipped, another seed':34s}", verdict(run(common.model(), seed=11)))
-    for name, kw in CASES + MILD:
+    for name, kw in CASES + MILD + INTERNALS:
         print(f"{name:34s}", verdict(run(variant(**kw))), flush=True)
     print(f"{'no capsule-box / box-box pairs':34s}", verdict(run(without_own_narrow_phase_pairs())))
     print(f"{'termination height 0.6':34s}", verdict(run(common.model(), z_min=0.6)))
