@@ -135,6 +135,9 @@ def main():
             t = lambda k: torch.as_tensor(np.concatenate([np.asarray(sg[k]) for sg in segs]), dtype=torch.float32).unsqueeze(1)
             st = learner.update({k: t(k) for k in ("ob", "ac", "adv", "tdlamret", "vpred")})
             pi.refresh()
+            if os.environ.get("DMB_REPLAY_UPDATES"):                        # one line per TRPO update (tests)
+                print(f"update expected {st.get('expectedimprove', float('nan')):.4f} actual {st['surrgain']:.4f} "
+                      f"meankl {st['meankl']:.6f} stepsize {st['stepsize']:.3f}", flush=True)
         for seg in segs:
             lenbuf.extend(seg["ep_lens"])                                   # trpo.py:300-304: every worker's last segment
         if it % (10 if start_iter else 50) == 0 or it == iters - 1:
