@@ -82,6 +82,29 @@ def cut(path, name, ns):
     return ns[name]
 
 
+def obfilter_report(pi, iters):
+    """The observation filter is a by-product that MuJoCo shaped too: the reference's checkpoint holds the sum / sum of
+    squares of every observation its two workers fed the filter during 1900 iterations -- per-joint mean angle, angle
+    spread and joint-velocity spread of the whole training run.  Print this run's next to it."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_trained_policy.npz"))
+    cnt = g["pi/obfilter/count"]
+    mr = g["pi/obfilter/runningsum"] / cnt
+    sr = np.sqrt(np.maximum(g["pi/obfilter/runningsumsq"] / cnt - mr * mr, 0))
+    c = pi.ob_rms.count.numpy()
+    m = pi.ob_rms.sum.numpy() / c
+    sd = np.sqrt(np.maximum(pi.ob_rms.sumsq.numpy() / c - m * m, 0))
+    import common
+    names = common.tables().joint_names[1:]
+    print(f"observation filter after {iters} iterations (count {float(c):.0f}) | the reference's checkpoint, 1900 iterations "
+          f"(count {float(cnt):.0f})")
+    print(f"{'joint':18s} {'mean angle':>17s} {'sd angle':>15s} {'sd velocity':>15s}   (this run | reference)")
+    for j in range(28):
+        print(f"{names[j]:18s} {m[j]:+8.3f} |{mr[j]:+7.3f} {sd[j]:7.3f} |{sr[j]:6.3f} {sd[28 + j]:7.3f} |{sr[28 + j]:6.3f}")
+    ra, rv = sd[:28] / sr[:28], sd[28:] / sr[28:]
+    print(f"ratio this run / reference over the 28 joints: sd angle median {np.median(ra):.2f} ({ra.min():.2f} .. {ra.max():.2f}), "
+          f"sd velocity median {np.median(rv):.2f} ({rv.min():.2f} .. {rv.max():.2f})")
+
+
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 1942
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
@@ -145,6 +168,13 @@ def main():
             print(f"{it:5d} {steps:10d} | {np.mean(lenbuf) if lenbuf else float('nan'):9.1f} {st['entropy']:8.3f} "
                   f"{st['meankl']:8.5f} {st.get('ev_tdlam_before', float('nan')):8.3f} | {float(r['EpLenMean']):9.1f} "
                   f"{float(r['entropy']):8.3f} {float(r['meankl']):8.5f} {float(r['ev_tdlam_before']):8.3f}", flush=True)
+    if os.environ.get("DMB_REPLAY_SAVE"):                                   # the trained policy, in the reference's format
+        from deepmimic_mujoco_b200.tf_checkpoint import policy_tensors, write_checkpoint
+        arrays = {k: v.detach().numpy() for k, v in pi.params.items()}
+        arrays.update(ob_sum=pi.ob_rms.sum.numpy(), ob_sumsq=pi.ob_rms.sumsq.numpy(), ob_count=pi.ob_rms.count.numpy())
+        write_checkpoint(os.environ["DMB_REPLAY_SAVE"], {**policy_tensors(arrays, "pi"), **policy_tensors(arrays, "oldpi")})
+    if not start_iter:
+        obfilter_report(pi, iters)
     lens = np.asarray(env.get_episode_lengths(), dtype=np.float64)
     env.close()
     print(f"{len(lens)} episodes, {int(lens.sum())} env steps in {time.time() - t0:.0f} s; mean length of the last 200 episodes "
