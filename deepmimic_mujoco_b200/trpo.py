@@ -158,7 +158,7 @@ class TRPO:
         ac = seg["ac"].detach().reshape(-1, seg["ac"].shape[-1])
         atarg = seg["adv"].detach().reshape(-1)
         tdlamret = seg["tdlamret"].detach().reshape(-1)
-        atarg = (atarg - atarg.mean()) / atarg.std()                      # trpo.py:240
+        atarg = (atarg - atarg.mean()) / atarg.std(unbiased=False)        # trpo.py:240 (numpy std: population)
         self.pi.ob_rms.update(ob, group=self.group)                       # trpo.py:242
         pol = [P[k] for k in POL_KEYS]
         with torch.no_grad():                                             # assign_old_eq_new (trpo.py:247)
