@@ -7,7 +7,9 @@ SURVEY 8(f) rows rebuilt in rollout.py / trpo.py are checked against these inste
   and cannot be imported, so the function's own source lines are cut out of the file with ``ast`` and executed
   unchanged in a namespace that holds only numpy;
 * ``explained_variance`` -- /root/reference/src/utils/math_util.py:25-38, cut out the same way (its module imports scipy
-  only, but lives in a package whose __init__ pulls TensorFlow).
+  only, but lives in a package whose __init__ pulls TensorFlow);
+* ``MpiAdam.update`` -- /root/reference/src/mpi_adam.py:21-35, the method's source lines bound to a stub object (one-process
+  communicator, flat get / set closures): seven steps on seeded gradients.
 Run in the build container only."""
 import ast
 import os
@@ -57,6 +59,40 @@ def main():
     # explained variance
     y = rng.normal(size=200); yp = 0.7 * y + 0.3 * rng.normal(size=200)
     out.update(ev_y=y, ev_ypred=yp, ev=np.float64(ev(yp, y)), ev_const=np.float64(ev(yp, np.ones(200))))
+    # MpiAdam.update (mpi_adam.py:21-35): the method's own source lines, bound to a stub that supplies the three things it
+    # touches outside numpy -- a one-process communicator and the flat get / set closures of the variable list
+    src = open(os.path.join(REF_SRC, "mpi_adam.py")).read()
+    cls = next(n for n in ast.parse(src).body if isinstance(n, ast.ClassDef) and n.name == "MpiAdam")
+    upd = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "update")
+    import types
+    ns = {"np": np, "MPI": types.SimpleNamespace(SUM="sum")}             # the one mpi4py name the method mentions
+    exec(compile(ast.Module(body=[upd], type_ignores=[]), "mpi_adam.py", "exec"), ns)
+
+    class Comm:
+        def Allreduce(self, a, b, op=None):
+            b[:] = a
+
+        def Get_size(self):
+            return 1
+
+    class Stub:
+        beta1, beta2, epsilon, scale_grad_by_procs, t = 0.9, 0.999, 1e-08, True, 0
+
+        def __init__(self, theta):
+            self.theta = theta.astype("float32")
+            self.m = np.zeros(theta.size, "float32"); self.v = np.zeros(theta.size, "float32"); self.comm = Comm()
+            self.getflat = lambda: self.theta
+            self.setfromflat = lambda x: setattr(self, "theta", np.asarray(x, "float32"))
+
+        def check_synced(self):
+            pass
+    theta0 = rng.normal(size=40).astype("float32")
+    grads = rng.normal(size=(7, 40)).astype("float32") * np.array([1, 1e-3, 10, 1, 0, 1, 1], "float32")[:, None]
+    st, traj = Stub(theta0), []
+    for gk in grads:
+        ns["update"](st, gk, 1e-3)
+        traj.append(st.theta.copy())
+    out.update(adam_theta0=theta0, adam_grads=grads, adam_traj=np.asarray(traj))
     np.savez_compressed(os.path.join(HERE, "learner_golden.npz"), **out)
     print("gae adv[0]", adv[0], "\ncg residual 10 / 100 iters", np.linalg.norm(A @ out["cg_x10"] - b),
           np.linalg.norm(A @ out["cg_x100"] - b), "\nev", out["ev"], out["ev_const"])

@@ -47,6 +47,18 @@ def test_cg_and_explained_variance_match_the_reference_routines_run_here():
     assert math.isnan(float(g["ev_const"]))
 
 
+def test_adam_matches_the_reference_mpi_adam_update_run_here():
+    """Golden parameter trajectory produced by the reference's own MpiAdam.update (mpi_adam.py:21-35, source lines
+    executed on a stub with a one-process communicator): tests/golden/make_learner_golden.py."""
+    g = np.load(os.path.join(common.GOLDEN, "learner_golden.npz"))
+    params = {"w": torch.tensor(g["adam_theta0"][:25].copy()), "b": torch.tensor(g["adam_theta0"][25:].copy())}
+    opt = T.Adam(params, ["w", "b"])
+    for k, gk in enumerate(g["adam_grads"]):
+        opt.update(torch.tensor(gk), 1e-3)
+        th = torch.cat([params["w"], params["b"]]).numpy()
+        assert np.abs(th - g["adam_traj"][k]).max() < 2e-7, k
+
+
 def test_diag_gaussian_formulas():
     rng = np.random.default_rng(1)
     m0, m1 = torch.tensor(rng.normal(size=(4, 3))), torch.tensor(rng.normal(size=(4, 3)))
