@@ -42,7 +42,7 @@ class RunningMeanStd:
 
     def load(self, total, sumsq, count):
         """Overwrite the accumulators (e.g. with ``obfilter/runningsum|runningsumsq|count`` of a reference checkpoint)."""
-        as64 = lambda a: torch.as_tensor(np.asarray(a, dtype=np.float64), device=self.sum.device)
+        as64 = lambda a: torch.as_tensor(np.array(a, dtype=np.float64), device=self.sum.device)
         self.sum.copy_(as64(total)); self.sumsq.copy_(as64(sumsq)); self.count.copy_(as64(count))
         self._refresh()
 
@@ -93,7 +93,7 @@ class MlpPolicy:
         """Overwrite parameters and the observation filter from host arrays named as in ``self.params`` plus
         ``ob_sum`` / ``ob_sumsq`` / ``ob_count`` (tf_checkpoint.policy_arrays); shapes must match this policy."""
         for k, t in self.params.items():
-            a = torch.as_tensor(np.asarray(arrays[k], dtype=np.float32))
+            a = torch.as_tensor(np.array(arrays[k], dtype=np.float32))      # a copy: checkpoint arrays are read-only views
             if tuple(a.shape) != tuple(t.shape):
                 raise ValueError(f"{k}: checkpoint shape {tuple(a.shape)} != policy shape {tuple(t.shape)}")
             t.copy_(a)                                           # in place: pointers held by a learner stay valid

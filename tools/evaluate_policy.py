@@ -8,7 +8,8 @@ kernel; every env plays one trajectory from reset_model_init (rollout.evaluate =
 traj_1_generator, horizon 1024 as in trpo.py:484) and the two numbers the reference prints are printed.  Without
 --load_model_path the policy the reference ships (its 1.0 M-step walk run, tests/golden/ref_trained_policy.npz) is
 used; the reference's monitor recorded ~290 steps per episode for it in MuJoCo with the stochastic policy.
-NOT YET RUN ON HARDWARE (written after this round's GPU minutes were spent); its pieces are covered by
+NOT YET RUN ON HARDWARE (written after this round's GPU minutes were spent; dry-run on the CPU with the stand-ins of
+tools/dry_run_gpu_reference_tests.py: stochastic 285 steps, deterministic cut at horizon + 1); its pieces are covered by
 tests/test_tf_checkpoint.py, tests/test_policy_rollout.py (CPU) and the GPU tests of MlpPolicy.act / DPVecEnv.step."""
 import argparse
 import os
